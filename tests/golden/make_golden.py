@@ -195,7 +195,7 @@ def main():
         worst = max(worst, close(rmpc.uPred, ompc.uPred, 1e-9, "lti uPred"))
         if t in (0, 7):
             for a, nm in zip(rq, "PqAlu"):
-                gold["lti_t%d_%s" % (t, nm)] = a
+                gold["lti_t%d_qp_%s" % (t, nm)] = a
             gold["lti_t%d_x0" % t], gold["lti_t%d_old" % t] = xs[-1], np.zeros(2) if t == 0 else prev_u
             gold["lti_t%d_xPred" % t], gold["lti_t%d_uPred" % t] = rmpc.xPred, rmpc.uPred
         prev_u = rmpc.uPred[0].copy()
@@ -228,7 +228,7 @@ def main():
             gold[k + "xLin"], gold[k + "uLin"], gold[k + "old"], gold[k + "x0"] = pre["xLin"], pre["uLin"], pre["old"], xs[-1]
             gold[k + "A"], gold[k + "B"], gold[k + "C"] = np.array(rltv.A), np.array(rltv.B), np.array(rltv.C)
             for a, nm in zip(qp_of(rltv, xs[-1]), "PqAlu"):
-                gold[k + nm] = a
+                gold[k + "qp_" + nm] = a
             gold[k + "xPred"], gold[k + "uPred"] = rltv.xPred, rltv.uPred
         xt, gt = vehicle.dyn_model(omap, xs[-1], gs[-1], rltv.uPred[0])
         xs.append(xt)
@@ -296,7 +296,7 @@ def main():
             if key in snaps:
                 k = "lmpc_%d_%d_" % key
                 for a, nm in zip(rq, "PqAlu"):
-                    gold[k + nm] = a
+                    gold[k + "qp_" + nm] = a
                 gold[k + "A"], gold[k + "B"], gold[k + "C"] = np.array(rl.A), np.array(rl.B), np.array(rl.C)
                 gold[k + "SS_sel"], gold[k + "Qfun_sel"] = rl.SS_PointSelectedTot, rl.Qfun_SelectedTot
                 gold[k + "Succ_SS"], gold[k + "Succ_uSS"] = rl.Succ_SS_PointSelectedTot, rl.Succ_uSS_PointSelectedTot
