@@ -55,7 +55,7 @@ def from_params(p, A, B, C, x0, uOld, SS=None, Qfun=None, Qts=None):
                    p.Fu, np.squeeze(p.bu), A, B, C, x0, np.asarray(uOld, float).ravel(), SS, Qfun, Qts)
 
 
-def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None):
+def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0=0.3, gamma=0.0):
     """Returns dict(x[N+1,n], u[N,d], s[N,ncx], lam[m], xi[n], iters, r_prim, r_dual, gap, status)."""
     N, n, d = qp.N, 6, 2
     Fx, bx, Fu, bu = qp.Fx, qp.bx, qp.Fu, qp.bu
@@ -84,18 +84,26 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None):
     w1 = np.zeros((N, ncx))
     for k in range(N):
         viol = Fx @ x[k] - bx
-        s[k] = np.maximum(viol, 0.0) + 0.1
+        s[k] = np.maximum(viol, 0.0) + s0
         w1[k] = bx - Fx @ x[k] + s[k]
     w2 = np.array([bu - Fu @ u[k] for k in range(N)])
-    nu1 = np.ones((N, ncx))
-    nu2 = np.ones((N, ncu))
-    nu3 = np.ones((N, ncx))
+    if mu0 is None:
+        nu1, nu2, nu3 = np.ones((N, ncx)), np.ones((N, ncu)), np.ones((N, ncx))
+    elif mu0 == "auto":
+        # slack-stationarity holds exactly (nu1 + nu3 = 2 qs s + ql) with w1 nu1 = s nu3 = mu_row;
+        # every other family is centred at the mean of those products
+        mur = (2 * qp.qs_quad * s + qp.qs_lin) * (w1 * s) / (w1 + s)
+        nu1, nu3 = mur / w1, mur / s
+        mu0 = max(float(np.mean(mur)), 1e-3)
+        nu2 = mu0 / w2
+    else:                                   # centred start: every complementarity product = mu0
+        nu1, nu2, nu3 = mu0 / w1, mu0 / w2, mu0 / s
     if lmpc:
         lam = np.ones(m) / m
         xi = SS @ lam - x[N]
         yT = -T @ xi
         red = Qfun - SS.T @ yT
-        y1 = -np.min(red) + 1.0
+        y1 = -np.min(red) + (1.0 if mu0 is None else mu0 * m)
         nu4 = red + y1
     n_ineq = N * (2 * ncx + ncu) + m
 
@@ -266,6 +274,19 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None):
                        s * nu3 + aff["ds"] * aff["dnu3"] - sm,
                        (lam * nu4 + aff["dlam"] * aff["dnu4"] - sm) if lmpc else None)
         al = min(1.0, 0.995 * max_step(cc))
+        if gamma > 0.0:
+            # stay in a wide neighbourhood of the central path: min_i w_i nu_i >= gamma * mu
+            def prods(a):
+                pr = [((w1 + a * cc["dw1"]) * (nu1 + a * cc["dnu1"])).ravel(), ((w2 + a * cc["dw2"]) * (nu2 + a * cc["dnu2"])).ravel(),
+                      ((s + a * cc["ds"]) * (nu3 + a * cc["dnu3"])).ravel()]
+                if lmpc:
+                    pr.append((lam + a * cc["dlam"]) * (nu4 + a * cc["dnu4"]))
+                return np.concatenate(pr)
+            for _ in range(12):
+                pr = prods(al)
+                if pr.min() >= gamma * pr.mean():
+                    break
+                al *= 0.8
         if DEBUG_HOOK:
             # residual of the u-rows and lambda-rows of the Newton system for the corrector step
             dx_, du_ = cc["dx"], cc["du"]
@@ -285,7 +306,8 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None):
                 if k > 0: e -= dR2 * du_[k - 1]
                 if k < N - 1: e -= dR2 * du_[k + 1]
                 worst_u = max(worst_u, np.abs(e).max())
-            msg = "   newton-resid u %.2e" % worst_u
+            prods = np.concatenate([(w1 * nu1).ravel(), (w2 * nu2).ravel(), (s * nu3).ravel()] + ([lam * nu4] if lmpc else []))
+            msg = "   newton-resid u %.2e  a_aff %.3f sigma %.2e alpha %.4f  min(prod)/mu %.2e max %.2e" % (worst_u, a_aff, sigma, al, prods.min() / mu, prods.max() / mu)
             if lmpc:
                 rc4 = lam * nu4 + aff["dlam"] * aff["dnu4"] - sm
                 e_l = (nu4 / lam) * cc["dlam"] - SS.T @ cc["dyT"] + cc["dy1"] - (-rlam - rc4 / lam)

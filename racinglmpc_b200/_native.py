@@ -1,0 +1,119 @@
+"""ctypes binding of liblmpc_b200.so (C ABI: include/lmpc_b200.h).
+
+There is NO fallback: if the library is missing or no B200-class device is present, importing the
+controllers works but constructing one raises (the product path never routes through the CPU oracle).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblmpc_b200.so")
+
+MAX_NCX, MAX_NCU, MAX_SEG = 4, 8, 16
+
+
+class Params(C.Structure):
+    _fields_ = [("N", C.c_int), ("ncx", C.c_int), ("ncu", C.c_int),
+                ("Q", C.c_double * 36), ("R", C.c_double * 4), ("Qf", C.c_double * 36),
+                ("dR", C.c_double * 2), ("Qslack", C.c_double * 2), ("xRef", C.c_double * 6),
+                ("Fx", C.c_double * (MAX_NCX * 6)), ("bx", C.c_double * MAX_NCX),
+                ("Fu", C.c_double * (MAX_NCU * 2)), ("bu", C.c_double * MAX_NCU),
+                ("numSS_Points", C.c_int), ("numSS_it", C.c_int), ("QterminalSlack", C.c_double * 36),
+                ("eps_res", C.c_double), ("eps_gap", C.c_double), ("max_iter", C.c_int)]
+
+
+class ModelParams(C.Structure):
+    _fields_ = [("trToUse", C.c_int), ("MaxNumPoint", C.c_int), ("h", C.c_double), ("lamb", C.c_double),
+                ("dt", C.c_double), ("scaling", C.c_double * 5), ("nseg", C.c_int),
+                ("seg", C.c_double * (MAX_SEG * 3)), ("TrackLength", C.c_double)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_LIB = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+
+def lib():
+    """Load the CUDA library; raise loudly when it is absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise NativeError("racinglmpc_b200: %s not found — run `python -c \"import __graft_entry__ as g; g.build()\"` "
+                          "(nvcc, sm_100a).  There is no CPU fallback." % _SO)
+    L = C.CDLL(_SO)
+    L.lmpc_last_error.restype = C.c_char_p
+    L.lmpc_device_count.restype = C.c_int
+    L.lmpc_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(_vp)]
+    L.lmpc_destroy.argtypes = [_vp]
+    L.lmpc_sync.argtypes = [_vp]
+    L.lmpc_stream.argtypes = [_vp]
+    L.lmpc_stream.restype = _vp
+    L.lmpc_kernel_launches.argtypes = [_vp]
+    L.lmpc_kernel_launches.restype = C.c_longlong
+    ll = C.c_longlong
+    for name in ("lmpc_solve_mpc_host", "lmpc_solve_mpc_dev"):
+        getattr(L, name).argtypes = [_vp, _vp, _vp, _vp, ll, ll, _vp, _vp, _vp, _vp, _vp, _vp]
+    for name in ("lmpc_solve_lmpc_host", "lmpc_solve_lmpc_dev"):
+        getattr(L, name).argtypes = [_vp, _vp, _vp, _vp, ll, ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError("liblmpc_b200 error %d: %s" % (rc, lib().lmpc_last_error().decode()))
+
+
+def exported_symbols():
+    """Names include/lmpc_b200.h declares; used by the CPU-tier test that the library exports them."""
+    hdr = os.path.join(_HERE, "..", "include", "lmpc_b200.h")
+    import re
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(lmpc_[a-z_0-9]+)\s*\(", txt)))
+
+
+def ptr(a):
+    """Host ndarray / int address / object with data_ptr() -> void*."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(_vp)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+def make_params(p, numSS_Points=0, numSS_it=0, QterminalSlack=None, eps_res=0.0, eps_gap=0.0, max_iter=0):
+    """p: object with the reference's MPCParams field names (PredictiveControllers.py:24-51)."""
+    if int(p.n) != 6 or int(p.d) != 2:
+        raise ValueError("racinglmpc_b200 supports n == 6, d == 2 (the reference's vehicle model)")
+    if not bool(p.slacks):
+        raise ValueError("racinglmpc_b200 implements the soft-lane formulation (slacks=True) the reference uses")
+    q = Params()
+    q.N = int(p.N)
+    Fx, Fu = np.asarray(p.Fx, float), np.asarray(p.Fu, float)
+    q.ncx, q.ncu = Fx.shape[0], Fu.shape[0]
+    if q.ncx > MAX_NCX or q.ncu > MAX_NCU:
+        raise ValueError("too many constraint rows")
+    q.Q[:] = np.asarray(p.Q, float).ravel()
+    q.R[:] = np.asarray(p.R, float).ravel()
+    q.Qf[:] = np.asarray(p.Qf, float).ravel()
+    q.dR[:] = np.asarray(p.dR, float).ravel()
+    q.Qslack[:] = np.asarray(p.Qslack, float).ravel()
+    q.xRef[:] = np.asarray(p.xRef, float).ravel()
+    fx = np.zeros(MAX_NCX * 6); fx[:Fx.size] = Fx.ravel()
+    fu = np.zeros(MAX_NCU * 2); fu[:Fu.size] = Fu.ravel()
+    bx = np.zeros(MAX_NCX); bx[:q.ncx] = np.asarray(p.bx, float).ravel()
+    bu = np.zeros(MAX_NCU); bu[:q.ncu] = np.asarray(p.bu, float).ravel()
+    q.Fx[:], q.Fu[:], q.bx[:], q.bu[:] = fx, fu, bx, bu
+    q.numSS_Points, q.numSS_it = int(numSS_Points), int(numSS_it)
+    q.QterminalSlack[:] = (np.asarray(QterminalSlack, float).ravel() if QterminalSlack is not None else np.zeros(36))
+    q.eps_res, q.eps_gap, q.max_iter = float(eps_res), float(eps_gap), int(max_iter)
+    return q
