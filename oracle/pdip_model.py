@@ -55,7 +55,7 @@ def from_params(p, A, B, C, x0, uOld, SS=None, Qfun=None, Qts=None):
                    p.Fu, np.squeeze(p.bu), A, B, C, x0, np.asarray(uOld, float).ravel(), SS, Qfun, Qts)
 
 
-def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0=0.3, gamma=0.0):
+def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0=0.3, gamma=0.01):
     """Returns dict(x[N+1,n], u[N,d], s[N,ncx], lam[m], xi[n], iters, r_prim, r_dual, gap, status)."""
     N, n, d = qp.N, 6, 2
     Fx, bx, Fu, bu = qp.Fx, qp.bx, qp.Fu, qp.bu
