@@ -114,6 +114,66 @@ int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, co
                         double* uPred, double* slack, double* lambd, double* slackTerminal, double* zt,
                         double* zt_u, int* status, int* iters, double* resid);
 
+/* ===== device-resident lap stores, k-NN regression, safe-set selection, fused controller step =========
+ *
+ * lmpc_store_create: allocates, per instance, `ss_cap` safe-set lap slots (x[T,6], u[T,2], Qfun[T]) and
+ * `model_cap` regression lap slots (x, u) of at most Tmax rows, plus the controller state
+ * (xLin, uLin, zt, OldInput, timeStep, previous xPred) that MPC/LMPC keep between solves (PC.py:88-93,129-137,330).
+ * Which slots are "the numSS_it fastest laps" (PC.py:395-402) and "usedIt" (PredictiveModel.py:31,35-46) is
+ * decided by the host shim at addTrajectory time (once per lap) and passed as small index arrays.
+ */
+int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, int model_cap, int Tmax);
+
+/* PredictiveModel.addTrajectory (PredictiveModel.py:35-46): copy one lap into a regression slot. */
+int lmpc_model_put_lap(lmpc_handle* h, int inst, int slot, int T, const double* x, const double* u);
+/* usedIt order: slots[B,trToUse]. */
+int lmpc_model_set_used(lmpc_handle* h, const int* slots);
+
+/* LMPC.addTrajectory (PC.py:418-445): copy one lap into a safe-set slot; qfun == NULL computes
+ * LMPC.computeCost (PC.py:447-464) on the device. */
+int lmpc_ss_put_lap(lmpc_handle* h, int inst, int slot, int T, const double* x, const double* u, const double* qfun);
+/* Selection for the coming lap: slots[B,numSS_it] in argsort(LapTime) order (PC.py:395,402); is_prev[B,numSS_it] = 1
+ * where that lap is iteration it-1 (PC.py:506-512); prev_slot[B] = slot receiving addPoint rows (-1: none). */
+int lmpc_ss_set_selection(lmpc_handle* h, const int* slots, const int* is_prev, const int* prev_slot);
+/* LMPC.addPoint (PC.py:466-476) for every instance: x[B,6], u[B,2] (host). */
+int lmpc_ss_add_point(lmpc_handle* h, const double* x, const double* u);
+/* Read a safe-set lap back (tests, plotting): x[Tmax,6], u[Tmax,2], qfun[Tmax] caller-allocated, *T rows valid. */
+int lmpc_ss_get_lap(lmpc_handle* h, int inst, int slot, int* T, double* x, double* u, double* qfun);
+/* Overwrite one stored state row (used to reproduce the aliased write of PC.py:394 on the very first solve). */
+int lmpc_ss_patch_row(lmpc_handle* h, int inst, int slot, int row, const double* x6, int also_model_slot);
+
+/* Controller state (host arrays; any pointer may be NULL = leave / skip):
+ * xLin[B,N+1,6], uLin[B,N,2] (PC.py:89-90,131-133,432-433), zt[B,6] (PC.py:330,383), OldInput[B,2] (PC.py:93,136),
+ * timeStep[B] (PC.py:107,137,445), has_pred[B] (`self.xPred == []`, PC.py:502), xPred[B,N+1,6]. */
+int lmpc_state_set(lmpc_handle* h, const double* xLin, const double* uLin, const double* zt, const double* OldInput,
+                   const int* timeStep, const int* has_pred, const double* xPred);
+int lmpc_state_get(lmpc_handle* h, double* xLin, double* uLin, double* zt, double* OldInput, int* timeStep);
+
+/* K1 alone — MPC.computeLTVdynamics (PC.py:140-145) from the stored xLin/uLin: abc_out[B,N,54] (may be NULL: result
+ * stays on the device for the next solve), flags[B] (0 ok; 1 singular regression, 2 curvature lookup failed,
+ * 4 single neighbour in a lap — cases where the reference raises). */
+int lmpc_identify_host(lmpc_handle* h, double* abc_out, int* flags);
+/* K2 alone — LMPC.addTerminalComponents (PC.py:386-416) for x0[B,6]: outputs as in lmpc_solve_lmpc_host plus
+ * min_index[B,numSS_it] (argmin row per lap) and flags[B] (8 = window past the stored lap). */
+int lmpc_select_host(lmpc_handle* h, const double* x0, double* SS_sel, double* Qfun_sel, double* Succ_SS,
+                     double* Succ_uSS, int* min_index, int* flags);
+
+/* One full controller step for the whole batch = MPC.solve / LMPC.solve (PC.py:110-137):
+ *   mode 0: LTV-MPC   K1 -> QP -> shift          (timeVarying MPC, main.py:91-94)
+ *   mode 1: LMPC      K1 -> K2 -> QP -> shift    (main.py:113-120)
+ * x0[B,6] host.  Outputs (host, any may be NULL): xPred[B,N+1,6], uPred[B,N,2], lambd[B,M], zt[B,6], zt_u[B,2],
+ * SS_sel[B,6,M] (for SSStoredPredTraj, PC.py:379), status[B], iters[B], resid[B,3], flags[B] (K1/K2 bits). */
+int lmpc_step_host(lmpc_handle* h, int mode, const double* x0, double* xPred, double* uPred, double* lambd, double* zt,
+                   double* zt_u, double* SS_sel, int* status, int* iters, double* resid, int* flags);
+/* Same with x0 already on the device; results stay in the handle's device buffers (lmpc_device_buffer). */
+int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev);
+/* Device address of an internal buffer by name: "xPred","uPred","lambd","zt","zt_u","abc","SS_sel","Qfun_sel",
+ * "Succ_SS","Succ_uSS","status","iters","resid","flags","xLin","uLin". */
+void* lmpc_device_buffer(lmpc_handle* h, const char* name);
+
+int lmpc_sizeof_params(void);
+int lmpc_sizeof_model_params(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,8 +62,47 @@ def lib():
         getattr(L, name).argtypes = [_vp, _vp, _vp, _vp, ll, ll, _vp, _vp, _vp, _vp, _vp, _vp]
     for name in ("lmpc_solve_lmpc_host", "lmpc_solve_lmpc_dev"):
         getattr(L, name).argtypes = [_vp, _vp, _vp, _vp, ll, ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    ip = C.POINTER(C.c_int)
+    L.lmpc_store_create.argtypes = [_vp, C.POINTER(ModelParams), C.c_int, C.c_int, C.c_int]
+    L.lmpc_model_put_lap.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.lmpc_model_set_used.argtypes = [_vp, _vp]
+    L.lmpc_ss_put_lap.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
+    L.lmpc_ss_set_selection.argtypes = [_vp, _vp, _vp, _vp]
+    L.lmpc_ss_add_point.argtypes = [_vp, _vp, _vp]
+    L.lmpc_ss_get_lap.argtypes = [_vp, C.c_int, C.c_int, ip, _vp, _vp, _vp]
+    L.lmpc_ss_patch_row.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int]
+    L.lmpc_state_set.argtypes = [_vp] + [_vp] * 7
+    L.lmpc_state_get.argtypes = [_vp] + [_vp] * 5
+    L.lmpc_identify_host.argtypes = [_vp, _vp, _vp]
+    L.lmpc_select_host.argtypes = [_vp] + [_vp] * 7
+    L.lmpc_step_host.argtypes = [_vp, C.c_int] + [_vp] * 11
+    L.lmpc_step_dev.argtypes = [_vp, C.c_int, _vp]
+    L.lmpc_device_buffer.argtypes = [_vp, C.c_char_p]
+    L.lmpc_device_buffer.restype = _vp
+    L.lmpc_sizeof_params.restype = C.c_int
+    L.lmpc_sizeof_model_params.restype = C.c_int
+    assert L.lmpc_sizeof_params() == C.sizeof(Params), "lmpc_params ABI mismatch"
+    assert L.lmpc_sizeof_model_params() == C.sizeof(ModelParams), "lmpc_model_params ABI mismatch"
     _LIB = L
     return L
+
+
+def make_model_params(seg_table, TrackLength, trToUse, MaxNumPoint=7, h=5.0, lamb=0.0, dt=0.1,
+                      scaling=(0.1, 1.0, 1.0, 1.0, 1.0)):
+    """PredictiveModel.__init__ constants (PredictiveModel.py:12-32) + the track's [s0, length, curvature] rows."""
+    m = ModelParams()
+    m.trToUse, m.MaxNumPoint = int(trToUse), int(MaxNumPoint)
+    m.h, m.lamb, m.dt = float(h), float(lamb), float(dt)
+    m.scaling[:] = list(scaling)
+    seg = np.asarray(seg_table, float).reshape(-1, 3)
+    if seg.shape[0] > MAX_SEG:
+        raise ValueError("track table has more than %d segments" % MAX_SEG)
+    m.nseg = seg.shape[0]
+    buf = np.zeros(MAX_SEG * 3)
+    buf[:seg.size] = seg.ravel()
+    m.seg[:] = buf
+    m.TrackLength = float(TrackLength)
+    return m
 
 
 def check(rc):

@@ -1,0 +1,237 @@
+"""Batched LTV-MPC / LMPC controllers: B independent reference controllers advanced in lock-step.
+
+State machine = src/fnc/controller/PredictiveControllers.py (MPC.solve :110-137, LMPC.addTrajectory :418-445,
+LMPC.addPoint :466-476, LMPC.addTerminalComponents :386-416) + PredictiveModel.addTrajectory
+(PredictiveModel.py:35-46).  Everything numeric runs on the GPU (csrc/safeset.cuh, csrc/ftocp_pdip.cuh);
+this file only does the once-per-lap bookkeeping that decides WHICH stored laps are "the numSS_it fastest"
+and "usedIt", exactly as the reference's Python lists do.
+"""
+import ctypes as C
+import numpy as np
+from . import _native as nat
+
+
+class _LapBook:
+    """Host-side index of one instance's laps in a device pool (slot ids, lengths, lap numbers)."""
+
+    def __init__(self, cap):
+        self.cap = cap
+        self.slot_of = {}          # lap number -> slot
+        self.free = list(range(cap))
+
+    def take(self, lap):
+        if not self.free:
+            raise RuntimeError("lap pool full")
+        s = self.free.pop(0)
+        self.slot_of[lap] = s
+        return s
+
+    def drop(self, lap):
+        self.free.append(self.slot_of.pop(lap))
+
+
+class BatchedController:
+    def __init__(self, params, batch, seg_table, TrackLength, trToUse=1, numSS_Points=0, numSS_it=0,
+                 QterminalSlack=None, device=0, Tmax=2048, ss_cap=None, model_cap=None,
+                 eps_res=0.0, eps_gap=0.0, max_iter=0, model_kwargs=None):
+        L = nat.lib()
+        self._lib = L
+        self.B, self.N, self.M = int(batch), int(params.N), int(numSS_Points)
+        self.numSS_it, self.trToUse = int(numSS_it), int(trToUse)
+        self.TrackLength = float(TrackLength)
+        self.lmpc = self.M > 0
+        self.ncx = np.asarray(params.Fx).shape[0]
+        self.Tmax = int(Tmax)
+        self._p = nat.make_params(params, numSS_Points, numSS_it, QterminalSlack, eps_res, eps_gap, max_iter)
+        h = C.c_void_p()
+        nat.check(L.lmpc_create(C.byref(self._p), self.B, int(device), C.byref(h)))
+        self._h = h
+        self.ss_cap = int(ss_cap) if ss_cap is not None else (self.numSS_it + 2 if self.lmpc else 0)
+        self.model_cap = int(model_cap) if model_cap is not None else self.trToUse + 1
+        self._mp = nat.make_model_params(seg_table, TrackLength, trToUse, **(model_kwargs or {}))
+        nat.check(L.lmpc_store_create(self._h, C.byref(self._mp), self.ss_cap, self.model_cap, self.Tmax))
+        # per-instance bookkeeping (PredictiveModel.lapTime / LMPC.LapTime lists)
+        self.model_laps = [[] for _ in range(self.B)]       # ordered (T, lapno) like xStored (ascending T)
+        self.model_book = [_LapBook(self.model_cap) for _ in range(self.B)]
+        self.model_count = [0] * self.B
+        self.LapTime = [[] for _ in range(self.B)]          # LMPC.LapTime
+        self.ss_book = [_LapBook(max(self.ss_cap, 1)) for _ in range(self.B)]
+        self.it = [0] * self.B
+        self._sel_dirty = True
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.lmpc_kernel_launches(self._h))
+
+    # ------------------------------------------------------------------ PredictiveModel.addTrajectory
+    def model_add_trajectory(self, inst, x, u):
+        """PredictiveModel.py:35-46: keep laps sorted by length; only the trToUse fastest are ever read."""
+        x = np.ascontiguousarray(x, float); u = np.ascontiguousarray(u, float)
+        T = x.shape[0]
+        laps = self.model_laps[inst]
+        lapno = self.model_count[inst]
+        self.model_count[inst] += 1
+        if not laps or T >= laps[-1][0]:
+            pos = len(laps)
+        else:
+            pos = next(i for i, (t, _) in enumerate(laps) if T < t)
+        laps.insert(pos, (T, lapno))
+        if pos < self.trToUse or len(laps) <= self.trToUse:
+            if len(self.model_book[inst].slot_of) >= self.model_cap:          # evict the slowest stored lap not in usedIt
+                stored = [ln for (_, ln) in laps if ln in self.model_book[inst].slot_of and ln != lapno]
+                keep = {ln for (_, ln) in laps[:self.trToUse]}
+                victims = [ln for ln in stored if ln not in keep]
+                self.model_book[inst].drop(victims[-1] if victims else stored[-1])
+            slot = self.model_book[inst].take(lapno)
+            nat.check(self._lib.lmpc_model_put_lap(self._h, inst, slot, T, nat.ptr(x), nat.ptr(u)))
+        self._push_used(inst)
+
+    def _push_used(self, inst=None):
+        used = np.zeros((self.B, self.trToUse), np.int32)
+        for b in range(self.B):
+            laps = self.model_laps[b]
+            for c in range(self.trToUse):
+                if c < len(laps) and laps[c][1] in self.model_book[b].slot_of:
+                    used[b, c] = self.model_book[b].slot_of[laps[c][1]]
+                elif laps:
+                    used[b, c] = self.model_book[b].slot_of.get(laps[min(c, len(laps) - 1)][1], 0)
+        nat.check(self._lib.lmpc_model_set_used(self._h, nat.ptr(used)))
+
+    # ------------------------------------------------------------------ LMPC.addTrajectory / addPoint
+    def add_trajectory(self, inst, x, u, qfun=None, lap_time=None):
+        """PC.py:418-445 for one instance (Qfun = computeCost on the device unless given).
+        ``qfun``/``lap_time`` exist so that a stored controller state (laps already grown by addPoint) can be
+        restored verbatim."""
+        x = np.ascontiguousarray(x, float); u = np.ascontiguousarray(u, float)
+        lapno = self.it[inst]
+        self.LapTime[inst].append(int(x.shape[0] if lap_time is None else lap_time))
+        book = self.ss_book[inst]
+        if not book.free:
+            order = list(np.argsort(np.array(self.LapTime[inst]), kind="stable"))
+            keep = set(order[:self.numSS_it]) | {lapno}
+            victims = [ln for ln in book.slot_of if ln not in keep]
+            if not victims:
+                raise RuntimeError("safe-set pool too small")
+            book.drop(max(victims, key=lambda ln: self.LapTime[inst][ln]))
+        slot = book.take(lapno)
+        q = None if qfun is None else np.ascontiguousarray(qfun, float)
+        nat.check(self._lib.lmpc_ss_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u), nat.ptr(q)))
+        first = (lapno == 0)
+        self.it[inst] += 1
+        self._sel_dirty = True
+        return first, slot
+
+    def _push_selection(self):
+        nit = max(self.numSS_it, 1)
+        sel = np.zeros((self.B, nit), np.int32); isp = np.zeros((self.B, nit), np.int32)
+        prev = -np.ones(self.B, np.int32)
+        for b in range(self.B):
+            if not self.LapTime[b]:
+                continue
+            order = np.argsort(np.array(self.LapTime[b]), kind="stable")[:nit]     # PC.py:395,402
+            for c, jj in enumerate(order):
+                sel[b, c] = self.ss_book[b].slot_of[int(jj)]
+                isp[b, c] = 0 if int(jj) < self.it[b] - 1 else 1                    # PC.py:506
+            prev[b] = self.ss_book[b].slot_of.get(self.it[b] - 1, -1)
+        nat.check(self._lib.lmpc_ss_set_selection(self._h, nat.ptr(sel), nat.ptr(isp), nat.ptr(prev)))
+        self._sel_dirty = False
+
+    def add_point(self, x, u):
+        """PC.py:466-476 for all instances: x[B,6], u[B,2]."""
+        if self._sel_dirty:
+            self._push_selection()
+        x = np.ascontiguousarray(np.asarray(x, float).reshape(self.B, 6))
+        u = np.ascontiguousarray(np.asarray(u, float).reshape(self.B, 2))
+        nat.check(self._lib.lmpc_ss_add_point(self._h, nat.ptr(x), nat.ptr(u)))
+
+    def get_lap(self, inst, lapno):
+        slot = self.ss_book[inst].slot_of[lapno]
+        T = C.c_int(0)
+        x, u, q = np.zeros((self.Tmax, 6)), np.zeros((self.Tmax, 2)), np.zeros(self.Tmax)
+        nat.check(self._lib.lmpc_ss_get_lap(self._h, inst, slot, C.byref(T), nat.ptr(x), nat.ptr(u), nat.ptr(q)))
+        return x[:T.value].copy(), u[:T.value].copy(), q[:T.value].copy()
+
+    def patch_row(self, inst, lapno, row, x6, model_lapno=None):
+        ms = -1 if model_lapno is None else self.model_book[inst].slot_of.get(model_lapno, -1)
+        x6 = np.ascontiguousarray(x6, float)
+        nat.check(self._lib.lmpc_ss_patch_row(self._h, inst, self.ss_book[inst].slot_of[lapno], int(row), nat.ptr(x6), ms))
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, xLin=None, uLin=None, zt=None, OldInput=None, timeStep=None, has_pred=None, xPred=None):
+        B, N = self.B, self.N
+        f = lambda a, shp: None if a is None else np.ascontiguousarray(np.asarray(a, float).reshape(shp))
+        g = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a).reshape(B), dtype=np.int32)
+        args = [f(xLin, (B, N + 1, 6)), f(uLin, (B, N, 2)), f(zt, (B, 6)), f(OldInput, (B, 2)), g(timeStep), g(has_pred),
+                f(xPred, (B, N + 1, 6))]
+        nat.check(self._lib.lmpc_state_set(self._h, *[nat.ptr(a) for a in args]))
+
+    def get_state(self):
+        B, N = self.B, self.N
+        o = dict(xLin=np.zeros((B, N + 1, 6)), uLin=np.zeros((B, N, 2)), zt=np.zeros((B, 6)), OldInput=np.zeros((B, 2)),
+                 timeStep=np.zeros(B, np.int32))
+        nat.check(self._lib.lmpc_state_get(self._h, nat.ptr(o["xLin"]), nat.ptr(o["uLin"]), nat.ptr(o["zt"]),
+                                           nat.ptr(o["OldInput"]), nat.ptr(o["timeStep"])))
+        return o
+
+    # ------------------------------------------------------------------ kernels
+    def identify(self):
+        """K1 only: MPC.computeLTVdynamics (PC.py:140-145).  Returns abc[B,N,54], flags[B]."""
+        abc = np.zeros((self.B, self.N, 54)); flags = np.zeros(self.B, np.int32)
+        nat.check(self._lib.lmpc_identify_host(self._h, nat.ptr(abc), nat.ptr(flags)))
+        return abc, flags
+
+    def select(self, x0):
+        """K2 only: LMPC.addTerminalComponents (PC.py:386-416)."""
+        if self._sel_dirty:
+            self._push_selection()
+        B, M = self.B, self.M
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(B, 6))
+        o = dict(SS_sel=np.zeros((B, 6, M)), Qfun_sel=np.zeros((B, M)), Succ_SS=np.zeros((B, 6, M)),
+                 Succ_uSS=np.zeros((B, 2, M)), min_index=np.zeros((B, self.numSS_it), np.int32), flags=np.zeros(B, np.int32))
+        nat.check(self._lib.lmpc_select_host(self._h, nat.ptr(x0), nat.ptr(o["SS_sel"]), nat.ptr(o["Qfun_sel"]),
+                                             nat.ptr(o["Succ_SS"]), nat.ptr(o["Succ_uSS"]), nat.ptr(o["min_index"]), nat.ptr(o["flags"])))
+        return o
+
+    def alloc_step_outputs(self):
+        B, N, M = self.B, self.N, max(self.M, 1)
+        return dict(xPred=np.zeros((B, N + 1, 6)), uPred=np.zeros((B, N, 2)), lambd=np.zeros((B, M)), zt=np.zeros((B, 6)),
+                    zt_u=np.zeros((B, 2)), SS_sel=np.zeros((B, 6, M)), status=np.zeros(B, np.int32),
+                    iters=np.zeros(B, np.int32), resid=np.zeros((B, 3)), flags=np.zeros(B, np.int32))
+
+    def step(self, x0, out=None, want_ss=True):
+        """One MPC.solve / LMPC.solve for every instance (PC.py:110-137)."""
+        if self.lmpc and self._sel_dirty:
+            self._push_selection()
+        x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(self.B, 6))
+        o = out if out is not None else self.alloc_step_outputs()
+        nat.check(self._lib.lmpc_step_host(self._h, 1 if self.lmpc else 0, nat.ptr(x0), nat.ptr(o["xPred"]), nat.ptr(o["uPred"]),
+                                           nat.ptr(o["lambd"]), nat.ptr(o["zt"]), nat.ptr(o["zt_u"]),
+                                           nat.ptr(o["SS_sel"]) if want_ss else None, nat.ptr(o["status"]), nat.ptr(o["iters"]),
+                                           nat.ptr(o["resid"]), nat.ptr(o["flags"])))
+        return o
+
+    def step_dev(self, x0_dev):
+        if self.lmpc and self._sel_dirty:
+            self._push_selection()
+        nat.check(self._lib.lmpc_step_dev(self._h, 1 if self.lmpc else 0, nat.ptr(x0_dev)))
+
+    def device_buffer(self, name):
+        return int(self._lib.lmpc_device_buffer(self._h, name.encode()) or 0)
+
+    def sync(self):
+        nat.check(self._lib.lmpc_sync(self._h))
+
+    @property
+    def stream(self):
+        return int(self._lib.lmpc_stream(self._h) or 0)

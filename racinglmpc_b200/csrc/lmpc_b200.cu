@@ -15,6 +15,7 @@
 
 #include "../../include/lmpc_b200.h"
 #include "ftocp_pdip.cuh"
+#include "safeset.cuh"
 
 using namespace lmpc;
 
@@ -175,6 +176,12 @@ struct lmpc_handle {
     double *d_x0, *d_uOld, *d_abc, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
     double *d_xPred, *d_uPred, *d_slack, *d_lambd, *d_slackT, *d_zt, *d_ztu, *d_resid;
     int *d_status, *d_iters;
+    // lap stores + controller state (lmpc_store_create)
+    bool has_store;
+    ModelConst mc;
+    LapPool ss, mdl;
+    int *d_used, *d_sel, *d_isprev, *d_prevslot, *d_timeStep, *d_hasPred, *d_flags, *d_minidx;
+    double *d_xLin, *d_uLin, *d_ztState, *d_ztFixed, *d_OldInput, *d_xPredPrev, *d_tmpx, *d_tmpu;
 };
 
 static bool inv6(const double* A, double* Ai) {
@@ -300,6 +307,12 @@ int lmpc_destroy(lmpc_handle* h) {
     if (!h) return LMPC_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->has_store) {
+        void* ptrs[] = {h->ss.x, h->ss.u, h->ss.q, h->ss.len, h->mdl.x, h->mdl.u, h->mdl.len, h->d_used, h->d_sel, h->d_isprev,
+                        h->d_prevslot, h->d_timeStep, h->d_hasPred, h->d_flags, h->d_minidx, h->d_xLin, h->d_uLin, h->d_ztState,
+                        h->d_ztFixed, h->d_OldInput, h->d_xPredPrev, h->d_tmpx, h->d_tmpu};
+        for (void* q : ptrs) cudaFree(q);
+    }
     double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
                      h->d_slack, h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid};
     for (double* q : dbl) cudaFree(q);
@@ -410,6 +423,340 @@ int lmpc_solve_mpc_host(lmpc_handle* h, const double* x0, const double* uOld, co
                         double* resid) {
     return lmpc_solve_lmpc_host(h, x0, uOld, abc, abc_inst_stride, abc_stage_stride, nullptr, nullptr, nullptr, nullptr, xPred,
                                 uPred, slack, nullptr, nullptr, nullptr, nullptr, status, iters, resid);
+}
+
+// ================================================================================================
+// lap stores, state, K1/K2/K6, fused step
+// ================================================================================================
+int lmpc_sizeof_params(void) { return (int)sizeof(lmpc_params); }
+int lmpc_sizeof_model_params(void) { return (int)sizeof(lmpc_model_params); }
+
+int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, int model_cap, int Tmax) {
+    if (!h || !mp || ss_cap < 0 || model_cap <= 0 || Tmax < 16) return fail(LMPC_E_INVALID, "bad store arguments");
+    if (h->has_store) return fail(LMPC_E_STATE, "store already created");
+    if (mp->trToUse < 1 || mp->trToUse > K1_MAXLAPS || mp->trToUse > model_cap) return fail(LMPC_E_INVALID, "trToUse out of range");
+    if (mp->MaxNumPoint < 1 || mp->MaxNumPoint > K1_MAXPTS) return fail(LMPC_E_INVALID, "MaxNumPoint must be <= 7");
+    if (mp->nseg < 1 || mp->nseg > 16) return fail(LMPC_E_INVALID, "track table has 1..16 segments");
+    if (h->M > 0) {
+        if (h->p.numSS_it < 1 || h->p.numSS_it > 8 || h->M % h->p.numSS_it) return fail(LMPC_E_INVALID, "numSS_Points must be a multiple of numSS_it <= 8");
+        if (((h->M / h->p.numSS_it) % 2) != 0) return fail(LMPC_E_INVALID, "numSS_Points/numSS_it must be even (PC.py:403,492-495)");
+        if (ss_cap < h->p.numSS_it) return fail(LMPC_E_INVALID, "ss_cap < numSS_it");
+    }
+    CK(cudaSetDevice(h->device));
+    ModelConst& m = h->mc;
+    memset(&m, 0, sizeof(m));
+    m.trToUse = mp->trToUse; m.MaxNumPoint = mp->MaxNumPoint; m.h = mp->h; m.lamb = mp->lamb; m.dt = mp->dt;
+    for (int i = 0; i < 5; ++i) m.scaling[i] = mp->scaling[i];
+    m.nseg = mp->nseg;
+    for (int i = 0; i < mp->nseg * 3; ++i) m.seg[i] = mp->seg[i];
+    m.TrackLength = mp->TrackLength;
+    const size_t B = h->batch, N = h->N;
+    h->ss.cap = ss_cap > 0 ? ss_cap : 1; h->ss.Tmax = Tmax;
+    h->mdl.cap = model_cap; h->mdl.Tmax = Tmax;
+#define DA(ptr, T, count) CK(cudaMalloc((void**)&(ptr), sizeof(T) * (count)))
+    DA(h->ss.x, double, B * h->ss.cap * Tmax * 6); DA(h->ss.u, double, B * h->ss.cap * Tmax * 2); DA(h->ss.q, double, B * h->ss.cap * Tmax);
+    DA(h->ss.len, int, B * h->ss.cap);
+    DA(h->mdl.x, double, B * model_cap * Tmax * 6); DA(h->mdl.u, double, B * model_cap * Tmax * 2); h->mdl.q = nullptr;
+    DA(h->mdl.len, int, B * model_cap);
+    DA(h->d_used, int, B * K1_MAXLAPS); DA(h->d_sel, int, B * 8); DA(h->d_isprev, int, B * 8); DA(h->d_prevslot, int, B);
+    DA(h->d_timeStep, int, B); DA(h->d_hasPred, int, B); DA(h->d_flags, int, B); DA(h->d_minidx, int, B * 8);
+    DA(h->d_xLin, double, B * (N + 1) * 6); DA(h->d_uLin, double, B * N * 2); DA(h->d_ztState, double, B * 6);
+    DA(h->d_ztFixed, double, B * 6); DA(h->d_OldInput, double, B * 2); DA(h->d_xPredPrev, double, B * (N + 1) * 6);
+    DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2);
+#undef DA
+    CK(cudaMemsetAsync(h->ss.len, 0, sizeof(int) * B * h->ss.cap, h->stream));
+    CK(cudaMemsetAsync(h->mdl.len, 0, sizeof(int) * B * model_cap, h->stream));
+    CK(cudaMemsetAsync(h->d_used, 0, sizeof(int) * B * K1_MAXLAPS, h->stream));
+    CK(cudaMemsetAsync(h->d_sel, 0, sizeof(int) * B * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_isprev, 0, sizeof(int) * B * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_prevslot, 0xff, sizeof(int) * B, h->stream));
+    CK(cudaMemsetAsync(h->d_timeStep, 0, sizeof(int) * B, h->stream));
+    CK(cudaMemsetAsync(h->d_hasPred, 0, sizeof(int) * B, h->stream));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * B, h->stream));
+    CK(cudaMemsetAsync(h->d_OldInput, 0, sizeof(double) * B * 2, h->stream));
+    CK(cudaMemsetAsync(h->d_ztState, 0, sizeof(double) * B * 6, h->stream));
+    CK(cudaMemsetAsync(h->d_xPredPrev, 0, sizeof(double) * B * (N + 1) * 6, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_store = true;
+    return LMPC_OK;
+}
+
+static int need_store(lmpc_handle* h) {
+    if (!h) return fail(LMPC_E_INVALID, "null handle");
+    if (!h->has_store) return fail(LMPC_E_STATE, "call lmpc_store_create first");
+    return LMPC_OK;
+}
+
+static int put_lap(lmpc_handle* h, LapPool& pool, int inst, int slot, int T, const double* x, const double* u) {
+    if (inst < 0 || inst >= h->batch || slot < 0 || slot >= pool.cap || T < 2 || T > pool.Tmax || !x || !u)
+        return fail(LMPC_E_INVALID, "put_lap: bad instance/slot/length");
+    CK(cudaSetDevice(h->device));
+    const size_t lap = pool.lap_index(inst, slot);
+    CK(cudaMemcpyAsync(pool.x + lap * pool.Tmax * 6, x, sizeof(double) * T * 6, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(pool.u + lap * pool.Tmax * 2, u, sizeof(double) * T * 2, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(pool.len + lap, &T, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // T lives on the caller's stack
+    return LMPC_OK;
+}
+
+int lmpc_model_put_lap(lmpc_handle* h, int inst, int slot, int T, const double* x, const double* u) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    return put_lap(h, h->mdl, inst, slot, T, x, u);
+}
+
+int lmpc_model_set_used(lmpc_handle* h, const int* slots) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!slots) return fail(LMPC_E_INVALID, "null slots");
+    for (size_t i = 0; i < (size_t)h->batch * h->mc.trToUse; ++i)
+        if (slots[i] < 0 || slots[i] >= h->mdl.cap) return fail(LMPC_E_INVALID, "model slot out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_used, slots, sizeof(int) * h->batch * h->mc.trToUse, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_ss_put_lap(lmpc_handle* h, int inst, int slot, int T, const double* x, const double* u, const double* qfun) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    rc = put_lap(h, h->ss, inst, slot, T, x, u);
+    if (rc) return rc;
+    const size_t lap = h->ss.lap_index(inst, slot);
+    if (qfun) {
+        CK(cudaMemcpyAsync(h->ss.q + lap * h->ss.Tmax, qfun, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        rollout_cost_kernel<<<1, 32, 0, h->stream>>>(h->ss, inst, slot, h->mc.TrackLength);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_ss_set_selection(lmpc_handle* h, const int* slots, const int* is_prev, const int* prev_slot) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!slots || !is_prev || !prev_slot) return fail(LMPC_E_INVALID, "null argument");
+    const int nit = h->p.numSS_it;
+    for (size_t i = 0; i < (size_t)h->batch * nit; ++i)
+        if (slots[i] < 0 || slots[i] >= h->ss.cap) return fail(LMPC_E_INVALID, "safe-set slot out of range");
+    for (int b = 0; b < h->batch; ++b)
+        if (prev_slot[b] >= h->ss.cap) return fail(LMPC_E_INVALID, "prev_slot out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_sel, slots, sizeof(int) * h->batch * nit, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_isprev, is_prev, sizeof(int) * h->batch * nit, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_prevslot, prev_slot, sizeof(int) * h->batch, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_ss_add_point(lmpc_handle* h, const double* x, const double* u) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!x || !u) return fail(LMPC_E_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_tmpx, x, sizeof(double) * h->batch * 6, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_tmpu, u, sizeof(double) * h->batch * 2, cudaMemcpyHostToDevice, h->stream));
+    ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, h->d_tmpx, h->d_tmpu,
+                                                                        h->mc.TrackLength, h->d_flags);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_ss_get_lap(lmpc_handle* h, int inst, int slot, int* T, double* x, double* u, double* qfun) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (inst < 0 || inst >= h->batch || slot < 0 || slot >= h->ss.cap || !T) return fail(LMPC_E_INVALID, "bad instance/slot");
+    CK(cudaSetDevice(h->device));
+    const size_t lap = h->ss.lap_index(inst, slot);
+    CK(cudaMemcpyAsync(T, h->ss.len + lap, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (x) CK(cudaMemcpyAsync(x, h->ss.x + lap * h->ss.Tmax * 6, sizeof(double) * (*T) * 6, cudaMemcpyDeviceToHost, h->stream));
+    if (u) CK(cudaMemcpyAsync(u, h->ss.u + lap * h->ss.Tmax * 2, sizeof(double) * (*T) * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (qfun) CK(cudaMemcpyAsync(qfun, h->ss.q + lap * h->ss.Tmax, sizeof(double) * (*T), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_ss_patch_row(lmpc_handle* h, int inst, int slot, int row, const double* x6, int also_model_slot) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (inst < 0 || inst >= h->batch || slot < 0 || slot >= h->ss.cap || row < 0 || row >= h->ss.Tmax || !x6)
+        return fail(LMPC_E_INVALID, "bad patch arguments");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->ss.x + (h->ss.lap_index(inst, slot) * h->ss.Tmax + row) * 6, x6, sizeof(double) * 6, cudaMemcpyHostToDevice, h->stream));
+    if (also_model_slot >= 0 && also_model_slot < h->mdl.cap)
+        CK(cudaMemcpyAsync(h->mdl.x + (h->mdl.lap_index(inst, also_model_slot) * h->mdl.Tmax + row) * 6, x6, sizeof(double) * 6,
+                           cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_state_set(lmpc_handle* h, const double* xLin, const double* uLin, const double* zt, const double* OldInput,
+                   const int* timeStep, const int* has_pred, const double* xPred) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch, N = h->N, D = sizeof(double);
+    cudaStream_t s = h->stream;
+    if (xLin) CK(cudaMemcpyAsync(h->d_xLin, xLin, B * (N + 1) * 6 * D, cudaMemcpyHostToDevice, s));
+    if (uLin) CK(cudaMemcpyAsync(h->d_uLin, uLin, B * N * 2 * D, cudaMemcpyHostToDevice, s));
+    if (zt) CK(cudaMemcpyAsync(h->d_ztState, zt, B * 6 * D, cudaMemcpyHostToDevice, s));
+    if (OldInput) CK(cudaMemcpyAsync(h->d_OldInput, OldInput, B * 2 * D, cudaMemcpyHostToDevice, s));
+    if (timeStep) CK(cudaMemcpyAsync(h->d_timeStep, timeStep, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (has_pred) CK(cudaMemcpyAsync(h->d_hasPred, has_pred, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (xPred) CK(cudaMemcpyAsync(h->d_xPredPrev, xPred, B * (N + 1) * 6 * D, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return LMPC_OK;
+}
+
+int lmpc_state_get(lmpc_handle* h, double* xLin, double* uLin, double* zt, double* OldInput, int* timeStep) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch, N = h->N, D = sizeof(double);
+    cudaStream_t s = h->stream;
+    if (xLin) CK(cudaMemcpyAsync(xLin, h->d_xLin, B * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
+    if (uLin) CK(cudaMemcpyAsync(uLin, h->d_uLin, B * N * 2 * D, cudaMemcpyDeviceToHost, s));
+    if (zt) CK(cudaMemcpyAsync(zt, h->d_ztState, B * 6 * D, cudaMemcpyDeviceToHost, s));
+    if (OldInput) CK(cudaMemcpyAsync(OldInput, h->d_OldInput, B * 2 * D, cudaMemcpyDeviceToHost, s));
+    if (timeStep) CK(cudaMemcpyAsync(timeStep, h->d_timeStep, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LMPC_OK;
+}
+
+static int launch_k1(lmpc_handle* h) {
+    K1Args a;
+    a.batch = h->batch; a.N = h->N;
+    a.wpb = h->N < 12 ? h->N : 12;
+    a.pts_stride = K1_MAXPTS * h->mc.trToUse * 10 + 48;
+    a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
+    dim3 grid(h->batch, (h->N + a.wpb - 1) / a.wpb);
+    size_t smem = sizeof(double) * a.pts_stride * a.wpb;
+    static thread_local int cfg_dev = -1;
+    if (cfg_dev != h->device) {
+        CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        cfg_dev = h->device;
+    }
+    knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, h->stream>>>(h->mc, a);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LMPC_OK;
+}
+
+static int launch_k2(lmpc_handle* h, const double* d_x0) {
+    K2Args a;
+    a.batch = h->batch; a.N = h->N; a.numSS_it = h->p.numSS_it; a.P = h->M / h->p.numSS_it;
+    a.TrackLength = h->mc.TrackLength;
+    a.x0 = d_x0; a.zt = h->d_ztState; a.pool = h->ss; a.sel = h->d_sel; a.is_prev = h->d_isprev;
+    a.timeStep = h->d_timeStep; a.has_pred = h->d_hasPred; a.xPred = h->d_xPredPrev;
+    a.SS_sel = h->d_SS; a.Qfun_sel = h->d_Qfun; a.Succ_SS = h->d_SuccSS; a.Succ_uSS = h->d_SuccU;
+    a.zt_fixed = h->d_ztFixed; a.status = h->d_flags; a.min_index = h->d_minidx;
+    ss_select_kernel<<<h->batch, 32 * a.numSS_it, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LMPC_OK;
+}
+
+int lmpc_identify_host(lmpc_handle* h, double* abc_out, int* flags) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
+    rc = launch_k1(h);
+    if (rc) return rc;
+    if (abc_out) CK(cudaMemcpyAsync(abc_out, h->d_abc, sizeof(double) * h->batch * h->N * 54, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, h->d_flags, sizeof(int) * h->batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_select_host(lmpc_handle* h, const double* x0, double* SS_sel, double* Qfun_sel, double* Succ_SS, double* Succ_uSS,
+                     int* min_index, int* flags) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (h->M <= 0 || !x0) return fail(LMPC_E_INVALID, "handle has no safe set or x0 is null");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch, M = h->M, D = sizeof(double);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_x0, x0, B * 6 * D, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * B, s));
+    rc = launch_k2(h, h->d_x0);
+    if (rc) return rc;
+    if (SS_sel) CK(cudaMemcpyAsync(SS_sel, h->d_SS, B * 6 * M * D, cudaMemcpyDeviceToHost, s));
+    if (Qfun_sel) CK(cudaMemcpyAsync(Qfun_sel, h->d_Qfun, B * M * D, cudaMemcpyDeviceToHost, s));
+    if (Succ_SS) CK(cudaMemcpyAsync(Succ_SS, h->d_SuccSS, B * 6 * M * D, cudaMemcpyDeviceToHost, s));
+    if (Succ_uSS) CK(cudaMemcpyAsync(Succ_uSS, h->d_SuccU, B * 2 * M * D, cudaMemcpyDeviceToHost, s));
+    if (min_index) CK(cudaMemcpyAsync(min_index, h->d_minidx, B * h->p.numSS_it * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (flags) CK(cudaMemcpyAsync(flags, h->d_flags, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LMPC_OK;
+}
+
+int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!x0_dev || (mode != 0 && mode != 1)) return fail(LMPC_E_INVALID, "bad mode or null x0");
+    if (mode == 1 && h->M <= 0) return fail(LMPC_E_INVALID, "LMPC step on a handle without a safe set");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
+    if ((rc = launch_k1(h)) != LMPC_OK) return rc;                      // PC.py:117
+    if (mode == 1 && (rc = launch_k2(h, x0_dev)) != LMPC_OK) return rc;  // PC.py:121
+    rc = lmpc_solve_lmpc_dev(h, x0_dev, h->d_OldInput, h->d_abc, (long long)h->N * 54, 54, mode == 1 ? h->d_SS : nullptr,
+                             mode == 1 ? h->d_Qfun : nullptr, mode == 1 ? h->d_SuccSS : nullptr, mode == 1 ? h->d_SuccU : nullptr,
+                             h->d_xPred, h->d_uPred, h->d_slack, mode == 1 ? h->d_lambd : nullptr, mode == 1 ? h->d_slackT : nullptr,
+                             mode == 1 ? h->d_zt : nullptr, mode == 1 ? h->d_ztu : nullptr, h->d_status, h->d_iters, h->d_resid);  // PC.py:124-125
+    if (rc) return rc;
+    ShiftArgs sa;
+    sa.batch = h->batch; sa.N = h->N; sa.lmpc = mode;
+    sa.xPred = h->d_xPred; sa.uPred = h->d_uPred; sa.zt_in = h->d_zt; sa.ztu_in = h->d_ztu;
+    sa.xLin = h->d_xLin; sa.uLin = h->d_uLin; sa.zt = h->d_ztState; sa.OldInput = h->d_OldInput; sa.xPredPrev = h->d_xPredPrev;
+    sa.timeStep = h->d_timeStep; sa.has_pred = h->d_hasPred;
+    shift_state_kernel<<<h->batch, 64, 0, h->stream>>>(sa);             // PC.py:129-137
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LMPC_OK;
+}
+
+int lmpc_step_host(lmpc_handle* h, int mode, const double* x0, double* xPred, double* uPred, double* lambd, double* zt,
+                   double* zt_u, double* SS_sel, int* status, int* iters, double* resid, int* flags) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!x0) return fail(LMPC_E_INVALID, "null x0");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1, D = sizeof(double);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_x0, x0, B * 6 * D, cudaMemcpyHostToDevice, s));
+    rc = lmpc_step_dev(h, mode, h->d_x0);
+    if (rc) return rc;
+    if (xPred) CK(cudaMemcpyAsync(xPred, h->d_xPred, B * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
+    if (uPred) CK(cudaMemcpyAsync(uPred, h->d_uPred, B * N * 2 * D, cudaMemcpyDeviceToHost, s));
+    if (mode == 1) {
+        if (lambd) CK(cudaMemcpyAsync(lambd, h->d_lambd, B * M * D, cudaMemcpyDeviceToHost, s));
+        if (zt) CK(cudaMemcpyAsync(zt, h->d_zt, B * 6 * D, cudaMemcpyDeviceToHost, s));
+        if (zt_u) CK(cudaMemcpyAsync(zt_u, h->d_ztu, B * 2 * D, cudaMemcpyDeviceToHost, s));
+        if (SS_sel) CK(cudaMemcpyAsync(SS_sel, h->d_SS, B * 6 * M * D, cudaMemcpyDeviceToHost, s));
+    }
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (resid) CK(cudaMemcpyAsync(resid, h->d_resid, B * 3 * D, cudaMemcpyDeviceToHost, s));
+    if (flags) CK(cudaMemcpyAsync(flags, h->d_flags, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LMPC_OK;
+}
+
+void* lmpc_device_buffer(lmpc_handle* h, const char* name) {
+    if (!h || !name) return nullptr;
+    struct { const char* n; void* p; } tab[] = {
+        {"xPred", h->d_xPred}, {"uPred", h->d_uPred}, {"lambd", h->d_lambd}, {"zt", h->d_zt}, {"zt_u", h->d_ztu},
+        {"abc", h->d_abc}, {"SS_sel", h->d_SS}, {"Qfun_sel", h->d_Qfun}, {"Succ_SS", h->d_SuccSS}, {"Succ_uSS", h->d_SuccU},
+        {"status", h->d_status}, {"iters", h->d_iters}, {"resid", h->d_resid}, {"flags", h->d_flags}, {"xLin", h->d_xLin},
+        {"uLin", h->d_uLin}, {"x0", h->d_x0}, {"OldInput", h->d_OldInput}};
+    for (auto& e : tab) if (strcmp(e.n, name) == 0) return e.p;
+    return nullptr;
 }
 
 }  // extern "C"

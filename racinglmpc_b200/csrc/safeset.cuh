@@ -1,0 +1,477 @@
+// racinglmpc_b200/csrc/safeset.cuh — device-resident lap stores and the HBM-scan kernels of the LMPC step.
+//
+//   K1 knn_ltv_regress   PredictiveModel.regressionAndLinearization + computeIndices + compute_Q_M +
+//                        compute_b + LMPC_LocLinReg (PredictiveModel.py:48-197), Map.curvature (Track.py:292-310)
+//   K2 ss_select         LMPC.addTerminalComponents / selectPoints (PredictiveControllers.py:386-416,478-514)
+//   K6 ss_add_point      LMPC.addPoint (PC.py:466-476);  rollout_cost = LMPC.computeCost (PC.py:447-464)
+//   K5 shift_state       xLin/uLin/OldInput/timeStep update of MPC.solve (PC.py:129-137)
+//
+// Lap store layout (one pool for the safe set, one for the regression model), per instance b, slot j:
+//   x  [b][j][Tmax][6]   row-major states      u [b][j][Tmax][2]      q [b][j][Tmax] (safe set only)
+//   len[b][j]            valid rows
+// Rows are contiguous, so a warp scanning a lap issues fully coalesced 48 B/row (x) + 16 B/row (u) loads.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+namespace lmpc {
+
+struct ModelConst {
+    int trToUse, MaxNumPoint;
+    double h, lamb, dt;
+    double scaling[5];
+    int nseg;
+    double seg[16 * 3];   // s_start, length, curvature
+    double TrackLength;
+};
+
+struct LapPool {
+    double* x;      // [B][cap][Tmax][6]
+    double* u;      // [B][cap][Tmax][2]
+    double* q;      // [B][cap][Tmax]   (nullptr for the model pool)
+    int* len;       // [B][cap]
+    int cap, Tmax;
+    __host__ __device__ size_t lap_index(int b, int slot) const { return (size_t)b * cap + slot; }
+};
+
+// Track.py:292-310 — wrap by repeated subtraction, first segment with s in [s0, s0+len)
+__device__ __forceinline__ double curvature_lookup(const ModelConst& m, double s, int* ok) {
+    while (s > m.TrackLength) s = s - m.TrackLength;
+    for (int i = 0; i < m.nseg; ++i) {
+        double s0 = m.seg[i * 3], ln = m.seg[i * 3 + 1];
+        if (s >= s0 && s < s0 + ln) return m.seg[i * 3 + 2];
+    }
+    *ok = 0;   // the reference raises here (negative s / exact end point)
+    return 0.0;
+}
+
+// (dist, idx) lexicographic "less": ties go to the lower row index
+__device__ __forceinline__ bool cand_less(double d1, int i1, double d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
+
+// Gaussian elimination with partial pivoting, n = 5, NR right-hand sides; lane-redundant.
+template <int NR>
+__device__ __forceinline__ bool solve5(double (&A)[5][5], double (&b)[NR][5]) {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        int piv = c;
+        double best = fabs(A[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < 5; ++r) {
+            double v = fabs(A[r][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (!(best > 0.0)) { ok = false; best = 1.0; }
+#pragma unroll
+        for (int r = c + 1; r < 5; ++r) {
+            if (piv == r) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { double t = A[c][j]; A[c][j] = A[r][j]; A[r][j] = t; }
+#pragma unroll
+                for (int k = 0; k < NR; ++k) { double t = b[k][c]; b[k][c] = b[k][r]; b[k][r] = t; }
+            }
+        }
+        double inv = 1.0 / A[c][c];
+#pragma unroll
+        for (int r = c + 1; r < 5; ++r) {
+            double f = A[r][c] * inv;
+#pragma unroll
+            for (int j = c + 1; j < 5; ++j) A[r][j] -= f * A[c][j];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) b[k][r] -= f * b[k][c];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+#pragma unroll
+        for (int r = 4; r >= 0; --r) {
+            double v = b[k][r];
+#pragma unroll
+            for (int j = r + 1; j < 5; ++j) v -= A[r][j] * b[k][j];
+            b[k][r] = v / A[r][r];
+        }
+    }
+    return ok;
+}
+
+constexpr int K1_MAXPTS = 7;     // MaxNumPoint supported by the register top-k
+constexpr int K1_MAXLAPS = 8;    // trToUse supported
+
+struct K1Args {
+    int batch, N, wpb, pts_stride;   // warps per block; doubles of staging per warp (7*trToUse*10 + 48)
+    const double* xLin;   // [B][N+1][6]
+    const double* uLin;   // [B][N][2]
+    LapPool pool;         // model pool
+    const int* used;      // [B][trToUse] slot ids, in usedIt order
+    double* abc;          // [B][N][54]
+    int* status;          // [B] : 0 ok, else bit flags (1 = singular regression, 2 = curvature lookup failed,
+                          //        4 = fewer than 2 neighbours in a lap — the reference would raise)
+};
+
+// grid = (B, ceil(N / wpb)); one warp per horizon step.
+__global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_constant__ ModelConst m, const K1Args a) {
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    const int b = blockIdx.x;
+    const int wib = threadIdx.x >> 5;
+    const int i = blockIdx.y * a.wpb + wib;   // horizon step
+    const int lane = threadIdx.x & 31;
+    if (b >= a.batch || i >= a.N) return;
+    // per-warp staging of the selected points: [<=7*trToUse][10] = x0,x1,x2,u0,u1,K,y0,y1,y2,(pad), then 48 scratch
+    double* pts = reinterpret_cast<double*>(k1_smem) + (size_t)wib * a.pts_stride;
+
+    const double* xl = a.xLin + ((size_t)b * (a.N + 1) + i) * 6;
+    const double* ul = a.uLin + ((size_t)b * a.N + i) * 2;
+    double q[5] = {xl[0], xl[1], xl[2], ul[0], ul[1]};
+    double xs[6] = {xl[0], xl[1], xl[2], xl[3], xl[4], xl[5]};
+    int flags = 0, npts = 0;
+
+    for (int c = 0; c < m.trToUse; ++c) {
+        const int slot = a.used[(size_t)b * m.trToUse + c];
+        const size_t lap = a.pool.lap_index(b, slot);
+        const double* X = a.pool.x + lap * a.pool.Tmax * 6;
+        const double* U = a.pool.u + lap * a.pool.Tmax * 2;
+        const int T = a.pool.len[lap];
+        // ---- scan rows 0..T-2 (PM.py:183), per-lane sorted top-7 ----
+        double bd[K1_MAXPTS];
+        int bi[K1_MAXPTS];
+#pragma unroll
+        for (int r = 0; r < K1_MAXPTS; ++r) { bd[r] = 1e300; bi[r] = 0x7fffffff; }
+        int cnt = 0;
+        for (int t = lane; t < T - 1; t += 32) {
+            const double* xr = X + (size_t)t * 6;
+            const double* ur = U + (size_t)t * 2;
+            // diff = (Data - x) * scaling ; 1-norm summed left to right (numpy semantics for 5 columns)
+            double d = fabs(__dmul_rn(__dsub_rn(xr[0], q[0]), m.scaling[0]));
+            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(xr[1], q[1]), m.scaling[1])));
+            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(xr[2], q[2]), m.scaling[2])));
+            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(ur[0], q[3]), m.scaling[3])));
+            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(ur[1], q[4]), m.scaling[4])));
+            if (d < m.h) ++cnt;
+            if (cand_less(d, t, bd[K1_MAXPTS - 1], bi[K1_MAXPTS - 1])) {
+                bd[K1_MAXPTS - 1] = d;
+                bi[K1_MAXPTS - 1] = t;
+#pragma unroll
+                for (int r = K1_MAXPTS - 1; r > 0; --r) {
+                    if (cand_less(bd[r], bi[r], bd[r - 1], bi[r - 1])) {
+                        double td = bd[r]; bd[r] = bd[r - 1]; bd[r - 1] = td;
+                        int ti = bi[r]; bi[r] = bi[r - 1]; bi[r - 1] = ti;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside
+        int ksel = cnt >= m.MaxNumPoint ? m.MaxNumPoint : cnt;
+        if (cnt == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
+        // ---- merge: ksel rounds of warp arg-min over the lane heads ----
+        for (int r = 0; r < ksel; ++r) {
+            double hd = bd[0];
+            int hi = bi[0];
+            double wd = hd;
+            int wi = hi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double od = __shfl_xor_sync(0xffffffffu, wd, o);
+                int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (cand_less(od, oi, wd, wi)) { wd = od; wi = oi; }
+            }
+            if (hi == wi && hd == wd) {   // this lane owned the winner: pop it
+#pragma unroll
+                for (int z = 0; z < K1_MAXPTS - 1; ++z) { bd[z] = bd[z + 1]; bi[z] = bi[z + 1]; }
+                bd[K1_MAXPTS - 1] = 1e300;
+                bi[K1_MAXPTS - 1] = 0x7fffffff;
+            }
+            if (lane == 0) {
+                double* p = pts + (size_t)(npts + r) * 10;
+                const double* xr = X + (size_t)wi * 6;
+                const double* xn = X + (size_t)(wi + 1) * 6;
+                const double* ur = U + (size_t)wi * 2;
+                double rr = wd / m.h;
+                p[0] = xr[0]; p[1] = xr[1]; p[2] = xr[2]; p[3] = ur[0]; p[4] = ur[1];
+                p[5] = (1.0 - rr * rr) * 3.0 / 4.0;      // Epanechnikov weight, PM.py:193
+                p[6] = xn[0]; p[7] = xn[1]; p[8] = xn[2];
+            }
+        }
+        npts += ksel;
+    }
+    __syncwarp();
+
+    // ---- normal equations (PM.py:141-168).  entries: Qvx(15) Qlat(15) bvx(5) bvy(5) bwz(5) ----
+    double* ne = pts + a.pts_stride - 48;   // tail of this warp's staging area
+    for (int e = lane; e < 45; e += 32) {
+        double acc = 0.0;
+        if (e < 30) {
+            const int lat = e >= 15;
+            int idx = lat ? e - 15 : e;
+            int r = 0;
+            while (idx >= 5 - r) { idx -= 5 - r; ++r; }
+            const int cc = idx + r;     // (r, cc), r <= cc
+            for (int p = 0; p < npts; ++p) {
+                const double* P = pts + (size_t)p * 10;
+                double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
+                double mc = (cc < 3) ? P[cc] : (cc == 3 ? (lat ? P[3] : P[4]) : 1.0);
+                acc += mr * P[5] * mc;
+            }
+            if (r == cc) acc += m.lamb;
+        } else {
+            const int which = (e - 30) / 5, r = (e - 30) % 5;   // 0 vx, 1 vy, 2 wz
+            const int lat = which > 0;
+            for (int p = 0; p < npts; ++p) {
+                const double* P = pts + (size_t)p * 10;
+                double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
+                acc += mr * P[5] * P[6 + which];
+            }
+        }
+        ne[e] = acc;
+    }
+    __syncwarp();
+    double Qv[5][5], Ql[5][5], bv[1][5], bl[2][5];
+    {
+        int e = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int cc = r; cc < 5; ++cc) { Qv[r][cc] = Qv[cc][r] = ne[e]; Ql[r][cc] = Ql[cc][r] = ne[15 + e]; ++e; }
+#pragma unroll
+        for (int r = 0; r < 5; ++r) { bv[0][r] = ne[30 + r]; bl[0][r] = ne[35 + r]; bl[1][r] = ne[40 + r]; }
+    }
+    if (!solve5<1>(Qv, bv)) flags |= 1;
+    if (!solve5<2>(Ql, bl)) flags |= 1;
+
+    // ---- A, B, C (PM.py:66-135) ----
+    double* out = a.abc + ((size_t)b * a.N + i) * 54;
+    const double vx = xs[0], vy = xs[1], wz = xs[2], epsi = xs[3], s = xs[4], ey = xs[5];
+    const double dt = m.dt;
+    int okc = 1;
+    const double cur = curvature_lookup(m, s, &okc);
+    if (!okc) flags |= 2;
+    const double den = 1.0 - cur * ey;
+    const double ce = cos(epsi), se = sin(epsi);
+    double A3[6], A4[6], A5[6];
+    A3[0] = -dt * ce / den * cur;
+    A3[1] = dt * se / den * cur;
+    A3[2] = dt;
+    A3[3] = 1.0 - dt * (-vx * se - vy * ce) / den * cur;
+    A3[4] = 0.0;
+    A3[5] = dt * (vx * ce - vy * se) / (den * den) * cur * (-cur);
+    A4[0] = dt * (ce / den);
+    A4[1] = -dt * (se / den);
+    A4[2] = 0.0;
+    A4[3] = dt * (-vx * se - vy * ce) / den;
+    A4[4] = 1.0;
+    A4[5] = -dt * (vx * ce - vy * se) / (den * den) * (-cur);
+    A5[0] = dt * se;
+    A5[1] = dt * ce;
+    A5[2] = 0.0;
+    A5[3] = dt * (vx * ce - vy * se);
+    A5[4] = 0.0;
+    A5[5] = 1.0;
+    double d3 = 0, d4 = 0, d5 = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { d3 += A3[j] * xs[j]; d4 += A4[j] * xs[j]; d5 += A5[j] * xs[j]; }
+    const double C3 = epsi + dt * (wz - (vx * ce - vy * se) / (1.0 - cur * ey) * cur) - d3;
+    const double C4 = s + dt * ((vx * ce - vy * se) / (1.0 - cur * ey)) - d4;
+    const double C5 = ey + dt * (vx * se + vy * ce) - d5;
+    for (int e = lane; e < 54; e += 32) {
+        double v = 0.0;
+        if (e < 36) {
+            const int r = e / 6, cc = e % 6;
+            if (r == 0) v = cc < 3 ? bv[0][cc] : 0.0;
+            else if (r == 1) v = cc < 3 ? bl[0][cc] : 0.0;
+            else if (r == 2) v = cc < 3 ? bl[1][cc] : 0.0;
+            else if (r == 3) v = A3[cc];
+            else if (r == 4) v = A4[cc];
+            else v = A5[cc];
+        } else if (e < 48) {
+            const int r = (e - 36) >> 1, cc = (e - 36) & 1;
+            if (r == 0 && cc == 1) v = bv[0][3];          // vx row uses the acceleration input (PM.py:29,70)
+            else if (r == 1 && cc == 0) v = bl[0][3];     // lateral rows use the steering input (PM.py:30,78,82)
+            else if (r == 2 && cc == 0) v = bl[1][3];
+        } else {
+            const int r = e - 48;
+            v = r == 0 ? bv[0][4] : r == 1 ? bl[0][4] : r == 2 ? bl[1][4] : r == 3 ? C3 : r == 4 ? C4 : C5;
+        }
+        out[e] = v;
+    }
+    if (lane == 0 && flags) atomicOr(&a.status[b], flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct K2Args {
+    int batch, N, numSS_it, P;   // P = numSS_Points / numSS_it
+    double TrackLength;
+    const double* x0;        // [B][6]
+    const double* zt;        // [B][6]
+    LapPool pool;            // safe-set pool
+    const int* sel;          // [B][numSS_it] slot ids in sortedLapTime order (PC.py:395,402)
+    const int* is_prev;      // [B][numSS_it] 1 if that lap is iteration it-1 (PC.py:506-512)
+    const int* timeStep;     // [B]
+    const int* has_pred;     // [B]
+    const double* xPred;     // [B][N+1][6] previous prediction
+    double* SS_sel;          // [B][6][M]
+    double* Qfun_sel;        // [B][M]
+    double* Succ_SS;         // [B][6][M]
+    double* Succ_uSS;        // [B][2][M]
+    double* zt_fixed;        // [B][6] zt after the lap-wrap fix (PC.py:392-393)
+    int* status;             // [B] bit 8 = selection window ran past the stored lap (reference: IndexError)
+    int* min_index;          // [B][numSS_it] argmin row (for tests)
+};
+
+// One CTA per instance, one warp per selected lap.
+__global__ void __launch_bounds__(32 * 8) ss_select_kernel(const K2Args a) {
+    const int b = blockIdx.x;
+    const int c = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= a.batch || c >= a.numSS_it) return;
+    const int M = a.P * a.numSS_it;
+    // lap-wrap fix of the terminal guess (PC.py:392-393)
+    double z[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) z[j] = a.zt[(size_t)b * 6 + j];
+    if (z[4] - a.x0[(size_t)b * 6 + 4] > a.TrackLength / 2) z[4] = fmax(z[4] - a.TrackLength, 0.0);
+    if (c == 0 && lane < 6) a.zt_fixed[(size_t)b * 6 + lane] = z[lane];
+
+    const int slot = a.sel[(size_t)b * a.numSS_it + c];
+    const size_t lap = a.pool.lap_index(b, slot);
+    const double* X = a.pool.x + lap * a.pool.Tmax * 6;
+    const double* U = a.pool.u + lap * a.pool.Tmax * 2;
+    const double* Q = a.pool.q + lap * a.pool.Tmax;
+    const int T = a.pool.len[lap];
+    // 1-nearest neighbour in the 1-norm over all six states (PC.py:486-490); first minimum wins
+    double bd = 1e300;
+    int bi = 0x7fffffff;
+    for (int t = lane; t < T; t += 32) {
+        const double* xr = X + (size_t)t * 6;
+        double d = fabs(__dsub_rn(xr[0], z[0]));
+        d = __dadd_rn(d, fabs(__dsub_rn(xr[1], z[1])));
+        d = __dadd_rn(d, fabs(__dsub_rn(xr[2], z[2])));
+        d = __dadd_rn(d, fabs(__dsub_rn(xr[3], z[3])));
+        d = __dadd_rn(d, fabs(__dsub_rn(xr[4], z[4])));
+        d = __dadd_rn(d, fabs(__dsub_rn(xr[5], z[5])));
+        if (d < bd) { bd = d; bi = t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (cand_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    const int mn = bi;
+    // window (PC.py:492-495), numPoints = P + 1
+    const int npt = a.P + 1;
+    const int half = npt / 2;
+    int start, count;
+    if ((double)mn - (double)npt / 2.0 >= 0.0) { start = mn - half; count = 2 * half + 1; }
+    else { start = mn; count = npt; }
+    if (lane == 0) a.min_index[(size_t)b * a.numSS_it + c] = mn;
+    if (start + count > T || count != npt) {
+        if (lane == 0) atomicOr(&a.status[b], 8);
+        return;
+    }
+    // Q-function shift when the prediction has crossed the finish line (PC.py:501-512)
+    double adj = 0.0;
+    if (a.has_pred[b]) {
+        int over = 0;
+        for (int k = 0; k <= a.N; ++k) over += (a.xPred[((size_t)b * (a.N + 1) + k) * 6 + 4] > a.TrackLength) ? 1 : 0;
+        if (over > 0) {
+            if (!a.is_prev[(size_t)b * a.numSS_it + c]) adj = Q[0];
+            else adj = (double)a.timeStep[b] + (double)(a.N - over);
+        }
+    }
+    for (int l = lane; l < count; l += 32) {
+        const int row = start + l;
+        const double* xr = X + (size_t)row * 6;
+        if (l < a.P) {
+            const int col = c * a.P + l;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a.SS_sel[((size_t)b * 6 + j) * M + col] = xr[j];
+            a.Qfun_sel[(size_t)b * M + col] = Q[row] + adj;
+        }
+        if (l >= 1) {
+            const int col = c * a.P + (l - 1);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a.Succ_SS[((size_t)b * 6 + j) * M + col] = xr[j];
+            a.Succ_uSS[((size_t)b * 2 + 0) * M + col] = U[(size_t)row * 2];
+            a.Succ_uSS[((size_t)b * 2 + 1) * M + col] = U[(size_t)row * 2 + 1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LMPC.addPoint (PC.py:466-476): append x + [0,0,0,0,L,0], u to lap it-1; Qfun extends by last - 1.
+__global__ void ss_add_point_kernel(int batch, LapPool pool, const int* prev_slot, const double* x, const double* u,
+                                    double TrackLength, int* status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int slot = prev_slot[b];
+    if (slot < 0) return;
+    const size_t lap = pool.lap_index(b, slot);
+    const int T = pool.len[lap];
+    if (T >= pool.Tmax || T < 1) { atomicOr(&status[b], 16); return; }
+    double* X = pool.x + (lap * pool.Tmax + T) * 6;
+    double* U = pool.u + (lap * pool.Tmax + T) * 2;
+    double* Q = pool.q + lap * pool.Tmax;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) X[j] = x[(size_t)b * 6 + j] + (j == 4 ? TrackLength : 0.0);
+    U[0] = u[(size_t)b * 2];
+    U[1] = u[(size_t)b * 2 + 1];
+    Q[T] = Q[T - 1] - 1.0;
+    pool.len[lap] = T + 1;
+}
+
+// LMPC.computeCost (PC.py:447-464) for one (instance, slot): backward count of steps to the finish line.
+__global__ void rollout_cost_kernel(LapPool pool, int b, int slot, double TrackLength) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const size_t lap = pool.lap_index(b, slot);
+    const int T = pool.len[lap];
+    const double* X = pool.x + lap * pool.Tmax * 6;
+    double* Q = pool.q + lap * pool.Tmax;
+    for (int i = 0; i < T; ++i) {
+        const int j = T - 1 - i;
+        if (i == 0) Q[j] = 0.0;
+        else if (X[(size_t)j * 6 + 4] < TrackLength) Q[j] = Q[j + 1] + 1.0;
+        else Q[j] = 0.0;
+    }
+}
+
+// MPC.solve tail (PC.py:129-137): xLin = [xPred[1:]; zt], uLin = [uPred[1:]; zt_u], OldInput = uPred[0], timeStep += 1
+struct ShiftArgs {
+    int batch, N, lmpc;
+    const double* xPred;   // [B][N+1][6]
+    const double* uPred;   // [B][N][2]
+    const double* zt_in;   // [B][6]  (LMPC: Succ_SS lam; MPC: unused -> xPred[N])
+    const double* ztu_in;  // [B][2]
+    double* xLin;          // [B][N+1][6]
+    double* uLin;          // [B][N][2]
+    double* zt;            // [B][6]
+    double* OldInput;      // [B][2]
+    double* xPredPrev;     // [B][N+1][6]
+    int* timeStep;
+    int* has_pred;
+};
+__global__ void shift_state_kernel(const ShiftArgs a) {
+    const int b = blockIdx.x;
+    if (b >= a.batch) return;
+    const int N = a.N;
+    for (int e = threadIdx.x; e < (N + 1) * 6; e += blockDim.x) {
+        const int k = e / 6, j = e % 6;
+        double v;
+        if (k < N) v = a.xPred[((size_t)b * (N + 1) + k + 1) * 6 + j];
+        else v = a.lmpc ? a.zt_in[(size_t)b * 6 + j] : a.xPred[((size_t)b * (N + 1) + N) * 6 + j];
+        a.xLin[(size_t)b * (N + 1) * 6 + e] = v;
+        a.xPredPrev[(size_t)b * (N + 1) * 6 + e] = a.xPred[(size_t)b * (N + 1) * 6 + e];
+        if (k == N) a.zt[(size_t)b * 6 + j] = v;
+    }
+    for (int e = threadIdx.x; e < N * 2; e += blockDim.x) {
+        const int k = e / 2, j = e % 2;
+        double v;
+        if (k < N - 1) v = a.uPred[((size_t)b * N + k + 1) * 2 + j];
+        else v = a.lmpc ? a.ztu_in[(size_t)b * 2 + j] : a.uPred[((size_t)b * N + N - 1) * 2 + j];
+        a.uLin[(size_t)b * N * 2 + e] = v;
+    }
+    if (threadIdx.x < 2) a.OldInput[(size_t)b * 2 + threadIdx.x] = a.uPred[(size_t)b * N * 2 + threadIdx.x];
+    if (threadIdx.x == 0) { a.timeStep[b] += 1; a.has_pred[b] = 1; }
+}
+
+}  // namespace lmpc

@@ -1,0 +1,170 @@
+"""GPU tier: K1 (k-NN regression), K2 (safe-set selection), K6 (addPoint / computeCost) and the fused
+LMPC step against golden vectors produced by the REAL reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from racinglmpc_b200 import reference_params as rp                  # noqa: E402
+from racinglmpc_b200.controller import BatchedController            # noqa: E402
+import replay                                                       # noqa: E402
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+
+
+def _restore(gold, track, keys, N=12):
+    """One controller instance per snapshot key, restored to the state just before LMPC.solve(x0)."""
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    B = len(keys)
+    c = BatchedController(par, B, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points,
+                          numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536, ss_cap=8, model_cap=5)
+    st = dict(xLin=[], uLin=[], zt=[], OldInput=[], timeStep=[], has_pred=[], xPred=[])
+    x0 = []
+    for b, key in enumerate(keys):
+        k = "lmpc_%d_%d_" % key
+        for j in range(int(gold[k + "pm_nlap"])):
+            c.model_add_trajectory(b, gold[k + "pmx%d" % j], gold[k + "pmu%d" % j])
+        for j in range(int(gold[k + "nlap"])):
+            c.add_trajectory(b, gold[k + "SS%d" % j], gold[k + "uSS%d" % j], qfun=gold[k + "Qfun%d" % j],
+                             lap_time=int(gold[k + "LapTime"][j]))
+        assert c.it[b] == int(gold[k + "it"])
+        if not int(gold[k + "has_pred"]):
+            # very first LMPC solve: reproduce the aliased write of PC.py:394 (row 1+4, column ey of the shared PID lap)
+            for j in range(int(gold[k + "nlap"])):
+                row = gold[k + "SS%d" % j][5].copy()
+                row[5] -= track.TrackLength
+                c.patch_row(b, j, 5, row)
+        st["xLin"].append(gold[k + "xLin"]); st["uLin"].append(gold[k + "uLin"]); st["zt"].append(gold[k + "zt"])
+        st["OldInput"].append(gold[k + "OldInput"].ravel()); st["timeStep"].append(int(gold[k + "timeStep"]))
+        st["has_pred"].append(int(gold[k + "has_pred"])); st["xPred"].append(gold[k + "xPred_prev"])
+        x0.append(gold[k + "x0"])
+    c.set_state(**{k: np.array(v) for k, v in st.items()})
+    return c, np.array(x0)
+
+
+def test_k1_regression_matches_reference(gold, track):
+    _need_gpu()
+    keys = replay.LMPC_KEYS
+    c, x0 = _restore(gold, track, keys)
+    abc, flags = c.identify()
+    assert np.all(flags == 0), flags
+    for b, key in enumerate(keys):
+        k = "lmpc_%d_%d_" % key
+        A = abc[b][:, 0:36].reshape(12, 6, 6); B = abc[b][:, 36:48].reshape(12, 6, 2); C = abc[b][:, 48:54]
+        # rows 3..5 are closed-form (sin/cos may differ in the last ulp); rows 0..2 come from 5x5 solves
+        assert np.max(np.abs(A - gold[k + "A"])) < 1e-9, key
+        assert np.max(np.abs(B - gold[k + "B"])) < 1e-9, key
+        assert np.max(np.abs(C - gold[k + "C"])) < 1e-9, key
+        assert np.max(np.abs(A[:, 3:, :] - gold[k + "A"][:, 3:, :])) < 1e-14
+    c.close()
+
+
+def test_k2_selection_is_bit_exact(gold, track):
+    _need_gpu()
+    keys = replay.LMPC_KEYS
+    c, x0 = _restore(gold, track, keys)
+    o = c.select(x0)
+    assert np.all(o["flags"] == 0), o["flags"]
+    for b, key in enumerate(keys):
+        k = "lmpc_%d_%d_" % key
+        assert np.array_equal(o["SS_sel"][b], gold[k + "SS_sel"]), key
+        assert np.array_equal(o["Qfun_sel"][b], gold[k + "Qfun_sel"]), key
+        assert np.array_equal(o["Succ_SS"][b], gold[k + "Succ_SS"]), key
+        assert np.array_equal(o["Succ_uSS"][b], gold[k + "Succ_uSS"]), key
+    c.close()
+
+
+def test_fused_lmpc_step_matches_reference(gold, track):
+    _need_gpu()
+    keys = replay.LMPC_KEYS
+    c, x0 = _restore(gold, track, keys)
+    l0 = c.kernel_launches
+    o = c.step(x0)
+    assert c.kernel_launches - l0 == 4                       # K1, K2, QP, shift
+    assert np.all(o["status"] == 1) and np.all(o["flags"] == 0), (o["status"], o["flags"])
+    st = c.get_state()
+    for b, key in enumerate(keys):
+        k = "lmpc_%d_%d_" % key
+        assert np.max(np.abs(o["xPred"][b] - gold[k + "xPred"])) < 1e-6, key
+        assert np.max(np.abs(o["uPred"][b] - gold[k + "uPred"])) < 1e-6, key
+        assert np.max(np.abs(o["zt"][b] - gold[k + "zt_out"])) < 1e-5, key
+        assert np.array_equal(o["SS_sel"][b], gold[k + "SS_sel"])
+        # state shift (PC.py:129-137)
+        assert np.array_equal(st["xLin"][b][:-1], o["xPred"][b][1:]) and np.array_equal(st["xLin"][b][-1], o["zt"][b])
+        assert np.array_equal(st["uLin"][b][:-1], o["uPred"][b][1:]) and np.array_equal(st["uLin"][b][-1], o["zt_u"][b])
+        assert np.array_equal(st["OldInput"][b], o["uPred"][b][0])
+        assert st["timeStep"][b] == int(gold[k + "timeStep"]) + 1
+    c.close()
+
+
+def test_add_point_and_rollout_cost(gold, track):
+    _need_gpu()
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(12)
+    c = BatchedController(par, 2, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points,
+                          numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536)
+    xP, uP = gold["pid_x"], gold["pid_u"]
+    for b in range(2):
+        for _ in range(4):
+            c.add_trajectory(b, xP, uP)
+    x, u, q = c.get_lap(0, 3)
+    assert np.array_equal(x, xP) and np.array_equal(u, uP)
+    assert np.array_equal(q, gold["pid_Qfun"])               # computeCost on the device (PC.py:447-464)
+    pts = np.array([[0.6, 0.01, 0.02, 0.03, 0.5, -0.1], [0.7, 0.0, 0.0, 0.0, 1.5, 0.2]])
+    us = np.array([[0.1, 0.2], [-0.1, 0.3]])
+    c.add_point(pts, us)
+    c.add_point(pts + 0.1, us)
+    for b in range(2):
+        x, u, q = c.get_lap(b, 3)
+        assert x.shape[0] == xP.shape[0] + 2
+        assert np.array_equal(x[-2], pts[b] + np.array([0, 0, 0, 0, track.TrackLength, 0]))
+        assert np.array_equal(u[-1], us[b])
+        assert q[-2] == gold["pid_Qfun"][-1] - 1 and q[-1] == gold["pid_Qfun"][-1] - 2
+        x2, _, _ = c.get_lap(b, 2)
+        assert x2.shape[0] == xP.shape[0]                    # only lap it-1 grows (PC.py:472)
+    c.close()
+
+
+def test_closed_loop_lap_matches_reference_lap(gold, track):
+    """Drive LMPC lap 4 (main.py:113-117) with the GPU controller and the oracle's vehicle simulator, same seed
+    as the golden run with the real reference: same lap length, same states at the snapshot steps."""
+    _need_gpu()
+    from oracle import vehicle
+    N = 12
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    xP, uP = gold["pid_x"].copy(), gold["pid_u"].copy()
+    c = BatchedController(par, 1, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points,
+                          numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536)
+    for _ in range(4):
+        c.model_add_trajectory(0, xP, uP)
+    for _ in range(4):
+        c.add_trajectory(0, xP, uP)
+    c.set_state(xLin=xP[1:N + 2], uLin=uP[1:N + 1], zt=np.array([0.0, 0, 0, 0, 10.0, 0]), OldInput=np.zeros(2),
+                timeStep=[0], has_pred=[0])
+    # aliased write of the first solve (PC.py:394)
+    row = xP[5].copy(); row[5] -= track.TrackLength
+    for j in range(4):
+        c.patch_row(0, j, 5, row)
+    np.random.seed(0)
+    x0 = np.array([0.5, 0, 0, 0, 0, 0.0])
+    vehicle.closed_loop(track, [x0, x0], vehicle.PIDFollower(0.8))      # consume the PID lap's random draws
+    xs, gs = [x0], [x0]
+    t = 0
+    out = c.alloc_step_outputs()
+    while True:
+        if t in (1, 60, 200):
+            assert np.max(np.abs(xs[-1] - gold["lmpc_4_%d_x0" % t])) < 1e-6, t
+        o = c.step(xs[-1], out=out)
+        assert o["status"][0] == 1 and o["flags"][0] == 0, (t, o["status"], o["flags"])
+        u = o["uPred"][0, 0].copy()
+        c.add_point(xs[-1], u)
+        xt, gt = vehicle.dyn_model(track, xs[-1], gs[-1], u)
+        xs.append(xt); gs.append(gt)
+        t += 1
+        if xs[-1][4] > track.TrackLength or t >= 400:
+            break
+    assert t == int(gold["lmpc_lap_lengths"][0])
+    c.close()
