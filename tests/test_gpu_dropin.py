@@ -134,7 +134,8 @@ def test_main_py_sequence_against_oracle(shim, gold, track):
     assert [q[0] for q in glm.Qfun] == [q[0] for q in olm.Qfun]          # main.py:120,127
     assert len(glm.SS) == 6 and glm.SS[4].shape == olm.SS[4].shape       # laps grown by addPoint
     assert np.array_equal(glm.LapTime, olm.LapTime)
-    assert len(glm.xStoredPredTraj[5]) == glaps[0][0].shape[0] and glm.SSStoredPredTraj[5][0].shape == (numSS_Points, 6)
+    assert len(glm.xStoredPredTraj[4]) == glaps[0][0].shape[0] and len(glm.xStoredPredTraj[5]) == glaps[1][0].shape[0]
+    assert glm.SSStoredPredTraj[5][0].shape == (numSS_Points, 6)
     # the device copy of a grown lap equals the host mirror
     xdev, udev, qdev = glm._engine.get_lap(0, 4)
     assert np.array_equal(xdev, glm.SS[4]) and np.array_equal(qdev, glm.Qfun[4])
