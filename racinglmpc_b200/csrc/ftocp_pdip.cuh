@@ -105,34 +105,40 @@ enum Status : int {
 template <int N, int M, int NCX, int NCU>
 struct Work {
     static constexpr int MM = (M > 0 ? M : 1);
+    static constexpr int TM = (M > 0 ? 36 : 1);
     // --- model (filled by the loader; ABC via cp.async.bulk) ---
-    alignas(16) double ABC[N][54];  // per stage: A (36, row major a*6+b) | B (12, a*2+c) | C (6)
+    // As loaded: per stage A (36, row major a*6+b) | B (12, a*2+q) | C (6).  prepare_model() transposes A and B in
+    // place, after which ABC[k][j*6 + c] = [A_k B_k](c, j), j < 8: every dot product of the sweeps then runs over a
+    // contiguous, 16 B-aligned 6-vector (LDS.128).
+    alignas(16) double ABC[N][54];
     alignas(16) double SS[6 * MM];  // SS[a*M + l]      (PC.py:411 SS_PointSelectedTot, 6 x M)
     double Qfun[MM];                // Qfun_SelectedTot (PC.py:412)
     double uOld[2];                 // OldInput         (PC.py:136,247)
     // --- iterate ---
-    double x[(N + 1) * 6], u[N * 2];
-    double dx[(N + 1) * 6], du[N * 2];
+    alignas(16) double x[(N + 1) * 6];
+    alignas(16) double dx[(N + 1) * 6];
+    double u[N * 2], du[N * 2];
     // --- per-row quantities shared between lanes ---
     double Dt[N * NCX], ex[N * NCX];  // condensed lane-constraint Hessian weights / rhs
     double d2[N * NCU], eu[N * NCU];  // input-bound Hessian weights / rhs
-    double nu1s[N * NCX], nu2s[N * NCU];  // multipliers staged for the costate sweep
+    double nu1s[N * NCX], nu2s[N * NCU];  // multipliers staged for the stage-gradient pre-pass
     double d4i[MM];                   // 1 / max(nu4/lam, d4_min)
     // --- Riccati factor, per stage ---
-    double Li[N][3];    // 1/L00, L10, 1/L11   (L = chol of the 2x2 input Hessian)
-    double Z[N][12];    // L^-1 (B'Pxx + Pxv')A,  Z[r*6+c]
-    double Zv[N][3];    // L^-1 diag(dR2): Zv00, Zv10, Zv11
-    double z0[N][2];    // L^-1 g0 for the current right-hand side
-    double ru[N][2];    // input-stationarity residual
-    // --- sweep scratch ---
-    double G[48];                     // Pxx [A B]   G[a*8+j]
-    double Pxx[36], Pxv[12], Pvv[3];  // cost-to-go Hessian blocks
-    double Sx[36], Y[12], Lam[3], g0[2], hx[6];
-    double pb[2][8];                  // cost-to-go gradient (px | pv), double buffered
-    double pi[2][6];                  // costate, double buffered
+    alignas(16) double Zt[N][16];   // Z~ = L^-1 [ (B'Pxx+Pxv')A | -diag(dR2) ]  (2 x 8, row major)
+    double Li[N][3];                // 1/L00, L10, 1/L11   (L = chol of the 2x2 input Hessian)
+    double z0[N][2];                // L^-1 g0 for the current right-hand side
+    double ru[N][2];                // input-stationarity residual
+    alignas(16) double gst[N][8];   // stage gradient: (2Q x + qx + Fx'nu1 | 2R u + rate + Fu'nu2)
+    // --- sweep scratch (augmented state (x, v = previous input), 8 x 8) ---
+    alignas(16) double Paug[64];    // cost-to-go Hessian of stage k+1
+    alignas(16) double Gt[64];      // Gt[j][a] = (Paug A~)(a, j),  A~ = [A B; 0 I]
+    alignas(16) double S[64];       // A~' Paug A~ + stage Hessian
+    alignas(16) double pb[2][8];    // cost-to-go gradient (px | pv), double buffered
+    alignas(16) double pi[2][8];    // costate (6 used), double buffered
+    double hv[8];                   // h~ = r~ + A~' p
     // --- terminal block ---
-    double Wm[36], Wi[36];
-    double sbar[6], c1[6], yT[6], dyT[6];
+    double Wm[TM], Wi[TM];
+    double sbar[6], yT[6];
     int flag;
 };
 
@@ -163,6 +169,31 @@ struct SolveInfo {
 LMPC_HD double dot6(const double* a, const double* b) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
 }
+// dot product of two contiguous, 16 B-aligned 6-vectors in shared memory (three LDS.128 per operand)
+LMPC_HD double dot6v(const double* a, const double* b) {
+#if defined(__CUDA_ARCH__)
+    const double2 a0 = *reinterpret_cast<const double2*>(a), a1 = *reinterpret_cast<const double2*>(a + 2),
+                  a2 = *reinterpret_cast<const double2*>(a + 4);
+    const double2 b0 = *reinterpret_cast<const double2*>(b), b1 = *reinterpret_cast<const double2*>(b + 2),
+                  b2 = *reinterpret_cast<const double2*>(b + 4);
+    return (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
+#else
+    return (a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3]) + (a[4] * b[4] + a[5] * b[5]);
+#endif
+}
+LMPC_HD double rsqrt_f64(double v) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(v);
+#else
+    return 1.0 / sqrt(v);
+#endif
+}
+// (i, j), i <= j, of the e-th entry of the upper triangle of an 8 x 8 matrix (row-wise)
+LMPC_HD void tri8(int e, int& i, int& j) {
+    i = 0;
+    while (e >= 8 - i) { e -= 8 - i; ++i; }
+    j = e + i;
+}
 LMPC_HD double step_bound(double v, double dv, double a) {
     // largest alpha keeping v + alpha dv >= 0
     return (dv < 0.0) ? fmin(a, -v / dv) : a;
@@ -174,6 +205,7 @@ struct Pdip {
     using RG = Regs<N, M, NCX, NCU>;
     static constexpr int R1 = N * NCX, R2 = N * NCU, R4 = (M > 0 ? M : 1);
     static constexpr bool LMPC = (M > 0);
+    static constexpr int TMW = (M > 0 ? 36 : 1);
 
     // ---------------------------------------------------------------- initial point ------
     static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0) {
@@ -186,12 +218,26 @@ struct Pdip {
         }
         FOR_LANES(e, N * 2) w.u[e] = tau * w.uOld[e & 1];
         FOR_LANES(e, 6) w.x[e] = x0[e];
+        FOR_LANES(k, N) {               // transpose A and B in place: ABC[k][j*6+c] = [A B](c, j)
+            double* A = &w.ABC[k][0];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a + 1; b < 6; ++b) { double t = A[a * 6 + b]; A[a * 6 + b] = A[b * 6 + a]; A[b * 6 + a] = t; }
+            double bt[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) bt[e] = A[36 + e];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) { A[36 + cc] = bt[cc * 2]; A[42 + cc] = bt[cc * 2 + 1]; }
+        }
         wsync();
         for (int k = 0; k < N; ++k) {   // roll the model out (dynamics hold from the start)
             FOR_LANES(a, 6) {
-                const double* A = &w.ABC[k][a * 6];
-                const double* B = &w.ABC[k][36 + a * 2];
-                w.x[(k + 1) * 6 + a] = dot6(A, &w.x[k * 6]) + B[0] * w.u[k * 2] + B[1] * w.u[k * 2 + 1] + w.ABC[k][48 + a];
+                const double* T = &w.ABC[k][0];
+                double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
+#pragma unroll
+                for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];
+                w.x[(k + 1) * 6 + a] = v;
             }
             wsync();
         }
@@ -363,17 +409,21 @@ struct Pdip {
     }
 
     // ---------------------------------------------------------------- backward sweeps ----
-    // Start of a backward sweep: terminal cost-to-go into (Pxx,Pxv,Pvv | pb[0]) and pi_N.
+    // Start of a backward sweep: terminal cost-to-go into (Paug | pb[N&1]) and pi_N.
     template <bool FACTOR>
     static LMPC_HD void backward_start(W& w, const FtocpConst& c, const double* c1) {
         if (FACTOR) {
-            FOR_LANES(e, 36) w.Pxx[e] = c.Qf2[e] + (LMPC ? w.Wi[e] : 0.0);
-            FOR_LANES(e, 12) w.Pxv[e] = 0.0;
-            FOR_LANES(e, 3) w.Pvv[e] = 0.0;
-            FOR_LANES(a, 6) {   // pi_N = -(Qf2 x_N + qxN + yT)
-                double v = c.qxN[a] + (LMPC ? w.yT[a] : 0.0);
+            FOR_LANES(e, 64) {
+                const int i = e >> 3, j = e & 7;
+                w.Paug[e] = (i < 6 && j < 6) ? c.Qf2[i * 6 + j] + (LMPC ? w.Wi[(i * 6 + j) % TMW] : 0.0) : 0.0;
+            }
+            FOR_LANES(a, 8) {   // pi_N = -(Qf2 x_N + qxN + yT)
+                double v = 0.0;
+                if (a < 6) {
+                    v = c.qxN[a] + (LMPC ? w.yT[a] : 0.0);
 #pragma unroll
-                for (int b = 0; b < 6; ++b) v += c.Qf2[a * 6 + b] * w.x[N * 6 + b];
+                    for (int b = 0; b < 6; ++b) v += c.Qf2[a * 6 + b] * w.x[N * 6 + b];
+                }
                 w.pi[N & 1][a] = -v;
             }
         }
@@ -381,137 +431,161 @@ struct Pdip {
             double v = 0.0;
             if (LMPC && a < 6) {
 #pragma unroll
-                for (int b = 0; b < 6; ++b) v += w.Wi[a * 6 + b] * c1[b];
+                for (int b = 0; b < 6; ++b) v += w.Wi[(a * 6 + b) % TMW] * c1[b];
             }
             w.pb[N & 1][a] = v;
         }
         wsync();
     }
 
-    static LMPC_HD double rtx(const W& w, const FtocpConst& c, int k, int a) {
+    // Stage gradients for the costate / input-residual recursion (embarrassingly parallel over stages).
+    static LMPC_HD void stage_gradients(W& w, const FtocpConst& c) {
+        FOR_LANES(e, N * 8) {
+            const int k = e >> 3, j = e & 7;
+            double v;
+            if (j < 6) {
+                v = c.qx[j];
+#pragma unroll
+                for (int b = 0; b < 6; ++b) v += c.Q2[j * 6 + b] * w.x[k * 6 + b];
+#pragma unroll
+                for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + j] * w.nu1s[k * NCX + i];
+            } else {
+                const int r = j - 6;
+                const double uk = w.u[k * 2 + r];
+                const double up = (k == 0) ? w.uOld[r] : w.u[(k - 1) * 2 + r];
+                v = c.R2[r * 2] * w.u[k * 2] + c.R2[r * 2 + 1] * w.u[k * 2 + 1] + c.dR2[r] * (uk - up);
+                if (k < N - 1) v += c.dR2[r] * (uk - w.u[(k + 1) * 2 + r]);
+#pragma unroll
+                for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.nu2s[k * NCU + jj];
+            }
+            w.gst[k][j] = v;
+        }
+    }
+
+    // r~_k: right-hand side contribution of the eliminated inequality rows (state part j < 6, input part r < 2)
+    static LMPC_HD double rhs_x(const W& w, const FtocpConst& c, int k, int j) {
         double v = 0.0;
 #pragma unroll
-        for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + a] * w.ex[k * NCX + i];
+        for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + j] * w.ex[k * NCX + i];
         return v;
     }
-    static LMPC_HD double fu_t(const FtocpConst& c, const double* row, int r) {
+    static LMPC_HD double rhs_u(const W& w, const FtocpConst& c, int k, int r) {
         double v = 0.0;
 #pragma unroll
-        for (int j = 0; j < NCU; ++j) v += c.Fu[j * 2 + r] * row[j];
+        for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.eu[k * NCU + jj];
         return v;
     }
 
-    // Factorising backward sweep: Riccati matrices, gradient recursion for the predictor
-    // right-hand side and the costate / input-residual recursion, four phases per stage.
+    // work item e < 36 of phase b/e: entry (i, j), i <= j, of the 8 x 8 stage matrix and its constant data
+    static constexpr int KF = (NCX > NCU ? NCX : NCU);
+    struct SEnt {
+        int i, j, cls;       // class 0 = state-state, 1 = input-state, 2 = input-input
+        double kq, kf[KF];
+    };
+    static LMPC_HD void s_entry(const FtocpConst& c, int e, SEnt& q) {
+        q.i = q.j = 0; q.cls = 1; q.kq = 0.0;
+#pragma unroll
+        for (int z = 0; z < KF; ++z) q.kf[z] = 0.0;
+        if (e >= 36) return;
+        tri8(e, q.i, q.j);
+        if (q.j < 6) {
+            q.cls = 0;
+            q.kq = c.Q2[q.i * 6 + q.j];
+#pragma unroll
+            for (int z = 0; z < NCX; ++z) q.kf[z] = c.Fx[z * 6 + q.i] * c.Fx[z * 6 + q.j];
+        } else if (q.i >= 6) {
+            q.cls = 2;
+            q.kq = c.R2[(q.i - 6) * 2 + (q.j - 6)];
+#pragma unroll
+            for (int z = 0; z < NCU; ++z) q.kf[z] = c.Fu[z * 2 + (q.i - 6)] * c.Fu[z * 2 + (q.j - 6)];
+        }
+    }
+
+    // Factorising backward sweep on the augmented state (x, v): Riccati matrices, gradient recursion for the
+    // predictor right-hand side and the costate / input-residual recursion.  Four uniform phases per stage.
     static LMPC_HD double backward_factor(W& w, const FtocpConst& c) {
         double ru_max = 0.0;
+        // loop-invariant per-lane work assignment, cached in registers on the device (2 items per lane)
+        constexpr bool CACHED = (LMPC_NLANE == 32);
+        SEnt se[CACHED ? 2 : 1];
+        if (CACHED) {
+            s_entry(c, LMPC_LANE, se[0]);
+            s_entry(c, LMPC_LANE + 32, se[CACHED ? 1 : 0]);
+        }
         for (int k = N - 1; k >= 0; --k) {
-            const double* A = &w.ABC[k][0];
-            const double* B = &w.ABC[k][36];
-            const double* pn = w.pb[(k + 1) & 1];    // px | pv of stage k+1
-            const double* pin = w.pi[(k + 1) & 1];   // pi_{k+1}
-            // ---- phase a: G = Pxx [A B]
-            FOR_LANES(e, 48) {
-                int a = e >> 3, j = e & 7;
-                double v = 0.0;
-                if (j < 6) {
-#pragma unroll
-                    for (int b = 0; b < 6; ++b) v += w.Pxx[a * 6 + b] * A[b * 6 + j];
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 6; ++b) v += w.Pxx[a * 6 + b] * B[b * 2 + (j - 6)];
-                }
-                w.G[e] = v;
+            const double* T = &w.ABC[k][0];           // T[j*6 + c] = [A B](c, j)
+            const double* pn = w.pb[(k + 1) & 1];     // px | pv of stage k+1
+            const double* pin = w.pi[(k + 1) & 1];    // pi_{k+1}
+            // ---- phase a: Gt[j][a] = (Paug A~)(a, j)
+            FOR_LANES(e, 64) {
+                const int j = e >> 3, a = e & 7;
+                double v = dot6v(&T[j * 6], &w.Paug[a * 8]);
+                if (j >= 6) v += w.Paug[a * 8 + j];
+                w.Gt[e] = v;
             }
             wsync();
-            // ---- phase b: stage matrix blocks, gradient pieces, costate
-            FOR_LANES(e, 21 + 12 + 3 + 2 + 6 + 6) {
-                if (e < 21) {                      // Sx(a,b), a <= b
-                    int a = 0, b = e;
-                    while (b >= 6 - a) { b -= 6 - a; ++a; }
-                    b += a;
-                    double v = c.Q2[a * 6 + b];
-#pragma unroll
-                    for (int i = 0; i < NCX; ++i) v += w.Dt[k * NCX + i] * c.Fx[i * 6 + a] * c.Fx[i * 6 + b];
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) v += A[cc * 6 + a] * w.G[cc * 8 + b];
-                    w.Sx[a * 6 + b] = v;
-                    w.Sx[b * 6 + a] = v;
-                } else if (e < 33) {               // Y(r,b) = B'G_A + Pxv'A
-                    int r = (e - 21) / 6, b = (e - 21) % 6;
-                    double v = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) v += B[cc * 2 + r] * w.G[cc * 8 + b] + w.Pxv[cc * 2 + r] * A[cc * 6 + b];
-                    w.Y[r * 6 + b] = v;
-                } else if (e < 36) {               // Lam: (0,0), (1,0), (1,1)
-                    int idx = e - 33;
-                    int r = (idx == 0) ? 0 : 1, q = (idx == 2) ? 1 : 0;
-                    double v = c.R2[r * 2 + q] + w.Pvv[idx];
-                    if (r == q) v += ((k < N - 1) ? 2.0 : 1.0) * c.dR2[r];
-#pragma unroll
-                    for (int j = 0; j < NCU; ++j) v += w.d2[k * NCU + j] * c.Fu[j * 2 + r] * c.Fu[j * 2 + q];
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc)
-                        v += B[cc * 2 + r] * w.G[cc * 8 + 6 + q] + B[cc * 2 + r] * w.Pxv[cc * 2 + q] + w.Pxv[cc * 2 + r] * B[cc * 2 + q];
-                    w.Lam[idx] = v;
-                } else if (e < 38) {               // ru_k(r) and g0(r)
-                    int r = e - 36;
-                    double uk = w.u[k * 2 + r];
-                    double up = (k == 0) ? w.uOld[r] : w.u[(k - 1) * 2 + r];
-                    double v = c.R2[r * 2] * w.u[k * 2] + c.R2[r * 2 + 1] * w.u[k * 2 + 1] + c.dR2[r] * (uk - up);
-                    if (k < N - 1) v += c.dR2[r] * (uk - w.u[(k + 1) * 2 + r]);
-                    v += fu_t(c, &w.nu2s[k * NCU], r);
-                    double bp = 0.0, bpi = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) { bp += B[cc * 2 + r] * pn[cc]; bpi += B[cc * 2 + r] * pin[cc]; }
-                    v -= bpi;
-                    w.ru[k][r] = v;
-                    w.g0[r] = v + fu_t(c, &w.eu[k * NCU], r) + bp + pn[6 + r];
-                } else if (e < 44) {               // hx(a) = rtx + A'px
-                    int a = e - 38;
-                    double v = rtx(w, c, k, a);
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) v += A[cc * 6 + a] * pn[cc];
-                    w.hx[a] = v;
-                } else {                           // pi_k(a)
-                    int a = e - 44;
-                    double v = c.qx[a];
-#pragma unroll
-                    for (int b = 0; b < 6; ++b) v += c.Q2[a * 6 + b] * w.x[k * 6 + b];
-#pragma unroll
-                    for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + a] * w.nu1s[k * NCX + i];
-                    double t = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) t += A[cc * 6 + a] * pin[cc];
-                    w.pi[k & 1][a] = t - v;
-                }
-            }
-            wsync();
-            // ---- phase c/d: 2x2 Cholesky (lane redundant), Z, Zv, z0
+            // ---- phase b: S = A~' G~ + stage Hessian (36 entries), then the vector recursions (8 items)
             {
-                double l00s = w.Lam[0], l10 = w.Lam[1], l11s = w.Lam[2];
+                int t = 0;
+                FOR_LANES(e, 44) {
+                    if (e < 36) {
+                        SEnt qq;
+                        if (!CACHED) s_entry(c, e, qq);
+                        const SEnt& q = CACHED ? se[t] : qq;
+                        const int i = q.i, j = q.j;
+                        double v = dot6v(&T[i * 6], &w.Gt[j * 8]);
+                        if (i >= 6) v += w.Gt[j * 8 + i];
+                        if (q.cls == 0) {
+                            v += q.kq;
+#pragma unroll
+                            for (int z = 0; z < NCX; ++z) v += w.Dt[k * NCX + z] * q.kf[z];
+                        } else if (q.cls == 2) {
+                            v += q.kq;
+                            if (i == j) v += ((k < N - 1) ? 2.0 : 1.0) * c.dR2[i - 6];
+#pragma unroll
+                            for (int z = 0; z < NCU; ++z) v += w.d2[k * NCU + z] * q.kf[z];
+                        }
+                        w.S[i * 8 + j] = v;
+                        w.S[j * 8 + i] = v;
+                    } else {
+                        const int j = e - 36;                       // 0..7
+                        const double hp = dot6v(&T[j * 6], pn);     // A~' p
+                        const double tp = dot6v(&T[j * 6], pin);    // A~' pi
+                        if (j < 6) {
+                            w.hv[j] = rhs_x(w, c, k, j) + hp;
+                            w.pi[k & 1][j] = tp - w.gst[k][j];
+                        } else {
+                            const double ru = w.gst[k][j] - tp;
+                            w.ru[k][j - 6] = ru;
+                            w.hv[j] = ru + rhs_u(w, c, k, j - 6) + hp + pn[j];
+                        }
+                    }
+                    ++t;
+                }
+            }
+            wsync();
+            // ---- phase c/d: 2x2 Cholesky (lane redundant), Z~, z0
+            {
+                double l00s = w.S[6 * 8 + 6], l10 = w.S[7 * 8 + 6], l11s = w.S[7 * 8 + 7];
                 bool bad = !(l00s > 0.0);
                 if (bad) l00s = 1.0;
-                double i00 = 1.0 / sqrt(l00s);
+                const double i00 = rsqrt_f64(l00s);
                 l10 *= i00;
-                double t = l11s - l10 * l10;
-                if (!(t > 0.0)) { bad = true; t = 1.0; }
-                double i11 = 1.0 / sqrt(t);
+                double tt = l11s - l10 * l10;
+                if (!(tt > 0.0)) { bad = true; tt = 1.0; }
+                const double i11 = rsqrt_f64(tt);
                 ru_max = fmax(ru_max, fmax(fabs(w.ru[k][0]), fabs(w.ru[k][1])));
-                FOR_LANES(e, 8) {
-                    if (e < 6) {
-                        double z0c = w.Y[e] * i00;
-                        w.Z[k][e] = z0c;
-                        w.Z[k][6 + e] = (w.Y[6 + e] - l10 * z0c) * i11;
-                    } else if (e == 6) {
-                        double a0 = w.g0[0] * i00;
-                        w.z0[k][0] = a0;
-                        w.z0[k][1] = (w.g0[1] - l10 * a0) * i11;
+                FOR_LANES(j, 9) {
+                    if (j < 8) {
+                        const double y0 = (j < 6) ? w.S[6 * 8 + j] : (j == 6 ? -c.dR2[0] : 0.0);
+                        const double y1 = (j < 6) ? w.S[7 * 8 + j] : (j == 7 ? -c.dR2[1] : 0.0);
+                        const double z0c = y0 * i00;
+                        w.Zt[k][j] = z0c;
+                        w.Zt[k][8 + j] = (y1 - l10 * z0c) * i11;
                     } else {
-                        double zv00 = c.dR2[0] * i00;
-                        w.Zv[k][0] = zv00;
-                        w.Zv[k][1] = -l10 * zv00 * i11;
-                        w.Zv[k][2] = c.dR2[1] * i11;
+                        const double a0 = w.hv[6] * i00;
+                        w.z0[k][0] = a0;
+                        w.z0[k][1] = (w.hv[7] - l10 * a0) * i11;
                         w.Li[k][0] = i00;
                         w.Li[k][1] = l10;
                         w.Li[k][2] = i11;
@@ -520,27 +594,26 @@ struct Pdip {
                 }
             }
             wsync();
-            // ---- phase e: cost-to-go of stage k
+            // ---- phase e: cost-to-go of stage k: Paug = [Sxx 0; 0 0] - Z~'Z~ ; p = [hx; 0] - Z~' z0
             {
-                const double* Z = w.Z[k];
-                const double zv00 = w.Zv[k][0], zv10 = w.Zv[k][1], zv11 = w.Zv[k][2];
+                const double* Z = w.Zt[k];
                 const double a0 = w.z0[k][0], a1 = w.z0[k][1];
                 double* po = w.pb[k & 1];
-                FOR_LANES(e, 36 + 12 + 3 + 8) {
+                int t = 0;
+                FOR_LANES(e, 44) {
                     if (e < 36) {
-                        int a = e / 6, b = e % 6;
-                        w.Pxx[e] = w.Sx[e] - Z[a] * Z[b] - Z[6 + a] * Z[6 + b];
-                    } else if (e < 48) {
-                        int a = (e - 36) >> 1, q = (e - 36) & 1;
-                        w.Pxv[e - 36] = (q == 0) ? (Z[a] * zv00 + Z[6 + a] * zv10) : (Z[6 + a] * zv11);
-                    } else if (e < 51) {
-                        int idx = e - 48;
-                        w.Pvv[idx] = (idx == 0) ? -(zv00 * zv00 + zv10 * zv10) : (idx == 1 ? -(zv10 * zv11) : -(zv11 * zv11));
+                        SEnt qq;
+                        if (!CACHED) s_entry(c, e, qq);
+                        const SEnt& q = CACHED ? se[t] : qq;
+                        const int i = q.i, j = q.j;
+                        const double v = ((q.cls == 0) ? w.S[i * 8 + j] : 0.0) - Z[i] * Z[j] - Z[8 + i] * Z[8 + j];
+                        w.Paug[i * 8 + j] = v;
+                        w.Paug[j * 8 + i] = v;
                     } else {
-                        int a = e - 51;
-                        if (a < 6) po[a] = w.hx[a] - Z[a] * a0 - Z[6 + a] * a1;
-                        else po[a] = (a == 6) ? (zv00 * a0 + zv10 * a1) : (zv11 * a1);
+                        const int a = e - 36;
+                        po[a] = ((a < 6) ? w.hv[a] : 0.0) - Z[a] * a0 - Z[8 + a] * a1;
                     }
+                    ++t;
                 }
             }
             wsync();
@@ -551,33 +624,19 @@ struct Pdip {
     // Gradient-only backward sweep for a new right-hand side (corrector), one phase per stage.
     static LMPC_HD void backward_rhs(W& w, const FtocpConst& c) {
         for (int k = N - 1; k >= 0; --k) {
-            const double* A = &w.ABC[k][0];
-            const double* B = &w.ABC[k][36];
+            const double* T = &w.ABC[k][0];
             const double* pn = w.pb[(k + 1) & 1];
             double* po = w.pb[k & 1];
             double g0[2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                double v = w.ru[k][r] + fu_t(c, &w.eu[k * NCU], r) + pn[6 + r];
-#pragma unroll
-                for (int cc = 0; cc < 6; ++cc) v += B[cc * 2 + r] * pn[cc];
-                g0[r] = v;
-            }
+            for (int r = 0; r < 2; ++r) g0[r] = w.ru[k][r] + rhs_u(w, c, k, r) + pn[6 + r] + dot6v(&T[(6 + r) * 6], pn);
             const double a0 = g0[0] * w.Li[k][0];
             const double a1 = (g0[1] - w.Li[k][1] * a0) * w.Li[k][2];
             FOR_LANES(a, 8) {
-                if (a < 6) {
-                    double v = rtx(w, c, k, a);
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) v += A[cc * 6 + a] * pn[cc];
-                    po[a] = v - w.Z[k][a] * a0 - w.Z[k][6 + a] * a1;
-                } else if (a == 6) {
-                    po[6] = w.Zv[k][0] * a0 + w.Zv[k][1] * a1;
-                    w.z0[k][0] = a0;
-                } else {
-                    po[7] = w.Zv[k][2] * a1;
-                    w.z0[k][1] = a1;
-                }
+                double v = 0.0;
+                if (a < 6) v = rhs_x(w, c, k, a) + dot6v(&T[a * 6], pn);
+                po[a] = v - w.Zt[k][a] * a0 - w.Zt[k][8 + a] * a1;
+                if (a >= 6) w.z0[k][a - 6] = (a == 6) ? a0 : a1;
             }
             wsync();
         }
@@ -589,19 +648,22 @@ struct Pdip {
         wsync();
         double dv0 = 0.0, dv1 = 0.0;
         for (int k = 0; k < N; ++k) {
-            const double* A = &w.ABC[k][0];
-            const double* B = &w.ABC[k][36];
-            const double* Z = w.Z[k];
+            const double* T = &w.ABC[k][0];
+            const double* Z = w.Zt[k];
             const double* d = &w.dx[k * 6];
-            double t0 = w.z0[k][0] - w.Zv[k][0] * dv0;
-            double t1 = w.z0[k][1] - w.Zv[k][1] * dv0 - w.Zv[k][2] * dv1;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) { t0 += Z[b] * d[b]; t1 += Z[6 + b] * d[b]; }
+            const double t0 = w.z0[k][0] + dot6v(Z, d) + Z[6] * dv0 + Z[7] * dv1;
+            const double t1 = w.z0[k][1] + dot6v(Z + 8, d) + Z[14] * dv0 + Z[15] * dv1;
             const double du1 = -t1 * w.Li[k][2];
             const double du0 = (-t0 - w.Li[k][1] * du1) * w.Li[k][0];
             FOR_LANES(a, 8) {
-                if (a < 6) w.dx[(k + 1) * 6 + a] = dot6(&A[a * 6], d) + B[a * 2] * du0 + B[a * 2 + 1] * du1;
-                else w.du[k * 2 + (a - 6)] = (a == 6) ? du0 : du1;
+                if (a < 6) {
+                    double v = T[36 + a] * du0 + T[42 + a] * du1;
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * d[b];
+                    w.dx[(k + 1) * 6 + a] = v;
+                } else {
+                    w.du[k * 2 + (a - 6)] = (a == 6) ? du0 : du1;
+                }
             }
             dv0 = du0;
             dv1 = du1;
@@ -694,6 +756,7 @@ struct Pdip {
             comp = wsum(comp);
             mu = comp / n_ineq;
             // ---- factorising backward sweep (also yields the input residual) ------------------
+            stage_gradients(w, c);
             backward_start<true>(w, c, c1);
             double ru_max = backward_factor(w, c);
             r_dual = fmax(wmax(rd_loc), ru_max);
@@ -869,10 +932,11 @@ struct Pdip {
         double rdyn = 0.0;
         FOR_LANES(e, N * 6) {
             int k = e / 6, a = e % 6;
-            const double* A = &w.ABC[k][a * 6];
-            const double* B = &w.ABC[k][36 + a * 2];
-            double v = w.x[(k + 1) * 6 + a] - (dot6(A, &w.x[k * 6]) + B[0] * w.u[k * 2] + B[1] * w.u[k * 2 + 1] + w.ABC[k][48 + a]);
-            rdyn = fmax(rdyn, fabs(v));
+            const double* T = &w.ABC[k][0];
+            double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
+#pragma unroll
+            for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];
+            rdyn = fmax(rdyn, fabs(w.x[(k + 1) * 6 + a] - v));
         }
         r_prim = fmax(r_prim, wmax(rdyn));
         info.status = status;
