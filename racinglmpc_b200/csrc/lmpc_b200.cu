@@ -78,7 +78,7 @@ struct KernelSmem {
 };
 
 template <int N, int M, int NCX, int NCU>
-__global__ void __launch_bounds__(32) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
+__global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 12 : 16) : 1)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using KS = KernelSmem<N, M, NCX, NCU>;
     KS& ks = *reinterpret_cast<KS*>(smem_raw);
