@@ -118,10 +118,11 @@ struct Work {
     alignas(16) double x[(N + 1) * 6];
     alignas(16) double dx[(N + 1) * 6];
     double u[N * 2], du[N * 2];
+    // (dx also stages nu1 | nu2 for the stage-gradient pre-pass: it is dead between the update and the next forward sweep)
+    static_assert(N * (NCX + NCU) <= (N + 1) * 6, "staging area too small");
     // --- per-row quantities shared between lanes ---
     double Dt[N * NCX], ex[N * NCX];  // condensed lane-constraint Hessian weights / rhs
     double d2[N * NCU], eu[N * NCU];  // input-bound Hessian weights / rhs
-    double nu1s[N * NCX], nu2s[N * NCU];  // multipliers staged for the stage-gradient pre-pass
     double d4i[MM];                   // 1 / max(nu4/lam, d4_min)
     // --- Riccati factor, per stage ---
     alignas(16) double Zt[N][16];   // Z~ = L^-1 [ (B'Pxx+Pxv')A | -diag(dR2) ]  (2 x 8, row major)
@@ -130,8 +131,9 @@ struct Work {
     double ru[N][2];                // input-stationarity residual
     alignas(16) double gst[N][8];   // stage gradient: (2Q x + qx + Fx'nu1 | 2R u + rate + Fu'nu2)
     // --- sweep scratch (augmented state (x, v = previous input), 8 x 8) ---
-    alignas(16) double Paug[64];    // cost-to-go Hessian of stage k+1
-    alignas(16) double Gt[64];      // Gt[j][a] = (Paug A~)(a, j),  A~ = [A B; 0 I]
+    static constexpr int PS = 10;   // padded row stride of Paug / Gt (80 B: the 8 rows hit distinct 16 B bank groups)
+    alignas(16) double Paug[8 * PS];  // cost-to-go Hessian of stage k+1
+    alignas(16) double Gt[8 * PS];    // Gt[j][a] = (Paug A~)(a, j),  A~ = [A B; 0 I]
     alignas(16) double S[64];       // A~' Paug A~ + stage Hessian
     alignas(16) double pb[2][8];    // cost-to-go gradient (px | pv), double buffered
     alignas(16) double pi[2][8];    // costate (6 used), double buffered
@@ -206,6 +208,7 @@ struct Pdip {
     static constexpr int R1 = N * NCX, R2 = N * NCU, R4 = (M > 0 ? M : 1);
     static constexpr bool LMPC = (M > 0);
     static constexpr int TMW = (M > 0 ? 36 : 1);
+    static constexpr int PS = W::PS;
 
     // ---------------------------------------------------------------- initial point ------
     static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0) {
@@ -415,7 +418,7 @@ struct Pdip {
         if (FACTOR) {
             FOR_LANES(e, 64) {
                 const int i = e >> 3, j = e & 7;
-                w.Paug[e] = (i < 6 && j < 6) ? c.Qf2[i * 6 + j] + (LMPC ? w.Wi[(i * 6 + j) % TMW] : 0.0) : 0.0;
+                w.Paug[i * PS + j] = (i < 6 && j < 6) ? c.Qf2[i * 6 + j] + (LMPC ? w.Wi[(i * 6 + j) % TMW] : 0.0) : 0.0;
             }
             FOR_LANES(a, 8) {   // pi_N = -(Qf2 x_N + qxN + yT)
                 double v = 0.0;
@@ -448,7 +451,7 @@ struct Pdip {
 #pragma unroll
                 for (int b = 0; b < 6; ++b) v += c.Q2[j * 6 + b] * w.x[k * 6 + b];
 #pragma unroll
-                for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + j] * w.nu1s[k * NCX + i];
+                for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + j] * w.dx[k * NCX + i];
             } else {
                 const int r = j - 6;
                 const double uk = w.u[k * 2 + r];
@@ -456,7 +459,7 @@ struct Pdip {
                 v = c.R2[r * 2] * w.u[k * 2] + c.R2[r * 2 + 1] * w.u[k * 2 + 1] + c.dR2[r] * (uk - up);
                 if (k < N - 1) v += c.dR2[r] * (uk - w.u[(k + 1) * 2 + r]);
 #pragma unroll
-                for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.nu2s[k * NCU + jj];
+                for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.dx[N * NCX + k * NCU + jj];
             }
             w.gst[k][j] = v;
         }
@@ -519,9 +522,9 @@ struct Pdip {
             // ---- phase a: Gt[j][a] = (Paug A~)(a, j)
             FOR_LANES(e, 64) {
                 const int j = e >> 3, a = e & 7;
-                double v = dot6v(&T[j * 6], &w.Paug[a * 8]);
-                if (j >= 6) v += w.Paug[a * 8 + j];
-                w.Gt[e] = v;
+                double v = dot6v(&T[j * 6], &w.Paug[a * PS]);
+                if (j >= 6) v += w.Paug[a * PS + j];
+                w.Gt[j * PS + a] = v;
             }
             wsync();
             // ---- phase b: S = A~' G~ + stage Hessian (36 entries), then the vector recursions (8 items)
@@ -533,8 +536,8 @@ struct Pdip {
                         if (!CACHED) s_entry(c, e, qq);
                         const SEnt& q = CACHED ? se[t] : qq;
                         const int i = q.i, j = q.j;
-                        double v = dot6v(&T[i * 6], &w.Gt[j * 8]);
-                        if (i >= 6) v += w.Gt[j * 8 + i];
+                        double v = dot6v(&T[i * 6], &w.Gt[j * PS]);
+                        if (i >= 6) v += w.Gt[j * PS + i];
                         if (q.cls == 0) {
                             v += q.kq;
 #pragma unroll
@@ -607,8 +610,8 @@ struct Pdip {
                         const SEnt& q = CACHED ? se[t] : qq;
                         const int i = q.i, j = q.j;
                         const double v = ((q.cls == 0) ? w.S[i * 8 + j] : 0.0) - Z[i] * Z[j] - Z[8 + i] * Z[8 + j];
-                        w.Paug[i * 8 + j] = v;
-                        w.Paug[j * 8 + i] = v;
+                        w.Paug[i * PS + j] = v;
+                        w.Paug[j * PS + i] = v;
                     } else {
                         const int a = e - 36;
                         po[a] = ((a < 6) ? w.hv[a] : 0.0) - Z[a] * a0 - Z[8 + a] * a1;
@@ -725,7 +728,7 @@ struct Pdip {
                 w.Dt[row] = d1 * (c.qs2 + d3) / hs;
                 // predictor: rc1 = w1 nu1, rc3 = s nu3  ->  e1 = -nu1, rs + rc3/s = rs + nu3
                 w.ex[row] = (-g.nu1[r] * (c.qs2 + d3) + d1 * (rs + g.nu3[r])) / hs;
-                w.nu1s[row] = g.nu1[r];
+                w.dx[row] = g.nu1[r];
             }
             FOR_SLOTS(r, row, R2) {
                 int k = row / NCU, j = row % NCU;
@@ -734,7 +737,7 @@ struct Pdip {
                 comp += w2 * g.nu2[r];
                 w.d2[row] = g.nu2[r] / w2;
                 w.eu[row] = -g.nu2[r];           // predictor: -rc2/w2
-                w.nu2s[row] = g.nu2[r];
+                w.dx[N * NCX + row] = g.nu2[r];
             }
             double rone = 0.0, delta = 1.0, beta = 0.0, c1[6] = {0, 0, 0, 0, 0, 0};
             if (LMPC) {
