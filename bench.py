@@ -313,6 +313,138 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# configs[2]: full LMPC steps (K1 k-NN regression -> K2 safe-set selection -> QP -> shift), per-instance 5-lap safe sets
+# ----------------------------------------------------------------------------------------------
+def run_lmpc_steps(args):
+    import torch
+    import torch.distributed as dist
+    from racinglmpc_b200 import workloads, reference_params as rp
+    from racinglmpc_b200.controller import BatchedController
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, N = args.batch, HORIZON
+    seg = workloads.track_seg_table()      # Map.PointAndTangent[:,3:6] from the reference-pinned fixture
+    data = workloads.lmpc_batch(B, seed=2 + rank)
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    c = BatchedController(par, B, seg, rp.TRACK_LENGTH, trToUse=5, numSS_Points=numSS_Points, numSS_it=numSS_it,
+                          QterminalSlack=Qts, device=local, Tmax=1280, ss_cap=5, model_cap=5)
+    workloads.restore_lmpc_batch(c, data)
+    stream = torch.cuda.ExternalStream(c.stream, device=dev)
+    d_x0 = torch.from_numpy(data["x0"]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    state = dict(xLin=data["xLin"], uLin=data["uLin"], zt=data["zt"], OldInput=data["OldInput"],
+                 timeStep=data["t"].astype(np.int32), has_pred=np.ones(B, np.int32), xPred=data["xPred"])
+
+    def reset():
+        c.set_state(**state)      # every timed step solves the same controller states (untimed host upload)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        reset(); c.step_dev(d_x0); c.sync()
+    l0 = c.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        reset()
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            ev[i][0].record(stream)
+            c.step_dev(d_x0)
+            ev[i][1].record(stream)
+        c.sync()
+    launches = c.kernel_launches - l0
+    torch.cuda.synchronize()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot = float(tot.item())
+    # e2e: host x0 in, results out through the public API
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_x0 = pin(data["x0"])
+    out = {k: pin(v) for k, v in c.alloc_step_outputs().items()}
+    reset(); c.step(h_x0, out=out, want_ss=False)
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c.step(h_x0, out=out, want_ss=False)
+        t_e2e += time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    ok = float(np.mean((out["status"] == 1) & (out["flags"] == 0)))
+    if rank == 0:
+        rows_model = sum(l[0].shape[0] for l in data["model_laps"][0])
+        rows_ss = sum(l[0].shape[0] for l in data["ss_laps"][0])
+        algo = rows_model * 64 + rows_ss * 48 + (656 + 106) * 8 + 5760
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ms = tot / args.steps
+        ach = B * algo / (ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": B * world * args.steps / (tot * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "configs[2]: batch=%d full LMPC steps (k-NN LTV regression over a 5-lap store, 4-lap sampled safe set, "
+                                       "180 vars / 229 rows QP), N=12" % B, "batch_per_gpu": B,
+                           "l2": "flushed between timed steps (256 MiB memset on the same stream)", "solved_fraction": ok,
+                           "ipm_iters_mean": float(out["iters"].mean()), "ipm_iters_max": int(out["iters"].max()),
+                           "kernels_per_step": "knn_ltv_regress, ss_select, ftocp_kernel<12,48>, shift_state"},
+                "clocks": clocks,
+                "e2e": {"value": B * world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h_x0.nbytes),
+                        "d2h_bytes_per_step": int(sum(out[k].nbytes for k in ("xPred", "uPred", "lambd", "zt", "zt_u", "status", "iters", "resid", "flags")))},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "kernel": "whole step (4 kernels)", "algorithmic_bytes_per_solve": algo}}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = lmpc_cpu_baseline(data)
+        print(json.dumps(line))
+    c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def lmpc_cpu_baseline(data, nsample=24):
+    """The reference's own way: one Python controller, one QP at a time (PC.py:110-137), restated by the oracle and
+    solved by the OSQP-algorithm port with the reference's settings."""
+    from oracle import ftocp, ltv_model, osqp_port
+    from oracle.track import TrackTable
+    trk = TrackTable()
+    numSS_it, numSS_Points, _, _, Qts, par = ftocp.lmpc_params(trk, HORIZON)
+    par.timeVarying = True
+    ctrls = []
+    for b in range(nsample):
+        pm = ltv_model.LocalLTVModel(6, 2, trk, 5)
+        pm.xStored = [lx for lx, _ in data["model_laps"][b]]
+        pm.uStored = [lu for _, lu in data["model_laps"][b]]
+        pm.lapTime = [lx.shape[0] for lx in pm.xStored]
+        lm = ftocp.OracleLMPC(numSS_Points, numSS_it, Qts, par, pm, qp=osqp_port.reference_qp)
+        lm.SS = [s[0] for s in data["ss_laps"][b]]; lm.uSS = [s[1] for s in data["ss_laps"][b]]
+        lm.Qfun = [s[2] for s in data["ss_laps"][b]]; lm.LapTime = list(data["lap_times"])
+        lm.it, lm.timeStep = 4, int(data["t"][b])
+        lm.zt, lm.xLin, lm.uLin = data["zt"][b].copy(), data["xLin"][b].copy(), data["uLin"][b].copy()
+        lm.OldInput, lm.xPred = data["OldInput"][b].copy(), data["xPred"][b].copy()
+        ctrls.append(lm)
+    t0 = time.perf_counter()
+    for b, lm in enumerate(ctrls):
+        lm.solve(data["x0"][b])
+    dt = time.perf_counter() - t0
+    return {"value": nsample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d controller steps, oracle restatement of LMPC.solve in Python (as the reference: single thread) + "
+                      "OSQP-algorithm C port, reference settings; cpu %s" % (nsample, cpu_model())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,8 +452,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2],
+                    help="index into BASELINE.json configs: 1 = batch=4096 LTV-MPC QPs (default, the headline), "
+                         "2 = batch=4096 full LMPC steps with k-NN regression over a 5-lap safe set")
+    ap.add_argument("--batch", type=int, default=BATCH)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == 2:
+        run_lmpc_steps(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

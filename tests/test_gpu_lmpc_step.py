@@ -168,3 +168,40 @@ def test_closed_loop_lap_matches_reference_lap(gold, track):
             break
     assert t == int(gold["lmpc_lap_lengths"][0])
     c.close()
+
+
+def test_config3_workload_step_vs_oracle(track):
+    """BASELINE configs[2] shapes (trToUse = 5, 4-lap safe set, grown lap it-1): a sample of instances is replayed
+    through the oracle controller (reference arithmetic) and compared with the fused GPU step."""
+    _need_gpu()
+    from racinglmpc_b200 import workloads
+    from oracle import ftocp, ltv_model, osqp_port
+    B, N = 96, 12
+    data = workloads.lmpc_batch(B)
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    c = BatchedController(par, B, track.seg_table(), track.TrackLength, trToUse=5, numSS_Points=numSS_Points,
+                          numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536, ss_cap=6, model_cap=6)
+    workloads.restore_lmpc_batch(c, data)
+    o = c.step(data["x0"])
+    assert np.all(o["status"] == 1) and np.all(o["flags"] == 0), (np.unique(o["status"]), np.unique(o["flags"]))
+    assert o["resid"].max() < 1e-8
+    _, _, _, _, oQts, opar = ftocp.lmpc_params(track, N)
+    opar.timeVarying = True
+    for b in (0, 1, 37, 60, 95):
+        pm = ltv_model.LocalLTVModel(6, 2, track, 5)
+        pm.xStored = [lx for lx, _ in data["model_laps"][b]]
+        pm.uStored = [lu for _, lu in data["model_laps"][b]]
+        pm.lapTime = [lx.shape[0] for lx in pm.xStored]
+        lm = ftocp.OracleLMPC(numSS_Points, numSS_it, oQts, opar, pm, qp=osqp_port.tight_qp)
+        lm.SS = [s[0] for s in data["ss_laps"][b]]
+        lm.uSS = [s[1] for s in data["ss_laps"][b]]
+        lm.Qfun = [s[2] for s in data["ss_laps"][b]]
+        lm.LapTime = list(data["lap_times"])
+        lm.it, lm.timeStep = 4, int(data["t"][b])
+        lm.zt, lm.xLin, lm.uLin = data["zt"][b].copy(), data["xLin"][b].copy(), data["uLin"][b].copy()
+        lm.OldInput, lm.xPred = data["OldInput"][b].copy(), data["xPred"][b].copy()
+        lm.solve(data["x0"][b])
+        assert np.max(np.abs(o["uPred"][b] - lm.uPred)) < 1e-6, b
+        assert np.max(np.abs(o["xPred"][b] - lm.xPred)) < 1e-6, b
+        assert np.max(np.abs(o["zt"][b] - lm.zt)) < 1e-5, b
+    c.close()
