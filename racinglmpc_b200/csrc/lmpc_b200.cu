@@ -632,10 +632,10 @@ static int launch_k1(lmpc_handle* h) {
     K1Args a;
     a.batch = h->batch; a.N = h->N;
     a.wpb = h->N < 12 ? h->N : 12;
-    a.pts_stride = K1_MAXPTS * h->mc.trToUse * 10 + 48;
+    a.pts_stride = k1_pts_stride(h->mc.trToUse);
     a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
     dim3 grid(h->batch, (h->N + a.wpb - 1) / a.wpb);
-    size_t smem = sizeof(double) * a.pts_stride * a.wpb;
+    size_t smem = sizeof(double) * ((size_t)5 * K1_TILE + (size_t)a.pts_stride * a.wpb);
     static thread_local int cfg_dev = -1;
     if (cfg_dev != h->device) {
         CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

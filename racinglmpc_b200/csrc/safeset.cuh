@@ -96,33 +96,41 @@ __device__ __forceinline__ bool solve5(double (&A)[5][5], double (&b)[NR][5]) {
 
 constexpr int K1_MAXPTS = 7;     // MaxNumPoint supported by the register top-k
 constexpr int K1_MAXLAPS = 8;    // trToUse supported
+constexpr int K1_TILE = 256;     // lap rows staged in shared memory per pass
 
 struct K1Args {
-    int batch, N, wpb, pts_stride;   // warps per block; doubles of staging per warp (7*trToUse*10 + 48)
+    int batch, N, wpb, pts_stride;   // warps per block; doubles of per-warp scratch (see k1_pts_stride)
     const double* xLin;   // [B][N+1][6]
     const double* uLin;   // [B][N][2]
     LapPool pool;         // model pool
     const int* used;      // [B][trToUse] slot ids, in usedIt order
     double* abc;          // [B][N][54]
     int* status;          // [B] : 0 ok, else bit flags (1 = singular regression, 2 = curvature lookup failed,
-                          //        4 = fewer than 2 neighbours in a lap — the reference would raise)
+                          //        4 = a single neighbour in a lap — cases where the reference raises)
 };
+// per-warp scratch: selected points [7*trToUse][9] | normal equations 45 (+3 pad) | two augmented systems 5x6 + 5x7 (+3 pad)
+__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * 9 + 48 + 68; }
 
-// grid = (B, ceil(N / wpb)); one warp per horizon step.
+// grid = (B, ceil(N / wpb)); one warp per horizon step; the CTA stages each lap tile in shared memory once
+// (feature-major, conflict-free) and every warp scans it for its own query point.
 __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_constant__ ModelConst m, const K1Args a) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     const int b = blockIdx.x;
     const int wib = threadIdx.x >> 5;
     const int i = blockIdx.y * a.wpb + wib;   // horizon step
     const int lane = threadIdx.x & 31;
-    if (b >= a.batch || i >= a.N) return;
-    // per-warp staging of the selected points: [<=7*trToUse][10] = x0,x1,x2,u0,u1,K,y0,y1,y2,(pad), then 48 scratch
-    double* pts = reinterpret_cast<double*>(k1_smem) + (size_t)wib * a.pts_stride;
+    const int nthr = blockDim.x;
+    const bool active = (i < a.N);            // all warps take part in the tile loads
+    double* tile = reinterpret_cast<double*>(k1_smem);                 // [5][K1_TILE] : vx vy wz | delta a
+    double* pts = tile + 5 * K1_TILE + (size_t)wib * a.pts_stride;     // this warp's scratch
+    const int np_max = K1_MAXPTS * m.trToUse;
+    double* ne = pts + (size_t)np_max * 9;                             // 48
+    double* sys = ne + 48;                                             // 30 + 35 (+3)
 
-    const double* xl = a.xLin + ((size_t)b * (a.N + 1) + i) * 6;
-    const double* ul = a.uLin + ((size_t)b * a.N + i) * 2;
-    double q[5] = {xl[0], xl[1], xl[2], ul[0], ul[1]};
-    double xs[6] = {xl[0], xl[1], xl[2], xl[3], xl[4], xl[5]};
+    const int ii = active ? i : 0;
+    const double* xl = a.xLin + ((size_t)b * (a.N + 1) + ii) * 6;
+    const double* ul = a.uLin + ((size_t)b * a.N + ii) * 2;
+    const double q0 = xl[0], q1 = xl[1], q2 = xl[2], q3 = ul[0], q4 = ul[1];
     int flags = 0, npts = 0;
 
     for (int c = 0; c < m.trToUse; ++c) {
@@ -131,49 +139,63 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
         const double* X = a.pool.x + lap * a.pool.Tmax * 6;
         const double* U = a.pool.u + lap * a.pool.Tmax * 2;
         const int T = a.pool.len[lap];
-        // ---- scan rows 0..T-2 (PM.py:183), per-lane sorted top-7 ----
         double bd[K1_MAXPTS];
         int bi[K1_MAXPTS];
 #pragma unroll
         for (int r = 0; r < K1_MAXPTS; ++r) { bd[r] = 1e300; bi[r] = 0x7fffffff; }
         int cnt = 0;
-        for (int t = lane; t < T - 1; t += 32) {
-            const double* xr = X + (size_t)t * 6;
-            const double* ur = U + (size_t)t * 2;
-            // diff = (Data - x) * scaling ; 1-norm summed left to right (numpy semantics for 5 columns)
-            double d = fabs(__dmul_rn(__dsub_rn(xr[0], q[0]), m.scaling[0]));
-            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(xr[1], q[1]), m.scaling[1])));
-            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(xr[2], q[2]), m.scaling[2])));
-            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(ur[0], q[3]), m.scaling[3])));
-            d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(ur[1], q[4]), m.scaling[4])));
-            if (d < m.h) ++cnt;
-            if (cand_less(d, t, bd[K1_MAXPTS - 1], bi[K1_MAXPTS - 1])) {
-                bd[K1_MAXPTS - 1] = d;
-                bi[K1_MAXPTS - 1] = t;
+        for (int t0 = 0; t0 < T - 1; t0 += K1_TILE) {
+            const int rows = min(K1_TILE, T - 1 - t0);      // rows 0..T-2 are candidates (PM.py:183)
+            __syncthreads();                                 // previous tile fully consumed
+            for (int e = threadIdx.x; e < rows * 6; e += nthr) {       // coalesced 48 B rows -> feature-major
+                const int r = e / 6, col = e - r * 6;
+                const double v = X[(size_t)t0 * 6 + e];
+                if (col < 3) tile[col * K1_TILE + r] = v;
+            }
+            for (int e = threadIdx.x; e < rows * 2; e += nthr) {
+                const int r = e >> 1, col = e & 1;
+                tile[(3 + col) * K1_TILE + r] = U[(size_t)t0 * 2 + e];
+            }
+            __syncthreads();
+            if (active) {
+                for (int r = lane; r < rows; r += 32) {
+                    // diff = (Data - x) * scaling ; 1-norm summed left to right (numpy semantics for 5 columns)
+                    double d = fabs(__dmul_rn(__dsub_rn(tile[r], q0), m.scaling[0]));
+                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[K1_TILE + r], q1), m.scaling[1])));
+                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[2 * K1_TILE + r], q2), m.scaling[2])));
+                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[3 * K1_TILE + r], q3), m.scaling[3])));
+                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[4 * K1_TILE + r], q4), m.scaling[4])));
+                    const int t = t0 + r;
+                    if (d < m.h) ++cnt;
+                    if (cand_less(d, t, bd[K1_MAXPTS - 1], bi[K1_MAXPTS - 1])) {
+                        bd[K1_MAXPTS - 1] = d;
+                        bi[K1_MAXPTS - 1] = t;
 #pragma unroll
-                for (int r = K1_MAXPTS - 1; r > 0; --r) {
-                    if (cand_less(bd[r], bi[r], bd[r - 1], bi[r - 1])) {
-                        double td = bd[r]; bd[r] = bd[r - 1]; bd[r - 1] = td;
-                        int ti = bi[r]; bi[r] = bi[r - 1]; bi[r - 1] = ti;
+                        for (int z = K1_MAXPTS - 1; z > 0; --z) {
+                            if (cand_less(bd[z], bi[z], bd[z - 1], bi[z - 1])) {
+                                double td = bd[z]; bd[z] = bd[z - 1]; bd[z - 1] = td;
+                                int ti = bi[z]; bi[z] = bi[z - 1]; bi[z - 1] = ti;
+                            }
+                        }
                     }
                 }
             }
         }
+        if (!active) continue;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside
-        int ksel = cnt >= m.MaxNumPoint ? m.MaxNumPoint : cnt;
+        const int ksel = cnt >= m.MaxNumPoint ? m.MaxNumPoint : cnt;
         if (cnt == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
-        // ---- merge: ksel rounds of warp arg-min over the lane heads ----
-        for (int r = 0; r < ksel; ++r) {
-            double hd = bd[0];
-            int hi = bi[0];
+        for (int r = 0; r < ksel; ++r) {   // ksel rounds of warp arg-min over the lane heads
+            const double hd = bd[0];
+            const int hi = bi[0];
             double wd = hd;
             int wi = hi;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                double od = __shfl_xor_sync(0xffffffffu, wd, o);
-                int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                const double od = __shfl_xor_sync(0xffffffffu, wd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
                 if (cand_less(od, oi, wd, wi)) { wd = od; wi = oi; }
             }
             if (hi == wi && hd == wd) {   // this lane owned the winner: pop it
@@ -182,23 +204,21 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
                 bd[K1_MAXPTS - 1] = 1e300;
                 bi[K1_MAXPTS - 1] = 0x7fffffff;
             }
-            if (lane == 0) {
-                double* p = pts + (size_t)(npts + r) * 10;
-                const double* xr = X + (size_t)wi * 6;
-                const double* xn = X + (size_t)(wi + 1) * 6;
-                const double* ur = U + (size_t)wi * 2;
-                double rr = wd / m.h;
-                p[0] = xr[0]; p[1] = xr[1]; p[2] = xr[2]; p[3] = ur[0]; p[4] = ur[1];
-                p[5] = (1.0 - rr * rr) * 3.0 / 4.0;      // Epanechnikov weight, PM.py:193
-                p[6] = xn[0]; p[7] = xn[1]; p[8] = xn[2];
+            if (lane < 9) {               // x0,x1,x2,u0,u1,K,y0,y1,y2 of the selected row, one value per lane
+                double v;
+                if (lane < 3) v = X[(size_t)wi * 6 + lane];
+                else if (lane < 5) v = U[(size_t)wi * 2 + (lane - 3)];
+                else if (lane == 5) { const double rr = wd / m.h; v = (1.0 - rr * rr) * 3.0 / 4.0; }   // PM.py:193
+                else v = X[(size_t)(wi + 1) * 6 + (lane - 6)];
+                pts[(size_t)(npts + r) * 9 + lane] = v;
             }
         }
         npts += ksel;
     }
+    if (!active) return;
     __syncwarp();
 
     // ---- normal equations (PM.py:141-168).  entries: Qvx(15) Qlat(15) bvx(5) bvy(5) bwz(5) ----
-    double* ne = pts + a.pts_stride - 48;   // tail of this warp's staging area
     for (int e = lane; e < 45; e += 32) {
         double acc = 0.0;
         if (e < 30) {
@@ -208,9 +228,9 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
             while (idx >= 5 - r) { idx -= 5 - r; ++r; }
             const int cc = idx + r;     // (r, cc), r <= cc
             for (int p = 0; p < npts; ++p) {
-                const double* P = pts + (size_t)p * 10;
-                double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
-                double mc = (cc < 3) ? P[cc] : (cc == 3 ? (lat ? P[3] : P[4]) : 1.0);
+                const double* P = pts + (size_t)p * 9;
+                const double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
+                const double mc = (cc < 3) ? P[cc] : (cc == 3 ? (lat ? P[3] : P[4]) : 1.0);
                 acc += mr * P[5] * mc;
             }
             if (r == cc) acc += m.lamb;
@@ -218,79 +238,149 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
             const int which = (e - 30) / 5, r = (e - 30) % 5;   // 0 vx, 1 vy, 2 wz
             const int lat = which > 0;
             for (int p = 0; p < npts; ++p) {
-                const double* P = pts + (size_t)p * 10;
-                double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
+                const double* P = pts + (size_t)p * 9;
+                const double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
                 acc += mr * P[5] * P[6 + which];
             }
         }
         ne[e] = acc;
     }
     __syncwarp();
-    double Qv[5][5], Ql[5][5], bv[1][5], bl[2][5];
-    {
-        int e = 0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int cc = r; cc < 5; ++cc) { Qv[r][cc] = Qv[cc][r] = ne[e]; Ql[r][cc] = Ql[cc][r] = ne[15 + e]; ++e; }
-#pragma unroll
-        for (int r = 0; r < 5; ++r) { bv[0][r] = ne[30 + r]; bl[0][r] = ne[35 + r]; bl[1][r] = ne[40 + r]; }
+    // ---- two augmented systems in shared memory: S1 = [Qvx | bvx] (5 x 6), S2 = [Qlat | bvy bwz] (5 x 7);
+    //      Gaussian elimination with partial pivoting, one lane per column (lanes 0..5 and 8..14)
+    double* S1 = sys;
+    double* S2 = sys + 30;
+    for (int e = lane; e < 65; e += 32) {
+        const bool second = e >= 30;
+        const int f = second ? e - 30 : e;
+        const int w_ = second ? 7 : 6;
+        const int r = f / w_, cc = f % w_;
+        double v;
+        if (cc < 5) {
+            const int lo = r < cc ? r : cc, hi = r < cc ? cc : r;
+            v = ne[(second ? 15 : 0) + lo * 5 - lo * (lo - 1) / 2 + (hi - lo)];
+        } else {
+            v = ne[(second ? 35 + 5 * (cc - 5) : 30) + r];
+        }
+        (second ? S2 : S1)[f] = v;
     }
-    if (!solve5<1>(Qv, bv)) flags |= 1;
-    if (!solve5<2>(Ql, bl)) flags |= 1;
+    __syncwarp();
+    {
+        const bool in1 = lane < 6, in2 = lane >= 8 && lane < 15;
+        double* Sm = in2 ? S2 : S1;
+        const int w_ = in2 ? 7 : 6;
+        const int col = in2 ? lane - 8 : lane;
+        bool ok = true;
+        for (int cpiv = 0; cpiv < 5; ++cpiv) {
+            // pivot search (lane redundant within each system)
+            int piv = cpiv;
+            double best = fabs(Sm[cpiv * w_ + cpiv]);
+            for (int r = cpiv + 1; r < 5; ++r) {
+                const double v = fabs(Sm[r * w_ + cpiv]);
+                if (v > best) { best = v; piv = r; }
+            }
+            if (!(best > 0.0)) ok = false;
+            __syncwarp();
+            if ((in1 || in2) && piv != cpiv) {               // swap rows, one column per lane
+                const double t = Sm[cpiv * w_ + col];
+                Sm[cpiv * w_ + col] = Sm[piv * w_ + col];
+                Sm[piv * w_ + col] = t;
+            }
+            __syncwarp();
+            const double pv = Sm[cpiv * w_ + cpiv];
+            const double inv = (pv != 0.0) ? 1.0 / pv : 0.0;
+            double f[5];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) f[r] = Sm[r * w_ + cpiv] * inv;   // multipliers (read before any update)
+            const double prow = Sm[cpiv * w_ + col];
+            __syncwarp();
+            if ((in1 || in2) && col > cpiv) {
+#pragma unroll
+                for (int r = 0; r < 5; ++r)
+                    if (r > cpiv) Sm[r * w_ + col] -= f[r] * prow;
+            }
+            __syncwarp();
+        }
+        if (!ok) flags |= 1;
+        // back substitution: rhs columns (lane 5 of S1; lanes 13, 14 of S2)
+        if ((in1 && col == 5) || (in2 && col >= 5)) {
+            double xs_[5];
+#pragma unroll
+            for (int r = 4; r >= 0; --r) {
+                double v = Sm[r * w_ + col];
+#pragma unroll
+                for (int j = 4; j > r; --j) v -= Sm[r * w_ + j] * xs_[j];
+                const double dg = Sm[r * w_ + r];
+                xs_[r] = (dg != 0.0) ? v / dg : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 5; ++r) Sm[r * w_ + col] = xs_[r];
+        }
+        __syncwarp();
+    }
+    // theta_vx = S1[:,5], theta_vy = S2[:,5], theta_wz = S2[:,6]
 
     // ---- A, B, C (PM.py:66-135) ----
     double* out = a.abc + ((size_t)b * a.N + i) * 54;
-    const double vx = xs[0], vy = xs[1], wz = xs[2], epsi = xs[3], s = xs[4], ey = xs[5];
+    const double vx = xl[0], vy = xl[1], wz = xl[2], epsi = xl[3], s = xl[4], ey = xl[5];
     const double dt = m.dt;
     int okc = 1;
     const double cur = curvature_lookup(m, s, &okc);
     if (!okc) flags |= 2;
     const double den = 1.0 - cur * ey;
     const double ce = cos(epsi), se = sin(epsi);
-    double A3[6], A4[6], A5[6];
-    A3[0] = -dt * ce / den * cur;
-    A3[1] = dt * se / den * cur;
-    A3[2] = dt;
-    A3[3] = 1.0 - dt * (-vx * se - vy * ce) / den * cur;
-    A3[4] = 0.0;
-    A3[5] = dt * (vx * ce - vy * se) / (den * den) * cur * (-cur);
-    A4[0] = dt * (ce / den);
-    A4[1] = -dt * (se / den);
-    A4[2] = 0.0;
-    A4[3] = dt * (-vx * se - vy * ce) / den;
-    A4[4] = 1.0;
-    A4[5] = -dt * (vx * ce - vy * se) / (den * den) * (-cur);
-    A5[0] = dt * se;
-    A5[1] = dt * ce;
-    A5[2] = 0.0;
-    A5[3] = dt * (vx * ce - vy * se);
-    A5[4] = 0.0;
-    A5[5] = 1.0;
-    double d3 = 0, d4 = 0, d5 = 0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) { d3 += A3[j] * xs[j]; d4 += A4[j] * xs[j]; d5 += A5[j] * xs[j]; }
-    const double C3 = epsi + dt * (wz - (vx * ce - vy * se) / (1.0 - cur * ey) * cur) - d3;
-    const double C4 = s + dt * ((vx * ce - vy * se) / (1.0 - cur * ey)) - d4;
-    const double C5 = ey + dt * (vx * se + vy * ce) - d5;
     for (int e = lane; e < 54; e += 32) {
         double v = 0.0;
-        if (e < 36) {
+        if (e < 18) {                       // rows 0..2 of A: regression coefficients on (vx, vy, wz)
             const int r = e / 6, cc = e % 6;
-            if (r == 0) v = cc < 3 ? bv[0][cc] : 0.0;
-            else if (r == 1) v = cc < 3 ? bl[0][cc] : 0.0;
-            else if (r == 2) v = cc < 3 ? bl[1][cc] : 0.0;
-            else if (r == 3) v = A3[cc];
-            else if (r == 4) v = A4[cc];
-            else v = A5[cc];
+            if (cc < 3) v = (r == 0) ? S1[cc * 6 + 5] : S2[cc * 7 + 5 + (r - 1)];
+        } else if (e < 36) {                // rows 3..5 of A: Jacobian of the curvilinear kinematics
+            const int r = e / 6, cc = e % 6;
+            if (r == 3) {
+                v = cc == 0 ? -dt * ce / den * cur : cc == 1 ? dt * se / den * cur : cc == 2 ? dt
+                    : cc == 3 ? 1.0 - dt * (-vx * se - vy * ce) / den * cur : cc == 4 ? 0.0
+                    : dt * (vx * ce - vy * se) / (den * den) * cur * (-cur);
+            } else if (r == 4) {
+                v = cc == 0 ? dt * (ce / den) : cc == 1 ? -dt * (se / den) : cc == 2 ? 0.0
+                    : cc == 3 ? dt * (-vx * se - vy * ce) / den : cc == 4 ? 1.0
+                    : -dt * (vx * ce - vy * se) / (den * den) * (-cur);
+            } else {
+                v = cc == 0 ? dt * se : cc == 1 ? dt * ce : cc == 2 ? 0.0 : cc == 3 ? dt * (vx * ce - vy * se)
+                    : cc == 4 ? 0.0 : 1.0;
+            }
         } else if (e < 48) {
             const int r = (e - 36) >> 1, cc = (e - 36) & 1;
-            if (r == 0 && cc == 1) v = bv[0][3];          // vx row uses the acceleration input (PM.py:29,70)
-            else if (r == 1 && cc == 0) v = bl[0][3];     // lateral rows use the steering input (PM.py:30,78,82)
-            else if (r == 2 && cc == 0) v = bl[1][3];
+            if (r == 0 && cc == 1) v = S1[3 * 6 + 5];          // vx row uses the acceleration input (PM.py:29,70)
+            else if (r == 1 && cc == 0) v = S2[3 * 7 + 5];     // lateral rows use the steering input (PM.py:30,78,82)
+            else if (r == 2 && cc == 0) v = S2[3 * 7 + 6];
         } else {
             const int r = e - 48;
-            v = r == 0 ? bv[0][4] : r == 1 ? bl[0][4] : r == 2 ? bl[1][4] : r == 3 ? C3 : r == 4 ? C4 : C5;
+            if (r == 0) v = S1[4 * 6 + 5];
+            else if (r == 1) v = S2[4 * 7 + 5];
+            else if (r == 2) v = S2[4 * 7 + 6];
+            else {
+                // C_r = f_r(x) - A_r x, products summed left to right like np.dot on 6 terms
+                double A3[6];
+                double fx;
+                if (r == 3) {
+                    A3[0] = -dt * ce / den * cur; A3[1] = dt * se / den * cur; A3[2] = dt;
+                    A3[3] = 1.0 - dt * (-vx * se - vy * ce) / den * cur; A3[4] = 0.0;
+                    A3[5] = dt * (vx * ce - vy * se) / (den * den) * cur * (-cur);
+                    fx = epsi + dt * (wz - (vx * ce - vy * se) / (1.0 - cur * ey) * cur);
+                } else if (r == 4) {
+                    A3[0] = dt * (ce / den); A3[1] = -dt * (se / den); A3[2] = 0.0;
+                    A3[3] = dt * (-vx * se - vy * ce) / den; A3[4] = 1.0;
+                    A3[5] = -dt * (vx * ce - vy * se) / (den * den) * (-cur);
+                    fx = s + dt * ((vx * ce - vy * se) / (1.0 - cur * ey));
+                } else {
+                    A3[0] = dt * se; A3[1] = dt * ce; A3[2] = 0.0; A3[3] = dt * (vx * ce - vy * se); A3[4] = 0.0; A3[5] = 1.0;
+                    fx = ey + dt * (vx * se + vy * ce);
+                }
+                double dsum = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) dsum += A3[j] * xl[j];
+                v = fx - dsum;
+            }
         }
         out[e] = v;
     }
