@@ -109,7 +109,8 @@ struct K1Args {
                           //        4 = a single neighbour in a lap — cases where the reference raises)
 };
 // per-warp scratch: selected points [7*trToUse][9] | normal equations 45 (+3 pad) | two augmented systems 5x6 + 5x7 (+3 pad)
-__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * 9 + 48 + 68; }
+//                   | candidate buffer 64 distances + 64 row indices
+__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * 9 + 48 + 68 + 96; }
 
 // grid = (B, ceil(N / wpb)); one warp per horizon step; the CTA stages each lap tile in shared memory once
 // (feature-major, conflict-free) and every warp scans it for its own query point.
@@ -126,6 +127,8 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
     const int np_max = K1_MAXPTS * m.trToUse;
     double* ne = pts + (size_t)np_max * 9;                             // 48
     double* sys = ne + 48;                                             // 30 + 35 (+3)
+    double* cbd = sys + 68;                                            // candidate distances [64]
+    int* cbi = reinterpret_cast<int*>(cbd + 64);                       // candidate rows [64]
 
     const int ii = active ? i : 0;
     const double* xl = a.xLin + ((size_t)b * (a.N + 1) + ii) * 6;
@@ -139,71 +142,97 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
         const double* X = a.pool.x + lap * a.pool.Tmax * 6;
         const double* U = a.pool.u + lap * a.pool.Tmax * 2;
         const int T = a.pool.len[lap];
-        double bd[K1_MAXPTS];
-        int bi[K1_MAXPTS];
+        // Warp-wide running top-k (k = MaxNumPoint): lanes 0..k-1 hold the current best (sorted), `tau` is the k-th
+        // best so far.  A row is a candidate only if it beats tau; candidates are compacted into a per-warp buffer
+        // (ballot + popc) and folded into the top-k when 32 or more have accumulated.
+        double topd = 1e300;            // lane r < k: r-th best distance so far
+        int topi = 0x7fffffff;
+        double tau_d = 1e300;           // k-th best (all lanes)
+        int tau_i = 0x7fffffff;
+        int nbuf = 0, cnt = 0;
+        const int kk = m.MaxNumPoint;
+        auto fold = [&]() {
+            // candidates: buffer entries lane, lane+32 (< nbuf <= 64) and the current top-k (lane < kk)
+            double c0d = (lane < nbuf) ? cbd[lane] : 1e300;
+            int c0i = (lane < nbuf) ? cbi[lane] : 0x7fffffff;
+            double c1d = (lane + 32 < nbuf) ? cbd[lane + 32] : 1e300;
+            int c1i = (lane + 32 < nbuf) ? cbi[lane + 32] : 0x7fffffff;
+            double c2d = (lane < kk) ? topd : 1e300;
+            int c2i = (lane < kk) ? topi : 0x7fffffff;
+            double nd = 1e300;
+            int ni = 0x7fffffff;
+            for (int r = 0; r < kk; ++r) {
+                double ld = c0d; int li = c0i;
+                if (cand_less(c1d, c1i, ld, li)) { ld = c1d; li = c1i; }
+                if (cand_less(c2d, c2i, ld, li)) { ld = c2d; li = c2i; }
+                double wd = ld; int wi = li;
 #pragma unroll
-        for (int r = 0; r < K1_MAXPTS; ++r) { bd[r] = 1e300; bi[r] = 0x7fffffff; }
-        int cnt = 0;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(0xffffffffu, wd, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                    if (cand_less(od, oi, wd, wi)) { wd = od; wi = oi; }
+                }
+                if (c0i == wi && c0d == wd) { c0d = 1e300; c0i = 0x7fffffff; }
+                else if (c1i == wi && c1d == wd) { c1d = 1e300; c1i = 0x7fffffff; }
+                else if (c2i == wi && c2d == wd) { c2d = 1e300; c2i = 0x7fffffff; }
+                if (lane == r) { nd = wd; ni = wi; }
+                if (r == kk - 1) { tau_d = wd; tau_i = wi; }
+            }
+            topd = nd; topi = ni;
+            nbuf = 0;
+            __syncwarp();
+        };
         for (int t0 = 0; t0 < T - 1; t0 += K1_TILE) {
             const int rows = min(K1_TILE, T - 1 - t0);      // rows 0..T-2 are candidates (PM.py:183)
             __syncthreads();                                 // previous tile fully consumed
-            for (int e = threadIdx.x; e < rows * 6; e += nthr) {       // coalesced 48 B rows -> feature-major
-                const int r = e / 6, col = e - r * 6;
-                const double v = X[(size_t)t0 * 6 + e];
-                if (col < 3) tile[col * K1_TILE + r] = v;
-            }
-            for (int e = threadIdx.x; e < rows * 2; e += nthr) {
-                const int r = e >> 1, col = e & 1;
-                tile[(3 + col) * K1_TILE + r] = U[(size_t)t0 * 2 + e];
+            for (int r = threadIdx.x; r < rows; r += nthr) {            // one 48 B + one 16 B row per thread -> feature-major
+                const double2 v01 = *reinterpret_cast<const double2*>(X + (size_t)(t0 + r) * 6);
+                const double v2 = X[(size_t)(t0 + r) * 6 + 2];
+                const double2 uu = *reinterpret_cast<const double2*>(U + (size_t)(t0 + r) * 2);
+                tile[r] = v01.x; tile[K1_TILE + r] = v01.y; tile[2 * K1_TILE + r] = v2;
+                tile[3 * K1_TILE + r] = uu.x; tile[4 * K1_TILE + r] = uu.y;
             }
             __syncthreads();
             if (active) {
-                for (int r = lane; r < rows; r += 32) {
-                    // diff = (Data - x) * scaling ; 1-norm summed left to right (numpy semantics for 5 columns)
-                    double d = fabs(__dmul_rn(__dsub_rn(tile[r], q0), m.scaling[0]));
-                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[K1_TILE + r], q1), m.scaling[1])));
-                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[2 * K1_TILE + r], q2), m.scaling[2])));
-                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[3 * K1_TILE + r], q3), m.scaling[3])));
-                    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[4 * K1_TILE + r], q4), m.scaling[4])));
+                for (int rb = 0; rb < rows; rb += 32) {
+                    const int r = rb + lane;
+                    bool cand = false;
+                    double d = 1e300;
                     const int t = t0 + r;
-                    if (d < m.h) ++cnt;
-                    if (cand_less(d, t, bd[K1_MAXPTS - 1], bi[K1_MAXPTS - 1])) {
-                        bd[K1_MAXPTS - 1] = d;
-                        bi[K1_MAXPTS - 1] = t;
-#pragma unroll
-                        for (int z = K1_MAXPTS - 1; z > 0; --z) {
-                            if (cand_less(bd[z], bi[z], bd[z - 1], bi[z - 1])) {
-                                double td = bd[z]; bd[z] = bd[z - 1]; bd[z - 1] = td;
-                                int ti = bi[z]; bi[z] = bi[z - 1]; bi[z - 1] = ti;
-                            }
+                    if (r < rows) {
+                        // diff = (Data - x) * scaling ; 1-norm summed left to right (numpy semantics for 5 columns)
+                        d = fabs(__dmul_rn(__dsub_rn(tile[r], q0), m.scaling[0]));
+                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[K1_TILE + r], q1), m.scaling[1])));
+                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[2 * K1_TILE + r], q2), m.scaling[2])));
+                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[3 * K1_TILE + r], q3), m.scaling[3])));
+                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[4 * K1_TILE + r], q4), m.scaling[4])));
+                        if (d < m.h) ++cnt;
+                        cand = cand_less(d, t, tau_d, tau_i);
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, cand);
+                    if (mask) {
+                        if (cand) {
+                            const int pos = nbuf + __popc(mask & ((1u << lane) - 1u));
+                            cbd[pos] = d;
+                            cbi[pos] = t;
                         }
+                        nbuf += __popc(mask);
+                        __syncwarp();
+                        if (nbuf > 32) fold();
                     }
                 }
             }
         }
         if (!active) continue;
+        if (nbuf > 0) fold();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside
         const int ksel = cnt >= m.MaxNumPoint ? m.MaxNumPoint : cnt;
         if (cnt == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
-        for (int r = 0; r < ksel; ++r) {   // ksel rounds of warp arg-min over the lane heads
-            const double hd = bd[0];
-            const int hi = bi[0];
-            double wd = hd;
-            int wi = hi;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double od = __shfl_xor_sync(0xffffffffu, wd, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-                if (cand_less(od, oi, wd, wi)) { wd = od; wi = oi; }
-            }
-            if (hi == wi && hd == wd) {   // this lane owned the winner: pop it
-#pragma unroll
-                for (int z = 0; z < K1_MAXPTS - 1; ++z) { bd[z] = bd[z + 1]; bi[z] = bi[z + 1]; }
-                bd[K1_MAXPTS - 1] = 1e300;
-                bi[K1_MAXPTS - 1] = 0x7fffffff;
-            }
+        for (int r = 0; r < ksel; ++r) {
+            const double wd = __shfl_sync(0xffffffffu, topd, r);
+            const int wi = __shfl_sync(0xffffffffu, topi, r);
             if (lane < 9) {               // x0,x1,x2,u0,u1,K,y0,y1,y2 of the selected row, one value per lane
                 double v;
                 if (lane < 3) v = X[(size_t)wi * 6 + lane];
