@@ -194,8 +194,11 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
             }
             __syncthreads();
             if (active) {
-                for (int rb = 0; rb < rows; rb += 32) {
-                    const int r = rb + lane;
+                // Rows of the tile are visited in a scrambled order (r = 37 i mod 256, a bijection on the tile): stored laps
+                // are time series, and an in-order scan approaching the query makes almost every row a new candidate
+                // (a fold per batch); scrambled, tau tightens after the first batch and few rows pass.
+                for (int rb = 0; rb < K1_TILE; rb += 32) {
+                    const int r = ((rb + lane) * 37) & (K1_TILE - 1);
                     bool cand = false;
                     double d = 1e300;
                     const int t = t0 + r;
@@ -252,10 +255,10 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
         double acc = 0.0;
         if (e < 30) {
             const int lat = e >= 15;
-            int idx = lat ? e - 15 : e;
-            int r = 0;
-            while (idx >= 5 - r) { idx -= 5 - r; ++r; }
-            const int cc = idx + r;     // (r, cc), r <= cc
+            const int idx = lat ? e - 15 : e;
+            // (r, cc), r <= cc, of the idx-th entry of the upper triangle of a 5 x 5 matrix
+            const int r = (idx >= 5) + (idx >= 9) + (idx >= 12) + (idx >= 14);
+            const int cc = idx - (r * 5 - r * (r - 1) / 2) + r;
             for (int p = 0; p < npts; ++p) {
                 const double* P = pts + (size_t)p * 9;
                 const double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
