@@ -66,7 +66,11 @@ inline double wmin(double v) { return v; }
 inline double wmax(double v) { return v; }
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define FOR_LANES(e, n) _Pragma("unroll") for (int e = LMPC_LANE; e < (n); e += LMPC_NLANE)
+#else
 #define FOR_LANES(e, n) for (int e = LMPC_LANE; e < (n); e += LMPC_NLANE)
+#endif
 #define NSLOT(CNT) (((CNT) + LMPC_NLANE - 1) / LMPC_NLANE)
 // row = lane + 32*r ; the body runs only for valid rows.  No warp collectives inside.
 #define FOR_SLOTS(r, row, CNT) \
@@ -708,7 +712,7 @@ struct Pdip {
         init_point(w, g, c, x0);
         const double n_ineq = (double)(2 * R1 + R2 + (LMPC ? M : 0));
         int it = 0, status = ST_MAX_ITER;
-        double r_prim = 0.0, r_dual = 0.0, mu = 0.0;
+        double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0;
 
         for (;; ++it) {
             // ---- lane-local residuals, barrier diagonals, predictor right-hand sides -------
@@ -751,19 +755,30 @@ struct Pdip {
                     comp += g.lam[r] * g.nu4[r];
                     g.rho[r] = -rl - g.nu4[r];   // predictor: rc4/lam = nu4
                 }
-                delta = terminal_factor(w, g, c);
-                terminal_rhs(w, g, -rone, c1, beta);
             } else {
                 wsync();
             }
             comp = wsum(comp);
             mu = comp / n_ineq;
+            rd_loc = wmax(rd_loc);
+            r_prim = fabs(rone);
+            if (it > 0) {
+                // The input-stationarity residual is linear in the iterate and every variable moved by the same step
+                // length, so after a step alpha it is exactly (1 - alpha) times its previous value: convergence can be
+                // decided here, before paying for another factorisation.
+                r_dual = fmax(rd_loc, (1.0 - al_prev) * ru_prev);
+                if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap) { status = ST_SOLVED; break; }
+            }
             // ---- factorising backward sweep (also yields the input residual) ------------------
+            if (LMPC) {
+                delta = terminal_factor(w, g, c);
+                terminal_rhs(w, g, -rone, c1, beta);
+            }
             stage_gradients(w, c);
             backward_start<true>(w, c, c1);
-            double ru_max = backward_factor(w, c);
-            r_dual = fmax(wmax(rd_loc), ru_max);
-            r_prim = fabs(rone);
+            const double ru_max = backward_factor(w, c);
+            ru_prev = ru_max;
+            r_dual = fmax(rd_loc, ru_max);
             if (w.flag != 0) { status = w.flag; break; }
             if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap) { status = ST_SOLVED; break; }
             if (it >= c.max_iter) { status = ST_MAX_ITER; break; }
@@ -926,6 +941,7 @@ struct Pdip {
                 }
                 g.y1 += al * dy1;
             }
+            al_prev = al;
             FOR_LANES(e, (N + 1) * 6) w.x[e] += al * w.dx[e];
             FOR_LANES(e, N * 2) w.u[e] += al * w.du[e];
             wsync();
