@@ -50,7 +50,8 @@ typedef struct lmpc_params {
     int numSS_Points, numSS_it;   /* 0,0 for a plain MPC                       LMPC.__init__      */
     double QterminalSlack[36];    /*                                           LMPC.__init__      */
     /* interior-point settings (no reference counterpart; OSQP's eps are 1e-3 + polish, PC.py:275) */
-    double eps_res, eps_gap;      /* <= 0 selects the defaults 1e-9 / 1e-11    */
+    double eps_res, eps_gap;      /* <= 0 selects the defaults 1e-8 / 1e-11 (unscaled inf-norms); an instance that runs
+                                     out of iterations is still reported solved if all three are <= 1e-6 */
     int max_iter;                 /* <= 0 selects the default 40               */
 } lmpc_params;
 

@@ -16,6 +16,8 @@ Problem (same data the reference assembles at PredictiveControllers.py:166-257,3
 """
 import numpy as np
 
+ADAPTIVE_FLOOR = False  # experiment (relax the floor on stall): helps some instances, hurts others -> off
+EXACT_TERMINAL_RECOVERY = False
 TERM_REFINE = 0   # terminal-block iterative refinement (experiment; the kernel does not need it)
 DEBUG_HOOK = False
 D4_MIN = 1e-4   # floor on the lambda barrier diagonal nu4/lambda (static primal regularisation).
@@ -117,6 +119,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
         return gr
 
     status, it = 2, 0
+    d4_floor, rdual_prev, al_prev = D4_MIN, 1e300, 0.0
     for it in range(max_iter + 1):
         # ---- residuals -----------------------------------------------------------
         r1 = np.array([Fx @ x[k] - s[k] + w1[k] - bx for k in range(N)])
@@ -147,6 +150,11 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
         if r_prim <= eps and r_dual <= eps and mu <= (eps if eps_gap is None else eps_gap):
             status = 1
             break
+        if ADAPTIVE_FLOOR and lmpc and it > 0 and al_prev >= 0.9 and r_dual > 0.25 * rdual_prev:
+            d4_floor = min(d4_floor, 0.1 * D4_MIN)
+            if verbose:
+                print("      floor ->", d4_floor)
+        rdual_prev = r_dual
         if it == max_iter:
             break
 
@@ -160,7 +168,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
             c = 2.0 if k < N - 1 else 1.0
             Huu.append(R2 + np.diag(c * dR2) + Fu.T @ (d2[k][:, None] * Fu))
         if lmpc:
-            d4 = np.maximum(nu4 / lam, D4_MIN)
+            d4 = np.maximum(nu4 / lam, d4_floor)
             delta = np.sum(1.0 / d4)
             sbar = (SS / d4[None, :]) @ np.ones(m) / delta   # D^-1-weighted centroid
             Sc = SS - sbar[:, None]
@@ -230,18 +238,30 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                 dyT = Wi @ (dx[N] + c1)
                 dy1t = -beta / delta                        # multiplier of the centred simplex row
                 dlam = (rho_l + Sc.T @ dyT - dy1t) / d4
-                for _ in range(TERM_REFINE):
-                    # residual of the terminal block in information form, dx_N held fixed
+                d4_true = nu4 / lam
+                for _ in range(TERM_REFINE if np.min(d4_true) < d4_floor else 0):
+                    # iterative refinement of (dlam, dy1) for the given dx_N: residual of the terminal block in
+                    # INFORMATION form with the TRUE barrier diagonal, correction by the floored covariance-form solve
                     yTi = T @ (dx[N] - Sc @ dlam - sbar * np.sum(dlam))
-                    e_l = rho_l - (d4 * dlam - Sc.T @ yTi + dy1t)
+                    e_l = rho_l - (d4_true * dlam - Sc.T @ yTi + dy1t)
                     e_1 = -rone - np.sum(dlam)
                     cc1 = -SD @ e_l - sbar * e_1
                     cyT = Wi @ cc1
                     cy1 = -(e_1 - np.sum(e_l / d4)) / delta
                     dlam = dlam + (e_l + Sc.T @ cyT - cy1) / d4
                     dy1t = dy1t + cy1
+                if EXACT_TERMINAL_RECOVERY:
+                    # experiment: information-form recovery of (dlam, dy1) given dx_N (dense bordered solve)
+                    Kb = np.zeros((m + 1, m + 1))
+                    Kb[:m, :m] = np.diag(nu4 / lam) + SS.T @ T @ SS
+                    Kb[:m, m] = 1.0
+                    Kb[m, :m] = 1.0
+                    sol_ = np.linalg.solve(Kb, np.concatenate([rho_l + SS.T @ (T @ dx[N]), [-rone]]))
+                    dlam = sol_[:m]
                 dyT = T @ (dx[N] - SS @ dlam)
                 dy1 = dy1t + sbar @ dyT
+                if EXACT_TERMINAL_RECOVERY:
+                    dy1 = sol_[m]
                 dxi = np.zeros(n)
                 dnu4 = (-rc4 - nu4 * dlam) / lam
                 out.update(dy1=dy1, dyT=dyT, dlam=dlam, dxi=dxi, dnu4=dnu4)
@@ -313,6 +333,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                 e_l = (nu4 / lam) * cc["dlam"] - SS.T @ cc["dyT"] + cc["dy1"] - (-rlam - rc4 / lam)
                 msg += " lam %.2e  |dlam| %.2e |dyT| %.2e |dxN| %.2e alpha %.3f sigma %.2e minD4 %.1e" % (np.abs(e_l).max(), np.abs(cc["dlam"]).max(), np.abs(cc["dyT"]).max(), np.abs(dx_[N]).max(), al, sigma, (nu4/lam).min())
             print(msg)
+        al_prev = al
         x = x + al * cc["dx"]
         u = u + al * cc["du"]
         s = s + al * cc["ds"]

@@ -184,7 +184,7 @@ def test_config3_workload_step_vs_oracle(track):
     workloads.restore_lmpc_batch(c, data)
     o = c.step(data["x0"])
     assert np.all(o["status"] == 1) and np.all(o["flags"] == 0), (np.unique(o["status"]), np.unique(o["flags"]))
-    assert o["resid"].max() < 1e-8
+    assert o["resid"].max() <= 1e-6
     _, _, _, _, oQts, opar = ftocp.lmpc_params(track, N)
     opar.timeVarying = True
     for b in (0, 1, 37, 60, 95):
