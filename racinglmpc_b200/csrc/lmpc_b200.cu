@@ -171,6 +171,7 @@ struct lmpc_handle {
     FtocpConst c;
     int batch, device, N, M;
     cudaStream_t stream;
+    cudaStream_t cstream[4];   // chunk pipeline of the *_host entry points (H2D | kernel | D2H overlap)
     long long launches;
     // device buffers used by the *_host entry points
     double *d_x0, *d_uOld, *d_abc, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
@@ -234,7 +235,7 @@ static int build_const(const lmpc_params& p, FtocpConst& c) {
 }
 
 template <int N, int M>
-static int launch_t(lmpc_handle* h, const FtocpArgs& a) {
+static int launch_t(lmpc_handle* h, const FtocpArgs& a, cudaStream_t st) {
     using KS = KernelSmem<N, M, 2, 4>;
     auto kern = ftocp_kernel<N, M, 2, 4>;
     static thread_local int configured_dev = -1;
@@ -242,15 +243,15 @@ static int launch_t(lmpc_handle* h, const FtocpArgs& a) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KS)));
         configured_dev = h->device;
     }
-    kern<<<a.batch, 32, sizeof(KS), h->stream>>>(h->c, a);
+    kern<<<a.batch, 32, sizeof(KS), st>>>(h->c, a);
     CK(cudaGetLastError());
     h->launches += 1;
     return LMPC_OK;
 }
 
-static int launch(lmpc_handle* h, const FtocpArgs& a, bool lmpc_mode) {
+static int launch(lmpc_handle* h, const FtocpArgs& a, bool lmpc_mode, cudaStream_t st) {
     const int N = h->N, M = lmpc_mode ? h->M : 0;
-#define LCASE(n, m) if (N == n && M == m) return launch_t<n, m>(h, a);
+#define LCASE(n, m) if (N == n && M == m) return launch_t<n, m>(h, a, st);
     LCASE(6, 0) LCASE(12, 0) LCASE(14, 0) LCASE(24, 0) LCASE(48, 0)
     LCASE(6, 48) LCASE(12, 48) LCASE(14, 48) LCASE(24, 48) LCASE(48, 48)
 #undef LCASE
@@ -291,6 +292,7 @@ int lmpc_create(const lmpc_params* p, int batch, int device, lmpc_handle** out) 
     if (rc != LMPC_OK) { delete h; return rc; }
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
     const size_t B = batch, N = p->N, M = p->numSS_Points > 0 ? p->numSS_Points : 1;
 #define DALLOC(ptr, count) CK(cudaMalloc((void**)&h->ptr, sizeof(*h->ptr) * (count)))
     DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54);
@@ -319,6 +321,7 @@ int lmpc_destroy(lmpc_handle* h) {
     cudaFree(h->d_status);
     cudaFree(h->d_iters);
     cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 4; ++i) cudaStreamDestroy(h->cstream[i]);
     delete h;
     return LMPC_OK;
 }
@@ -356,7 +359,7 @@ int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, co
     a.SS = SS_sel; a.Qfun = Qfun_sel; a.SuccSS = Succ_SS; a.SuccU = Succ_uSS;
     a.xPred = xPred; a.uPred = uPred; a.slack = slack; a.lambd = lambd; a.slackT = slackTerminal;
     a.zt = zt; a.ztu = zt_u; a.status = status; a.iters = iters; a.resid = resid;
-    return launch(h, a, lm);
+    return launch(h, a, lm, h->stream);
 }
 
 int lmpc_solve_mpc_dev(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
@@ -375,46 +378,60 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
     if (lm && (h->M <= 0 || !Qfun_sel)) return fail(LMPC_E_INVALID, "handle was created without a safe set (numSS_Points == 0)");
     CK(cudaSetDevice(h->device));
     const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
-    cudaStream_t s = h->stream;
     const size_t D = sizeof(double);
-    CK(cudaMemcpyAsync(h->d_x0, x0, B * 6 * D, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_uOld, uOld, B * 2 * D, cudaMemcpyHostToDevice, s));
     long long dis, dss;
-    if (abc_inst_stride == 0 && abc_stage_stride == 0) {            // one shared LTI model
-        CK(cudaMemcpyAsync(h->d_abc, abc, 54 * D, cudaMemcpyHostToDevice, s));
-        dis = 0; dss = 0;
-    } else if (abc_inst_stride == (long long)N * 54 && abc_stage_stride == 54) {
-        CK(cudaMemcpyAsync(h->d_abc, abc, B * N * 54 * D, cudaMemcpyHostToDevice, s));
-        dis = N * 54; dss = 54;
-    } else if (abc_inst_stride == 0 && abc_stage_stride == 54) {     // one shared LTV model
-        CK(cudaMemcpyAsync(h->d_abc, abc, N * 54 * D, cudaMemcpyHostToDevice, s));
-        dis = 0; dss = 54;
-    } else {
-        return fail(LMPC_E_INVALID, "host entry supports abc strides (N*54,54), (0,54) or (0,0)");
+    bool per_inst = false;
+    if (abc_inst_stride == 0 && abc_stage_stride == 0) { dis = 0; dss = 0; }                       // one shared LTI model
+    else if (abc_inst_stride == (long long)N * 54 && abc_stage_stride == 54) { dis = N * 54; dss = 54; per_inst = true; }
+    else if (abc_inst_stride == 0 && abc_stage_stride == 54) { dis = 0; dss = 54; }                // one shared LTV model
+    else return fail(LMPC_E_INVALID, "host entry supports abc strides (N*54,54), (0,54) or (0,0)");
+    CK(cudaStreamSynchronize(h->stream));    // earlier work of this handle is done before the chunk streams start
+    if (!per_inst) {
+        CK(cudaMemcpyAsync(h->d_abc, abc, (dss ? N * 54 : 54) * D, cudaMemcpyHostToDevice, h->cstream[0]));
+        CK(cudaStreamSynchronize(h->cstream[0]));
     }
-    if (lm) {
-        CK(cudaMemcpyAsync(h->d_SS, SS_sel, B * 6 * M * D, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(h->d_Qfun, Qfun_sel, B * M * D, cudaMemcpyHostToDevice, s));
-        if (Succ_SS) CK(cudaMemcpyAsync(h->d_SuccSS, Succ_SS, B * 6 * M * D, cudaMemcpyHostToDevice, s));
-        if (Succ_uSS) CK(cudaMemcpyAsync(h->d_SuccU, Succ_uSS, B * 2 * M * D, cudaMemcpyHostToDevice, s));
+    // Chunk pipeline: the batch is cut into up to four instance ranges, each on its own stream, so that the H2D copy
+    // of range i+1, the solve of range i and the D2H copy of range i-1 overlap (PCIe is full duplex).
+    const int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    for (int ci = 0; ci < nchunk; ++ci) {
+        const size_t lo = B * ci / nchunk, hi = B * (ci + 1) / nchunk, nb = hi - lo;
+        cudaStream_t s = h->cstream[ci];
+        CK(cudaMemcpyAsync(h->d_x0 + lo * 6, x0 + lo * 6, nb * 6 * D, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->d_uOld + lo * 2, uOld + lo * 2, nb * 2 * D, cudaMemcpyHostToDevice, s));
+        if (per_inst) CK(cudaMemcpyAsync(h->d_abc + lo * N * 54, abc + lo * N * 54, nb * N * 54 * D, cudaMemcpyHostToDevice, s));
+        if (lm) {
+            CK(cudaMemcpyAsync(h->d_SS + lo * 6 * M, SS_sel + lo * 6 * M, nb * 6 * M * D, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(h->d_Qfun + lo * M, Qfun_sel + lo * M, nb * M * D, cudaMemcpyHostToDevice, s));
+            if (Succ_SS) CK(cudaMemcpyAsync(h->d_SuccSS + lo * 6 * M, Succ_SS + lo * 6 * M, nb * 6 * M * D, cudaMemcpyHostToDevice, s));
+            if (Succ_uSS) CK(cudaMemcpyAsync(h->d_SuccU + lo * 2 * M, Succ_uSS + lo * 2 * M, nb * 2 * M * D, cudaMemcpyHostToDevice, s));
+        }
+        FtocpArgs a;
+        a.batch = (int)nb;
+        a.x0 = h->d_x0 + lo * 6; a.uOld = h->d_uOld + lo * 2;
+        a.abc = per_inst ? h->d_abc + lo * N * 54 : h->d_abc;
+        a.abc_inst_stride = dis; a.abc_stage_stride = dss;
+        a.SS = lm ? h->d_SS + lo * 6 * M : nullptr; a.Qfun = lm ? h->d_Qfun + lo * M : nullptr;
+        a.SuccSS = (lm && Succ_SS) ? h->d_SuccSS + lo * 6 * M : nullptr; a.SuccU = (lm && Succ_uSS) ? h->d_SuccU + lo * 2 * M : nullptr;
+        a.xPred = h->d_xPred + lo * (N + 1) * 6; a.uPred = h->d_uPred + lo * N * 2;
+        a.slack = slack ? h->d_slack + lo * N * 2 : nullptr;
+        a.lambd = (lm && lambd) ? h->d_lambd + lo * M : nullptr;
+        a.slackT = (lm && slackTerminal) ? h->d_slackT + lo * 6 : nullptr;
+        a.zt = (lm && zt) ? h->d_zt + lo * 6 : nullptr; a.ztu = (lm && zt_u) ? h->d_ztu + lo * 2 : nullptr;
+        a.status = h->d_status + lo; a.iters = h->d_iters + lo; a.resid = h->d_resid + lo * 3;
+        int rc = launch(h, a, lm, s);
+        if (rc != LMPC_OK) return rc;
+        CK(cudaMemcpyAsync(xPred + lo * (N + 1) * 6, h->d_xPred + lo * (N + 1) * 6, nb * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(uPred + lo * N * 2, h->d_uPred + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
+        if (slack) CK(cudaMemcpyAsync(slack + lo * N * 2, h->d_slack + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
+        if (lm && lambd) CK(cudaMemcpyAsync(lambd + lo * M, h->d_lambd + lo * M, nb * M * D, cudaMemcpyDeviceToHost, s));
+        if (lm && slackTerminal) CK(cudaMemcpyAsync(slackTerminal + lo * 6, h->d_slackT + lo * 6, nb * 6 * D, cudaMemcpyDeviceToHost, s));
+        if (lm && zt && Succ_SS) CK(cudaMemcpyAsync(zt + lo * 6, h->d_zt + lo * 6, nb * 6 * D, cudaMemcpyDeviceToHost, s));
+        if (lm && zt_u && Succ_uSS) CK(cudaMemcpyAsync(zt_u + lo * 2, h->d_ztu + lo * 2, nb * 2 * D, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + lo, h->d_status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(iters + lo, h->d_iters + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(resid + lo * 3, h->d_resid + lo * 3, nb * 3 * D, cudaMemcpyDeviceToHost, s));
     }
-    int rc = lmpc_solve_lmpc_dev(h, h->d_x0, h->d_uOld, h->d_abc, dis, dss, lm ? h->d_SS : nullptr, lm ? h->d_Qfun : nullptr,
-                                 (lm && Succ_SS) ? h->d_SuccSS : nullptr, (lm && Succ_uSS) ? h->d_SuccU : nullptr, h->d_xPred,
-                                 h->d_uPred, slack ? h->d_slack : nullptr, (lm && lambd) ? h->d_lambd : nullptr,
-                                 (lm && slackTerminal) ? h->d_slackT : nullptr, (lm && zt) ? h->d_zt : nullptr,
-                                 (lm && zt_u) ? h->d_ztu : nullptr, h->d_status, h->d_iters, h->d_resid);
-    if (rc != LMPC_OK) return rc;
-    CK(cudaMemcpyAsync(xPred, h->d_xPred, B * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(uPred, h->d_uPred, B * N * 2 * D, cudaMemcpyDeviceToHost, s));
-    if (slack) CK(cudaMemcpyAsync(slack, h->d_slack, B * N * 2 * D, cudaMemcpyDeviceToHost, s));
-    if (lm && lambd) CK(cudaMemcpyAsync(lambd, h->d_lambd, B * M * D, cudaMemcpyDeviceToHost, s));
-    if (lm && slackTerminal) CK(cudaMemcpyAsync(slackTerminal, h->d_slackT, B * 6 * D, cudaMemcpyDeviceToHost, s));
-    if (lm && zt && Succ_SS) CK(cudaMemcpyAsync(zt, h->d_zt, B * 6 * D, cudaMemcpyDeviceToHost, s));
-    if (lm && zt_u && Succ_uSS) CK(cudaMemcpyAsync(zt_u, h->d_ztu, B * 2 * D, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(status, h->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(resid, h->d_resid, B * 3 * D, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    for (int ci = 0; ci < nchunk; ++ci) CK(cudaStreamSynchronize(h->cstream[ci]));
     return LMPC_OK;
 }
 
