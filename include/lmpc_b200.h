@@ -172,6 +172,21 @@ int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev);
  * "Succ_SS","Succ_uSS","status","iters","resid","flags","xLin","uLin". */
 void* lmpc_device_buffer(lmpc_handle* h, const char* name);
 
+/* ===== device-resident closed loop (the caller of the hot path) =======================================
+ * Simulator.sim's loop body (SysModel.py:33-48) for every instance without host round trips:
+ *   Controller.solve(x) -> u = uPred[0] -> Controller.addPoint(x,u) -> x+ = Simulator.dynModel(x, x_glob, u)
+ * (100 explicit-Euler sub-steps of the dynamic bicycle model with Pacejka tyres, SysModel.py:56-147).
+ * z_host[B,3] = standard-normal draws for the (vx, vy, wz) noise in the reference's order; NULL = Philox4x32-10 on the
+ * device keyed by (seed, instance, step).  The visited (x, u) pairs are recorded per instance (Tcl rows). */
+int lmpc_rollout_create(lmpc_handle* h, int Tcl);
+int lmpc_rollout_set_state(lmpc_handle* h, const double* x, const double* xglob);              /* [B,6] host, may be NULL */
+int lmpc_rollout_get_state(lmpc_handle* h, double* x, double* xglob, int* done, int* cl_len);  /* any may be NULL      */
+int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned long long seed);
+int lmpc_rollout_get_lap(lmpc_handle* h, int inst, int* T, double* x, double* u);              /* closed-loop record   */
+/* Lap hand-over on the device = LMPC.addTrajectory + PredictiveModel.addTrajectory of the lap just driven (either slot may
+ * be -1), then s -= TrackLength (SysModel.py:50), record restarted, timeStep = 0 (PC.py:445). */
+int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slot);
+
 int lmpc_sizeof_params(void);
 int lmpc_sizeof_model_params(void);
 

@@ -78,7 +78,14 @@ class BatchedController:
     def model_add_trajectory(self, inst, x, u):
         """PredictiveModel.py:35-46: keep laps sorted by length; only the trToUse fastest are ever read."""
         x = np.ascontiguousarray(x, float); u = np.ascontiguousarray(u, float)
-        T = x.shape[0]
+        slot = self._model_slot_for(inst, x.shape[0])
+        if slot >= 0:
+            nat.check(self._lib.lmpc_model_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u)))
+        self._push_used(inst)
+
+    def _model_slot_for(self, inst, T):
+        """Ordering rule of PredictiveModel.py:35-46 for a new lap of T rows; returns the device slot or -1 when the lap
+        can never be among the trToUse fastest (it is then not stored on the device)."""
         laps = self.model_laps[inst]
         lapno = self.model_count[inst]
         self.model_count[inst] += 1
@@ -93,9 +100,8 @@ class BatchedController:
                 keep = {ln for (_, ln) in laps[:self.trToUse]}
                 victims = [ln for ln in stored if ln not in keep]
                 self.model_book[inst].drop(victims[-1] if victims else stored[-1])
-            slot = self.model_book[inst].take(lapno)
-            nat.check(self._lib.lmpc_model_put_lap(self._h, inst, slot, T, nat.ptr(x), nat.ptr(u)))
-        self._push_used(inst)
+            return self.model_book[inst].take(lapno)
+        return -1
 
     def _push_used(self, inst=None):
         used = np.zeros((self.B, self.trToUse), np.int32)
@@ -115,7 +121,18 @@ class BatchedController:
         restored verbatim."""
         x = np.ascontiguousarray(x, float); u = np.ascontiguousarray(u, float)
         lapno = self.it[inst]
-        self.LapTime[inst].append(int(x.shape[0] if lap_time is None else lap_time))
+        slot = self._ss_slot_for(inst, int(x.shape[0] if lap_time is None else lap_time))
+        q = None if qfun is None else np.ascontiguousarray(qfun, float)
+        nat.check(self._lib.lmpc_ss_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u), nat.ptr(q)))
+        first = (lapno == 0)
+        self.it[inst] += 1
+        self._sel_dirty = True
+        return first, slot
+
+    def _ss_slot_for(self, inst, lap_time):
+        """LMPC.addTrajectory bookkeeping (PC.py:425-428): new lap number = it; keep the numSS_it fastest + lap it-1."""
+        lapno = self.it[inst]
+        self.LapTime[inst].append(int(lap_time))
         book = self.ss_book[inst]
         if not book.free:
             order = list(np.argsort(np.array(self.LapTime[inst]), kind="stable"))
@@ -124,13 +141,7 @@ class BatchedController:
             if not victims:
                 raise RuntimeError("safe-set pool too small")
             book.drop(max(victims, key=lambda ln: self.LapTime[inst][ln]))
-        slot = book.take(lapno)
-        q = None if qfun is None else np.ascontiguousarray(qfun, float)
-        nat.check(self._lib.lmpc_ss_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u), nat.ptr(q)))
-        first = (lapno == 0)
-        self.it[inst] += 1
-        self._sel_dirty = True
-        return first, slot
+        return book.take(lapno)
 
     def _push_selection(self):
         nit = max(self.numSS_it, 1)
@@ -225,6 +236,57 @@ class BatchedController:
         if self.lmpc and self._sel_dirty:
             self._push_selection()
         nat.check(self._lib.lmpc_step_dev(self._h, 1 if self.lmpc else 0, nat.ptr(x0_dev)))
+
+    # ------------------------------------------------------------------ device-resident closed loop
+    def enable_rollout(self, Tcl=512):
+        nat.check(self._lib.lmpc_rollout_create(self._h, int(Tcl)))
+        self.Tcl = int(Tcl)
+
+    def rollout_set_state(self, x, xglob):
+        x = np.ascontiguousarray(np.asarray(x, float).reshape(self.B, 6))
+        g = np.ascontiguousarray(np.asarray(xglob, float).reshape(self.B, 6))
+        nat.check(self._lib.lmpc_rollout_set_state(self._h, nat.ptr(x), nat.ptr(g)))
+
+    def rollout_state(self):
+        o = dict(x=np.zeros((self.B, 6)), xglob=np.zeros((self.B, 6)), done=np.zeros(self.B, np.int32), cl_len=np.zeros(self.B, np.int32))
+        nat.check(self._lib.lmpc_rollout_get_state(self._h, nat.ptr(o["x"]), nat.ptr(o["xglob"]), nat.ptr(o["done"]), nat.ptr(o["cl_len"])))
+        return o
+
+    def rollout_step(self, z=None, seed=0):
+        """Simulator.sim loop body (SysModel.py:34-48) for every instance on the device.  z[B,3]: standard-normal draws for
+        the process noise (reference order vx, vy, wz); None = Philox on the device."""
+        if self.lmpc and self._sel_dirty:
+            self._push_selection()
+        zz = None if z is None else np.ascontiguousarray(np.asarray(z, float).reshape(self.B, 3))
+        nat.check(self._lib.lmpc_rollout_step(self._h, 1 if self.lmpc else 0, nat.ptr(zz), int(seed)))
+
+    def rollout_done(self):
+        d = np.zeros(self.B, np.int32); n = np.zeros(self.B, np.int32)
+        nat.check(self._lib.lmpc_rollout_get_state(self._h, None, None, nat.ptr(d), nat.ptr(n)))
+        return d, n
+
+    def rollout_get_lap(self, inst):
+        T = C.c_int(0)
+        x, u = np.zeros((self.Tcl, 6)), np.zeros((self.Tcl, 2))
+        nat.check(self._lib.lmpc_rollout_get_lap(self._h, int(inst), C.byref(T), nat.ptr(x), nat.ptr(u)))
+        return x[:T.value].copy(), u[:T.value].copy()
+
+    def rollout_finish_laps(self, done, cl_len, to_model=True):
+        """main.py:113-119 for every instance whose lap just ended: lmpc.addTrajectory + predictiveModel.addTrajectory of the
+        lap recorded on the device (no host copy of the lap), then the next lap starts from xF (SysModel.py:50)."""
+        finished = np.nonzero(done)[0]
+        for b in finished:
+            T = int(cl_len[b])
+            ss_slot = self._ss_slot_for(b, T) if self.lmpc else -1
+            m_slot = self._model_slot_for(b, T) if to_model else -1
+            nat.check(self._lib.lmpc_rollout_commit_lap(self._h, int(b), int(ss_slot), int(m_slot)))
+            if self.lmpc:
+                self.it[b] += 1
+        if len(finished):
+            self._sel_dirty = True
+            if to_model:
+                self._push_used()
+        return finished
 
     def device_buffer(self, name):
         return int(self._lib.lmpc_device_buffer(self._h, name.encode()) or 0)

@@ -183,6 +183,12 @@ struct lmpc_handle {
     LapPool ss, mdl;
     int *d_used, *d_sel, *d_isprev, *d_prevslot, *d_timeStep, *d_hasPred, *d_flags, *d_minidx;
     double *d_xLin, *d_uLin, *d_ztState, *d_ztFixed, *d_OldInput, *d_xPredPrev, *d_tmpx, *d_tmpu;
+    // device-resident closed loop (lmpc_rollout_create)
+    bool has_rollout;
+    int Tcl;
+    unsigned long long sim_step;
+    double *d_rx[2], *d_rg[2], *d_clx, *d_clu, *d_z;
+    int *d_cllen, *d_done, cur;
 };
 
 static bool inv6(const double* A, double* Ai) {
@@ -309,6 +315,10 @@ int lmpc_destroy(lmpc_handle* h) {
     if (!h) return LMPC_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->has_rollout) {
+        void* rp[] = {h->d_rx[0], h->d_rx[1], h->d_rg[0], h->d_rg[1], h->d_clx, h->d_clu, h->d_z, h->d_cllen, h->d_done};
+        for (void* q : rp) cudaFree(q);
+    }
     if (h->has_store) {
         void* ptrs[] = {h->ss.x, h->ss.u, h->ss.q, h->ss.len, h->mdl.x, h->mdl.u, h->mdl.len, h->d_used, h->d_sel, h->d_isprev,
                         h->d_prevslot, h->d_timeStep, h->d_hasPred, h->d_flags, h->d_minidx, h->d_xLin, h->d_uLin, h->d_ztState,
@@ -575,7 +585,7 @@ int lmpc_ss_add_point(lmpc_handle* h, const double* x, const double* u) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->d_tmpx, x, sizeof(double) * h->batch * 6, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_tmpu, u, sizeof(double) * h->batch * 2, cudaMemcpyHostToDevice, h->stream));
-    ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, h->d_tmpx, h->d_tmpu,
+    ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, h->d_tmpx, h->d_tmpu, 2,
                                                                         h->mc.TrackLength, h->d_flags);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -774,6 +784,136 @@ void* lmpc_device_buffer(lmpc_handle* h, const char* name) {
         {"uLin", h->d_uLin}, {"x0", h->d_x0}, {"OldInput", h->d_OldInput}};
     for (auto& e : tab) if (strcmp(e.n, name) == 0) return e.p;
     return nullptr;
+}
+
+// ================================================================================================
+// device-resident closed loop: Simulator.sim's loop body (SysModel.py:33-48) without host round trips
+// ================================================================================================
+int lmpc_rollout_create(lmpc_handle* h, int Tcl) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (h->has_rollout) return fail(LMPC_E_STATE, "rollout buffers already created");
+    if (Tcl < 16) return fail(LMPC_E_INVALID, "Tcl too small");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc((void**)&h->d_rx[i], sizeof(double) * B * 6));
+        CK(cudaMalloc((void**)&h->d_rg[i], sizeof(double) * B * 6));
+    }
+    CK(cudaMalloc((void**)&h->d_clx, sizeof(double) * B * Tcl * 6));
+    CK(cudaMalloc((void**)&h->d_clu, sizeof(double) * B * Tcl * 2));
+    CK(cudaMalloc((void**)&h->d_z, sizeof(double) * B * 3));
+    CK(cudaMalloc((void**)&h->d_cllen, sizeof(int) * B));
+    CK(cudaMalloc((void**)&h->d_done, sizeof(int) * B));
+    CK(cudaMemsetAsync(h->d_cllen, 0, sizeof(int) * B, h->stream));
+    CK(cudaMemsetAsync(h->d_done, 0, sizeof(int) * B, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->Tcl = Tcl; h->cur = 0; h->sim_step = 0; h->has_rollout = true;
+    return LMPC_OK;
+}
+
+static int need_rollout(lmpc_handle* h) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!h->has_rollout) return fail(LMPC_E_STATE, "call lmpc_rollout_create first");
+    return LMPC_OK;
+}
+
+int lmpc_rollout_set_state(lmpc_handle* h, const double* x, const double* xglob) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (x) CK(cudaMemcpyAsync(h->d_rx[h->cur], x, sizeof(double) * h->batch * 6, cudaMemcpyHostToDevice, h->stream));
+    if (xglob) CK(cudaMemcpyAsync(h->d_rg[h->cur], xglob, sizeof(double) * h->batch * 6, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_rollout_get_state(lmpc_handle* h, double* x, double* xglob, int* done, int* cl_len) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch;
+    if (x) CK(cudaMemcpyAsync(x, h->d_rx[h->cur], sizeof(double) * B * 6, cudaMemcpyDeviceToHost, h->stream));
+    if (xglob) CK(cudaMemcpyAsync(xglob, h->d_rg[h->cur], sizeof(double) * B * 6, cudaMemcpyDeviceToHost, h->stream));
+    if (done) CK(cudaMemcpyAsync(done, h->d_done, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (cl_len) CK(cudaMemcpyAsync(cl_len, h->d_cllen, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+// One closed-loop step for every instance, all on the device (SysModel.py:34-48):
+//   Controller.solve(x) -> u = uPred[0] -> Controller.addPoint(x, u) (LMPC) -> x+ = dynModel(x, x_glob, u); done = s+ > TrackLength
+int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned long long seed) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const double* xc = h->d_rx[h->cur];
+    rc = lmpc_step_dev(h, mode, xc);
+    if (rc) return rc;
+    if (mode == 1) {
+        ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, xc, h->d_uPred,
+                                                                            (long long)h->N * 2, h->mc.TrackLength, h->d_flags);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    if (z_host) CK(cudaMemcpyAsync(h->d_z, z_host, sizeof(double) * h->batch * 3, cudaMemcpyHostToDevice, h->stream));
+    SimArgs sa;
+    sa.batch = h->batch; sa.x = xc; sa.xg = h->d_rg[h->cur]; sa.u = h->d_uPred; sa.u_stride = (long long)h->N * 2;
+    sa.z = z_host ? h->d_z : nullptr; sa.seed = seed; sa.step = h->sim_step;
+    sa.xn = h->d_rx[h->cur ^ 1]; sa.xgn = h->d_rg[h->cur ^ 1];
+    sa.cl_x = h->d_clx; sa.cl_u = h->d_clu; sa.cl_len = h->d_cllen; sa.Tcl = h->Tcl; sa.done = h->d_done; sa.active = nullptr;
+    sim_step_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->mc, sa);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    h->cur ^= 1;
+    h->sim_step += 1;
+    return LMPC_OK;
+}
+
+int lmpc_rollout_get_lap(lmpc_handle* h, int inst, int* T, double* x, double* u) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (inst < 0 || inst >= h->batch || !T) return fail(LMPC_E_INVALID, "bad instance");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(T, h->d_cllen + inst, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (x) CK(cudaMemcpyAsync(x, h->d_clx + (size_t)inst * h->Tcl * 6, sizeof(double) * (*T) * 6, cudaMemcpyDeviceToHost, h->stream));
+    if (u) CK(cudaMemcpyAsync(u, h->d_clu + (size_t)inst * h->Tcl * 2, sizeof(double) * (*T) * 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+// Hand the finished lap of `inst` over to the stores without leaving the device: safe-set slot (computeCost on the
+// device) and/or regression slot (either may be -1), then restart the record; the curvilinear state is moved back by one
+// track length (SysModel.py:50) and the controller's step counter is reset (PC.py:445).
+int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slot) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (inst < 0 || inst >= h->batch || ss_slot >= h->ss.cap || model_slot >= h->mdl.cap) return fail(LMPC_E_INVALID, "bad instance/slot");
+    CK(cudaSetDevice(h->device));
+    if (ss_slot >= 0) {
+        commit_lap_kernel<<<1, 256, 0, h->stream>>>(h->ss, inst, ss_slot, h->d_clx, h->d_clu, h->d_cllen, h->Tcl);
+        rollout_cost_kernel<<<1, 32, 0, h->stream>>>(h->ss, inst, ss_slot, h->mc.TrackLength);
+        h->launches += 2;
+    }
+    if (model_slot >= 0) {
+        commit_lap_kernel<<<1, 256, 0, h->stream>>>(h->mdl, inst, model_slot, h->d_clx, h->d_clu, h->d_cllen, h->Tcl);
+        h->launches += 1;
+    }
+    CK(cudaGetLastError());
+    // restart: cl_len = 0, s -= TrackLength, timeStep = 0, done = 0
+    double s;
+    CK(cudaMemcpyAsync(&s, h->d_rx[h->cur] + (size_t)inst * 6 + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    s -= h->mc.TrackLength;
+    const int zero = 0;
+    CK(cudaMemcpyAsync(h->d_rx[h->cur] + (size_t)inst * 6 + 4, &s, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_cllen + inst, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_done + inst, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_timeStep + inst, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
 }
 
 }  // extern "C"

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(32 * 8) ss_select_kernel(const K2Args a) {
 // ------------------------------------------------------------------------------------------------
 // LMPC.addPoint (PC.py:466-476): append x + [0,0,0,0,L,0], u to lap it-1; Qfun extends by last - 1.
 __global__ void ss_add_point_kernel(int batch, LapPool pool, const int* prev_slot, const double* x, const double* u,
-                                    double TrackLength, int* status) {
+                                    long long u_stride, double TrackLength, int* status) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const int slot = prev_slot[b];
@@ -536,10 +536,20 @@ __global__ void ss_add_point_kernel(int batch, LapPool pool, const int* prev_slo
     double* Q = pool.q + lap * pool.Tmax;
 #pragma unroll
     for (int j = 0; j < 6; ++j) X[j] = x[(size_t)b * 6 + j] + (j == 4 ? TrackLength : 0.0);
-    U[0] = u[(size_t)b * 2];
-    U[1] = u[(size_t)b * 2 + 1];
+    U[0] = u[(size_t)b * u_stride];
+    U[1] = u[(size_t)b * u_stride + 1];
     Q[T] = Q[T - 1] - 1.0;
     pool.len[lap] = T + 1;
+}
+
+// Copy the closed-loop record of instance b into a pool slot (device to device): the device-resident counterpart of
+// LMPC.addTrajectory / PredictiveModel.addTrajectory receiving the lap that Simulator.sim just returned.
+__global__ void commit_lap_kernel(LapPool pool, int b, int slot, const double* cl_x, const double* cl_u, const int* cl_len, int Tcl) {
+    const int T = min(cl_len[b], pool.Tmax);
+    const size_t lap = pool.lap_index(b, slot);
+    for (int e = threadIdx.x; e < T * 6; e += blockDim.x) pool.x[lap * pool.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
+    for (int e = threadIdx.x; e < T * 2; e += blockDim.x) pool.u[lap * pool.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
+    if (threadIdx.x == 0) pool.len[lap] = T;
 }
 
 // LMPC.computeCost (PC.py:447-464) for one (instance, slot): backward count of steps to the finish line.
@@ -594,6 +604,104 @@ __global__ void shift_state_kernel(const ShiftArgs a) {
     }
     if (threadIdx.x < 2) a.OldInput[(size_t)b * 2 + threadIdx.x] = a.uPred[(size_t)b * N * 2 + threadIdx.x];
     if (threadIdx.x == 0) { a.timeStep[b] += 1; a.has_pred[b] = 1; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Simulator.dynModel (src/fnc/simulator/SysModel.py:56-147): 100 explicit-Euler sub-steps (1 ms) of the dynamic
+// bicycle model with Pacejka tyres in the curvilinear and the global frame, then clipped Gaussian noise on
+// (vx, vy, wz).  One thread per instance.  `z` = three standard-normal draws per instance (the reference consumes
+// np.random.randn() in this order: vx, vy, wz); when z == nullptr they come from Philox4x32-10 keyed by
+// (seed, instance, step) — statistical, not bit-wise, parity with the reference's unseeded global RNG.
+// Also appends (x, u) to the closed-loop buffer and flags lap completion (SysModel.py:45-47).
+struct SimArgs {
+    int batch;
+    const double* x;       // [B][6] curvilinear state
+    const double* xg;      // [B][6] global state (psi, X, Y at 3..5)
+    const double* u;       // [B][2]  or uPred [B][N][2] with u_stride = N*2
+    long long u_stride;
+    const double* z;       // [B][3] or nullptr
+    unsigned long long seed, step;
+    double* xn;            // [B][6]
+    double* xgn;           // [B][6]
+    double* cl_x;          // [B][Tcl][6] closed-loop record (may be nullptr)
+    double* cl_u;          // [B][Tcl][2]
+    int* cl_len;           // [B]
+    int Tcl;
+    int* done;             // [B] 1 when s_next > TrackLength
+    const int* active;     // [B] or nullptr: instances with active == 0 are left untouched
+};
+
+}  // namespace lmpc
+#include <curand_kernel.h>
+namespace lmpc {
+
+__global__ void sim_step_kernel(const __grid_constant__ ModelConst m, const SimArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    if (a.active && !a.active[b]) return;
+    // vehicle parameters, SysModel.py:61-70
+    const double mass = 1.98, lf = 0.125, lr = 0.125, Iz = 0.024;
+    const double Df = 0.8 * mass * 9.81 / 2.0, Cf = 1.25, Bf = 1.0;
+    const double Dr = 0.8 * mass * 9.81 / 2.0, Cr = 1.25, Br = 1.0;
+    const double h = 0.001;
+    const double* x = a.x + (size_t)b * 6;
+    const double* g = a.xg + (size_t)b * 6;
+    const double delta = a.u[(size_t)b * a.u_stride], acc = a.u[(size_t)b * a.u_stride + 1];
+    double vx = x[0], vy = x[1], wz = x[2], epsi = x[3], s = x[4], ey = x[5];
+    double psi = g[3], X = g[4], Y = g[5];
+    if (a.cl_x) {
+        const int T = a.cl_len[b];
+        if (T < a.Tcl) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a.cl_x[((size_t)b * a.Tcl + T) * 6 + j] = x[j];
+            a.cl_u[((size_t)b * a.Tcl + T) * 2] = delta;
+            a.cl_u[((size_t)b * a.Tcl + T) * 2 + 1] = acc;
+            a.cl_len[b] = T + 1;
+        }
+    }
+    const double sd = sin(delta), cd = cos(delta);
+    int i = 0;
+    int okc = 1;
+    while ((i + 1) * h <= m.dt) {
+        const double af = delta - atan2(vy + lf * wz, vx);
+        const double ar = -atan2(vy - lf * wz, vx);
+        const double Fyf = Df * sin(Cf * atan(Bf * af));
+        const double Fyr = Dr * sin(Cr * atan(Br * ar));
+        const double nvx = vx + h * (acc - 1 / mass * Fyf * sd + wz * vy);
+        const double nvy = vy + h * (1 / mass * (Fyf * cd + Fyr) - wz * vx);
+        const double nwz = wz + h * (1 / Iz * (lf * Fyf * cd - lr * Fyr));
+        const double npsi = psi + h * wz;
+        const double nX = X + h * (vx * cos(psi) - vy * sin(psi));
+        const double nY = Y + h * (vx * sin(psi) + vy * cos(psi));
+        const double cur = curvature_lookup(m, s, &okc);
+        const double ce = cos(epsi), se = sin(epsi);
+        const double nepsi = epsi + h * (wz - (vx * ce - vy * se) / (1 - cur * ey) * cur);
+        const double ns = s + h * ((vx * ce - vy * se) / (1 - cur * ey));
+        const double ney = ey + h * (vx * se + vy * ce);
+        psi = npsi; X = nX; Y = nY;
+        vx = nvx; vy = nvy; wz = nwz; epsi = nepsi; s = ns; ey = ney;
+        ++i;
+    }
+    double z0, z1, z2;
+    if (a.z) {
+        z0 = a.z[(size_t)b * 3]; z1 = a.z[(size_t)b * 3 + 1]; z2 = a.z[(size_t)b * 3 + 2];
+    } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(a.seed, (unsigned long long)b, a.step, &st);
+        const double2 n01 = curand_normal2_double(&st);
+        const double2 n23 = curand_normal2_double(&st);
+        z0 = n01.x; z1 = n01.y; z2 = n23.x;
+    }
+    const double n_vx = fmax(-0.05, fmin(z0 * 0.01, 0.05));
+    const double n_vy = fmax(-0.05, fmin(z1 * 0.01, 0.05));
+    const double n_wz = fmax(-0.05, fmin(z2 * 0.005, 0.05));
+    double* xn = a.xn + (size_t)b * 6;
+    double* gn = a.xgn + (size_t)b * 6;
+    // SysModel.py:143-147: the noise is added to the curvilinear copy only
+    gn[0] = vx; gn[1] = vy; gn[2] = wz; gn[3] = psi; gn[4] = X; gn[5] = Y;
+    xn[0] = vx + 0.01 * n_vx; xn[1] = vy + 0.01 * n_vy; xn[2] = wz + 0.01 * n_wz;
+    xn[3] = epsi; xn[4] = s; xn[5] = ey;
+    if (a.done) a.done[b] = (s > m.TrackLength) ? 1 : 0;
 }
 
 }  // namespace lmpc

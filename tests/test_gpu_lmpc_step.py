@@ -205,3 +205,70 @@ def test_config3_workload_step_vs_oracle(track):
         assert np.max(np.abs(o["xPred"][b] - lm.xPred)) < 1e-6, b
         assert np.max(np.abs(o["zt"][b] - lm.zt)) < 1e-5, b
     c.close()
+
+
+def test_device_resident_closed_loop_matches_host_driven_loop(gold, track):
+    """§8f rank 1: the on-GPU Simulator.dynModel + device addPoint + device lap hand-over.  Two LMPC laps driven entirely
+    on the device (noise draws supplied from the host RNG in the reference's order) against the same laps driven step by
+    step through the oracle's restated simulator."""
+    _need_gpu()
+    from oracle import vehicle
+    N = 12
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    xP, uP = gold["pid_x"].copy(), gold["pid_u"].copy()
+
+    def fresh():
+        c = BatchedController(par, 1, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points,
+                              numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536, ss_cap=6, model_cap=5)
+        for _ in range(4):
+            c.model_add_trajectory(0, xP, uP)
+        for _ in range(4):
+            c.add_trajectory(0, xP, uP)
+        c.set_state(xLin=xP[1:N + 2], uLin=uP[1:N + 1], zt=np.array([0.0, 0, 0, 0, 10.0, 0]), OldInput=np.zeros(2), timeStep=[0], has_pred=[0])
+        return c
+    x0 = np.array([0.5, 0, 0, 0, 0, 0.0])
+    # (a) host-driven reference loop: GPU controller + oracle simulator
+    ca = fresh()
+    rng = np.random.default_rng(42)
+    zs = rng.standard_normal((600, 3))
+    xa, ga = x0.copy(), x0.copy()
+    lapsA, cur = [], []
+    k = 0
+    out = ca.alloc_step_outputs()
+    for lap in range(2):
+        xs, us = [], []
+        while True:
+            o = ca.step(xa, out=out)
+            u = o["uPred"][0, 0].copy()
+            ca.add_point(xa, u)
+            xs.append(xa.copy()); us.append(u)
+            zi = iter(zs[k]); k += 1
+            fake = type("R", (), {"standard_normal": lambda self, it=zi: next(it)})()
+            xa, ga = vehicle.dyn_model(track, xa, ga, u, rng=fake)
+            if xa[4] > track.TrackLength:
+                break
+        xl, ul = np.array(xs), np.array(us)
+        lapsA.append((xl, ul))
+        ca.add_trajectory(0, xl, ul)
+        ca.model_add_trajectory(0, xl, ul)
+        xa = xa - np.array([0, 0, 0, 0, track.TrackLength, 0])
+    ca.close()
+    # (b) device-resident loop
+    cb = fresh()
+    cb.enable_rollout(Tcl=512)
+    cb.rollout_set_state(x0, x0)
+    lapsB = []
+    k = 0
+    while len(lapsB) < 2:
+        cb.rollout_step(z=zs[k]); k += 1
+        done, n = cb.rollout_done()
+        if done[0]:
+            lapsB.append(cb.rollout_get_lap(0))
+            cb.rollout_finish_laps(done, n)
+    for (xa_, ua_), (xb_, ub_) in zip(lapsA, lapsB):
+        assert xa_.shape == xb_.shape
+        assert np.max(np.abs(xa_ - xb_)) < 1e-7 and np.max(np.abs(ua_ - ub_)) < 1e-7
+    # the lap handed over on the device equals the recorded one; Q-function computed on the device
+    xs_, us_, q_ = cb.get_lap(0, 5)
+    assert np.array_equal(xs_, lapsB[1][0]) and q_[0] == lapsB[1][0].shape[0] - 1
+    cb.close()
