@@ -251,6 +251,7 @@ def test_device_resident_closed_loop_matches_host_driven_loop(gold, track):
         lapsA.append((xl, ul))
         ca.add_trajectory(0, xl, ul)
         ca.model_add_trajectory(0, xl, ul)
+        ca.set_state(timeStep=[0])                     # LMPC.addTrajectory resets the step counter (PC.py:445)
         xa = xa - np.array([0, 0, 0, 0, track.TrackLength, 0])
     ca.close()
     # (b) device-resident loop
