@@ -186,6 +186,9 @@ int lmpc_rollout_get_lap(lmpc_handle* h, int inst, int* T, double* x, double* u)
 /* Lap hand-over on the device = LMPC.addTrajectory + PredictiveModel.addTrajectory of the lap just driven (either slot may
  * be -1), then s -= TrackLength (SysModel.py:50), record restarted, timeStep = 0 (PC.py:445). */
 int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slot);
+/* Pack all closed-loop records into rows_dev[B,Tpad,8] = (x | u), lens_dev[B] (device buffers of the caller): the send
+ * buffer of the once-per-lap all-gather of the pooled-safe-set mode. */
+int lmpc_rollout_export_laps_dev(lmpc_handle* h, int Tpad, double* rows_dev, int* lens_dev);
 
 int lmpc_sizeof_params(void);
 int lmpc_sizeof_model_params(void);

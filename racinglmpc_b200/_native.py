@@ -85,6 +85,7 @@ def lib():
     L.lmpc_rollout_step.argtypes = [_vp, C.c_int, _vp, C.c_ulonglong]
     L.lmpc_rollout_get_lap.argtypes = [_vp, C.c_int, ip, _vp, _vp]
     L.lmpc_rollout_commit_lap.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+    L.lmpc_rollout_export_laps_dev.argtypes = [_vp, C.c_int, _vp, _vp]
     L.lmpc_sizeof_params.restype = C.c_int
     L.lmpc_sizeof_model_params.restype = C.c_int
     assert L.lmpc_sizeof_params() == C.sizeof(Params), "lmpc_params ABI mismatch"

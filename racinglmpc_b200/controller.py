@@ -288,6 +288,10 @@ class BatchedController:
                 self._push_used()
         return finished
 
+    def rollout_export_laps(self, Tpad, rows_dev, lens_dev):
+        """Pack the closed-loop records into caller-owned device tensors rows[B,Tpad,8], lens[B] (int32)."""
+        nat.check(self._lib.lmpc_rollout_export_laps_dev(self._h, int(Tpad), nat.ptr(rows_dev), nat.ptr(lens_dev)))
+
     def device_buffer(self, name):
         return int(self._lib.lmpc_device_buffer(self._h, name.encode()) or 0)
 

@@ -916,4 +916,15 @@ int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slo
     return LMPC_OK;
 }
 
+int lmpc_rollout_export_laps_dev(lmpc_handle* h, int Tpad, double* rows_dev, int* lens_dev) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (!rows_dev || !lens_dev || Tpad < 1) return fail(LMPC_E_INVALID, "bad export arguments");
+    CK(cudaSetDevice(h->device));
+    export_laps_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->d_clx, h->d_clu, h->d_cllen, h->Tcl, Tpad, rows_dev, lens_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LMPC_OK;
+}
+
 }  // extern "C"

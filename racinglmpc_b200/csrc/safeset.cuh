@@ -552,6 +552,22 @@ __global__ void commit_lap_kernel(LapPool pool, int b, int slot, const double* c
     if (threadIdx.x == 0) pool.len[lap] = T;
 }
 
+// Pack every instance's closed-loop record into rows[B][Tpad][8] = (x | u) + lens[B]: the send buffer of the per-lap
+// all-gather of the pooled-safe-set mode.
+__global__ void export_laps_kernel(int batch, const double* cl_x, const double* cl_u, const int* cl_len, int Tcl, int Tpad,
+                                   double* rows, int* lens) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int T = min(cl_len[b], Tpad);
+    for (int e = threadIdx.x; e < Tpad * 8; e += blockDim.x) {
+        const int t = e >> 3, j = e & 7;
+        double v = 0.0;
+        if (t < T) v = (j < 6) ? cl_x[((size_t)b * Tcl + t) * 6 + j] : cl_u[((size_t)b * Tcl + t) * 2 + (j - 6)];
+        rows[(size_t)b * Tpad * 8 + e] = v;
+    }
+    if (threadIdx.x == 0) lens[b] = T;
+}
+
 // LMPC.computeCost (PC.py:447-464) for one (instance, slot): backward count of steps to the finish line.
 __global__ void rollout_cost_kernel(LapPool pool, int b, int slot, double TrackLength) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
