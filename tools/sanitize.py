@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Small-batch run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
+    compute-sanitizer --tool racecheck python tools/sanitize.py
+Exercises: ftocp_kernel<12,0> and <12,48> (host + device entry points), knn_ltv_regress, ss_select, shift_state,
+ss_add_point, rollout_cost, sim_step, commit_lap, export_laps."""
+import os
+import sys
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from racinglmpc_b200 import BatchedFTOCP, workloads, reference_params as rp
+from racinglmpc_b200.controller import BatchedController
+
+B, N = 8, 12
+x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
+s = BatchedFTOCP(rp.mpc_params(N), batch=B)
+o = s.solve(x0, uold, abc)
+assert np.all(o["status"] == 1)
+s.close()
+data = workloads.lmpc_batch(B)
+numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+c = BatchedController(par, B, workloads.track_seg_table(), rp.TRACK_LENGTH, trToUse=5, numSS_Points=numSS_Points,
+                      numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1280, ss_cap=6, model_cap=6)
+workloads.restore_lmpc_batch(c, data)
+o = c.step(data["x0"])
+assert np.all(o["status"] == 1) and np.all(o["flags"] == 0)
+c.add_point(data["x0"], o["uPred"][:, 0])
+c.enable_rollout(Tcl=64)
+c.rollout_set_state(data["x0"], data["x0"])
+for _ in range(3):
+    c.rollout_step(seed=1)
+done, n = c.rollout_done()
+c.rollout_finish_laps(np.array([1] + [0] * (B - 1), np.int32), n)
+rows = torch.zeros(B, 16, 8, dtype=torch.float64, device="cuda")
+lens = torch.zeros(B, dtype=torch.int32, device="cuda")
+c.rollout_export_laps(16, rows, lens)
+c.sync()
+c.close()
+print("sanitize workload done")
