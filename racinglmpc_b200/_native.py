@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "liblmpc_b200.so")
+_SO = os.environ.get("LMPC_B200_SO", os.path.join(_HERE, "liblmpc_b200.so"))   # override: kernel-variant experiments only
 
 MAX_NCX, MAX_NCU, MAX_SEG = 4, 8, 16
 

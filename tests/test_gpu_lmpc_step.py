@@ -84,7 +84,7 @@ def test_fused_lmpc_step_matches_reference(gold, track):
     c, x0 = _restore(gold, track, keys)
     l0 = c.kernel_launches
     o = c.step(x0)
-    assert c.kernel_launches - l0 == 4                       # K1, K2, QP, shift
+    assert c.kernel_launches - l0 == 4                       # K1 (writes transposed records itself), K2, QP, shift
     assert np.all(o["status"] == 1) and np.all(o["flags"] == 0), (o["status"], o["flags"])
     st = c.get_state()
     for b, key in enumerate(keys):
