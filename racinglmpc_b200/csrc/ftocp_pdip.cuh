@@ -110,16 +110,11 @@ template <int N, int M, int NCX, int NCU>
 struct Work {
     static constexpr int MM = (M > 0 ? M : 1);
     static constexpr int TM = (M > 0 ? 36 : 1);
-    // --- model ---
-    // The stage model lives in global memory (L2 resident), PRE-TRANSPOSED: per stage 54 doubles,
-    //   T[j*6 + c] = [A_k B_k](c, j) for j < 8 (so every dot product of the sweeps runs over a contiguous, 16 B-aligned
-    //   6-vector -> LDS.128), then C_k (6).
-    // Every sweep streams it through this 3-deep ring with 1-D bulk async copies (cp.async.bulk / UBLKCP, completion on
-    // one mbarrier per slot), two stages ahead of the stage being processed: 1.3 KB of shared memory instead of N*432 B.
-    static constexpr int NBUF = 3;
-    alignas(16) double MB[NBUF][54];
-    alignas(8) unsigned long long mbar[NBUF];
-    unsigned int mb_uses[NBUF];     // per slot: number of completed fills (parity of the next wait), lane-redundant
+    // --- model (filled by the loader; ABC via cp.async.bulk) ---
+    // As loaded: per stage A (36, row major a*6+b) | B (12, a*2+q) | C (6).  prepare_model() transposes A and B in
+    // place, after which ABC[k][j*6 + c] = [A_k B_k](c, j), j < 8: every dot product of the sweeps then runs over a
+    // contiguous, 16 B-aligned 6-vector (LDS.128).
+    alignas(16) double ABC[N][54];
     alignas(16) double SS[6 * MM];  // SS[a*M + l]      (PC.py:411 SS_PointSelectedTot, 6 x M)
     double Qfun[MM];                // Qfun_SelectedTot (PC.py:412)
     double uOld[2];                 // OldInput         (PC.py:136,247)
@@ -211,77 +206,6 @@ LMPC_HD double step_bound(double v, double dv, double a) {
     return (dv < 0.0) ? fmin(a, -v / dv) : a;
 }
 
-
-// ------------------------------------------------------------------------------------------
-// stage-model streaming (global -> shared ring)
-// ------------------------------------------------------------------------------------------
-struct ModelSrc {
-    const double* g;          // transposed stage records of this instance
-    long long stage_stride;   // doubles between consecutive stages (54, or 0 for one LTI model)
-};
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ unsigned int lmpc_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-#endif
-template <class WK>
-LMPC_HD void ring_init(WK& w) {
-#if defined(__CUDA_ARCH__)
-    if (LMPC_LANE == 0) {
-#pragma unroll
-        for (int i = 0; i < WK::NBUF; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lmpc_smem_u32(&w.mbar[i])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-#endif
-    FOR_LANES(i, WK::NBUF) w.mb_uses[i] = 0;
-    wsync();
-}
-// issue the fill of ring slot (k % NBUF) with stage k.  All earlier generic-proxy reads of that slot must be behind a wsync().
-template <class WK>
-LMPC_HD void ring_issue(WK& w, const ModelSrc& ms, int k) {
-    double* dst = w.MB[k % WK::NBUF];
-    const double* src = ms.g + (long long)k * ms.stage_stride;
-#if defined(__CUDA_ARCH__)
-    if (LMPC_LANE == 0) {
-        const unsigned int bar = lmpc_smem_u32(&w.mbar[k % WK::NBUF]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(54 * 8) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lmpc_smem_u32(dst)),
-                     "l"(src), "r"(54 * 8), "r"(bar)
-                     : "memory");
-    }
-#else
-    for (int i = 0; i < 54; ++i) dst[i] = src[i];
-#endif
-}
-// wait until stage k has landed in its slot; returns the slot.
-template <class WK>
-LMPC_HD const double* ring_wait(WK& w, int k) {
-    const int sl = k % WK::NBUF;
-#if defined(__CUDA_ARCH__)
-    const unsigned int parity = w.mb_uses[sl] & 1u;
-    const unsigned int bar = lmpc_smem_u32(&w.mbar[sl]);
-    unsigned int done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-    __syncwarp();
-    if (LMPC_LANE == 0) w.mb_uses[sl] += 1;   // read again only after the wsync() that ends this stage
-#endif
-    return w.MB[sl];
-}
-// Prologue of a sweep over stages first, first+dir, ... : put two stages in flight.
-template <class WK>
-LMPC_HD void ring_begin(WK& w, const ModelSrc& ms, int first, int dir, int count) {
-    ring_issue(w, ms, first);
-    if (count > 1) ring_issue(w, ms, first + dir);
-}
-
 template <int N, int M, int NCX, int NCU>
 struct Pdip {
     using W = Work<N, M, NCX, NCU>;
@@ -292,7 +216,7 @@ struct Pdip {
     static constexpr int PS = W::PS;
 
     // ---------------------------------------------------------------- initial point ------
-    static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0, const ModelSrc& ms) {
+    static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0) {
         // inputs: a strictly feasible multiple of the previous input, held over the horizon
         double tau = 1.0;
 #pragma unroll
@@ -302,18 +226,28 @@ struct Pdip {
         }
         FOR_LANES(e, N * 2) w.u[e] = tau * w.uOld[e & 1];
         FOR_LANES(e, 6) w.x[e] = x0[e];
+        FOR_LANES(k, N) {               // transpose A and B in place: ABC[k][j*6+c] = [A B](c, j)
+            double* A = &w.ABC[k][0];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a + 1; b < 6; ++b) { double t = A[a * 6 + b]; A[a * 6 + b] = A[b * 6 + a]; A[b * 6 + a] = t; }
+            double bt[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) bt[e] = A[36 + e];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) { A[36 + cc] = bt[cc * 2]; A[42 + cc] = bt[cc * 2 + 1]; }
+        }
         wsync();
-        ring_begin(w, ms, 0, +1, N);
         for (int k = 0; k < N; ++k) {   // roll the model out (dynamics hold from the start)
-            const double* T = ring_wait(w, k);
             FOR_LANES(a, 6) {
+                const double* T = &w.ABC[k][0];
                 double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
 #pragma unroll
                 for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];
                 w.x[(k + 1) * 6 + a] = v;
             }
             wsync();
-            if (k + 2 < N) ring_issue(w, ms, k + 2);
         }
         // Dual-feasible, centred start (oracle/pdip_model.py, mu0 = "auto"): the slack-stationarity row
         // nu1 + nu3 = 2 qs s + ql holds exactly with w1 nu1 = s nu3 = mu_row; every other constraint
@@ -577,7 +511,7 @@ struct Pdip {
 
     // Factorising backward sweep on the augmented state (x, v): Riccati matrices, gradient recursion for the
     // predictor right-hand side and the costate / input-residual recursion.  Four uniform phases per stage.
-    static LMPC_HD double backward_factor(W& w, const FtocpConst& c, const ModelSrc& ms) {
+    static LMPC_HD double backward_factor(W& w, const FtocpConst& c) {
         double ru_max = 0.0;
         // loop-invariant per-lane work assignment, cached in registers on the device (2 items per lane)
         constexpr bool CACHED = (LMPC_NLANE == 32);
@@ -586,9 +520,8 @@ struct Pdip {
             s_entry(c, LMPC_LANE, se[0]);
             s_entry(c, LMPC_LANE + 32, se[CACHED ? 1 : 0]);
         }
-        ring_begin(w, ms, N - 1, -1, N);
         for (int k = N - 1; k >= 0; --k) {
-            const double* T = ring_wait(w, k);        // T[j*6 + c] = [A B](c, j)
+            const double* T = &w.ABC[k][0];           // T[j*6 + c] = [A B](c, j)
             const double* pn = w.pb[(k + 1) & 1];     // px | pv of stage k+1
             const double* pin = w.pi[(k + 1) & 1];    // pi_{k+1}
             // ---- phase a: Gt[j][a] = (Paug A~)(a, j)
@@ -692,16 +625,14 @@ struct Pdip {
                 }
             }
             wsync();
-            if (k - 2 >= 0) ring_issue(w, ms, k - 2);
         }
         return ru_max;
     }
 
     // Gradient-only backward sweep for a new right-hand side (corrector), one phase per stage.
-    static LMPC_HD void backward_rhs(W& w, const FtocpConst& c, const ModelSrc& ms) {
-        ring_begin(w, ms, N - 1, -1, N);
+    static LMPC_HD void backward_rhs(W& w, const FtocpConst& c) {
         for (int k = N - 1; k >= 0; --k) {
-            const double* T = ring_wait(w, k);
+            const double* T = &w.ABC[k][0];
             const double* pn = w.pb[(k + 1) & 1];
             double* po = w.pb[k & 1];
             double g0[2];
@@ -716,18 +647,16 @@ struct Pdip {
                 if (a >= 6) w.z0[k][a - 6] = (a == 6) ? a0 : a1;
             }
             wsync();
-            if (k - 2 >= 0) ring_issue(w, ms, k - 2);
         }
     }
 
     // ---------------------------------------------------------------- forward sweep ------
-    static LMPC_HD void forward(W& w, const ModelSrc& ms) {
+    static LMPC_HD void forward(W& w) {
         FOR_LANES(a, 6) w.dx[a] = 0.0;
         wsync();
-        ring_begin(w, ms, 0, +1, N);
         double dv0 = 0.0, dv1 = 0.0;
         for (int k = 0; k < N; ++k) {
-            const double* T = ring_wait(w, k);
+            const double* T = &w.ABC[k][0];
             const double* Z = w.Zt[k];
             const double* d = &w.dx[k * 6];
             const double t0 = w.z0[k][0] + dot6v(Z, d) + Z[6] * dv0 + Z[7] * dv1;
@@ -747,7 +676,6 @@ struct Pdip {
             dv0 = du0;
             dv1 = du1;
             wsync();
-            if (k + 2 < N) ring_issue(w, ms, k + 2);
         }
     }
 
@@ -776,14 +704,13 @@ struct Pdip {
     }
 
     // ---------------------------------------------------------------- the solver ---------
-    // Preconditions: w.SS, w.Qfun, w.uOld loaded and visible to the warp; x0[6]; ms = this instance's transposed stage model.
-    static LMPC_HD void solve(W& w, const FtocpConst& c, const double* x0, const ModelSrc& ms, SolveInfo& info,
+    // Preconditions: w.ABC, w.SS, w.Qfun, w.uOld loaded and visible to the warp; x0[6].
+    static LMPC_HD void solve(W& w, const FtocpConst& c, const double* x0, SolveInfo& info,
                               double* lam_out /* M or null */, double* slack_out /* R1 or null */) {
         RG g;
         if (LMPC_LANE == 0) w.flag = 0;
         wsync();
-        ring_init(w);
-        init_point(w, g, c, x0, ms);
+        init_point(w, g, c, x0);
         const double n_ineq = (double)(2 * R1 + R2 + (LMPC ? M : 0));
         int it = 0, status = ST_MAX_ITER;
         double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0;
@@ -859,7 +786,7 @@ struct Pdip {
             }
             stage_gradients(w, c);
             backward_start<true>(w, c, c1);
-            const double ru_max = backward_factor(w, c, ms);
+            const double ru_max = backward_factor(w, c);
             ru_prev = ru_max;
             r_dual = fmax(rd_loc, ru_max);
             if (w.flag != 0) { status = w.flag; break; }
@@ -867,7 +794,7 @@ struct Pdip {
             if (it >= c.max_iter) { status = (r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) ? ST_SOLVED : ST_MAX_ITER; break; }
 
             // ---- predictor -----------------------------------------------------------------------
-            forward(w, ms);
+            forward(w);
             double dy1 = 0.0;
             if (LMPC) dy1 = terminal_recover(w, g, c1, beta, delta);
             double a_aff = 1.0;
@@ -943,8 +870,8 @@ struct Pdip {
             }
             wsync();
             backward_start<false>(w, c, c1);
-            backward_rhs(w, c, ms);
-            forward(w, ms);
+            backward_rhs(w, c);
+            forward(w);
             if (LMPC) dy1 = terminal_recover(w, g, c1, beta, delta);
 
             // ---- step length and update ----------------------------------------------------------
@@ -1032,17 +959,13 @@ struct Pdip {
 
         // ---- final residual (adds the dynamics defect, which the iteration keeps at rounding level)
         double rdyn = 0.0;
-        ring_begin(w, ms, 0, +1, N);
-        for (int k = 0; k < N; ++k) {
-            const double* T = ring_wait(w, k);
-            FOR_LANES(a, 6) {
-                double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
+        FOR_LANES(e, N * 6) {
+            int k = e / 6, a = e % 6;
+            const double* T = &w.ABC[k][0];
+            double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
 #pragma unroll
-                for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];
-                rdyn = fmax(rdyn, fabs(w.x[(k + 1) * 6 + a] - v));
-            }
-            wsync();
-            if (k + 2 < N) ring_issue(w, ms, k + 2);
+            for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];
+            rdyn = fmax(rdyn, fabs(w.x[(k + 1) * 6 + a] - v));
         }
         r_prim = fmax(r_prim, wmax(rdyn));
         info.status = status;

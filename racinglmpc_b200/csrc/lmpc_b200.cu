@@ -53,7 +53,7 @@ struct FtocpArgs {
     int batch;
     const double* x0;     // [B,6]
     const double* uOld;   // [B,2]
-    const double* abc;    // stage model, TRANSPOSED records (see abc_transpose_kernel)
+    const double* abc;    // stage model
     long long abc_inst_stride, abc_stage_stride;   // doubles
     const double* SS;     // [B,6,M]
     const double* Qfun;   // [B,M]
@@ -78,7 +78,7 @@ struct KernelSmem {
 };
 
 template <int N, int M, int NCX, int NCU>
-__global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 14 : 20) : 1)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
+__global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 12 : 16) : 1)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using KS = KernelSmem<N, M, NCX, NCU>;
     KS& ks = *reinterpret_cast<KS*>(smem_raw);
@@ -87,11 +87,18 @@ __global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 14 : 20) : 1)) ftocp_k
     if (b >= a.batch) return;
     const int lane = threadIdx.x;
 
-    // ---- stage the selected safe set into shared memory (1-D bulk async copies); the stage model is streamed by the solver ----
-    if (M > 0) {
-        if (lane == 0) {
-            mbar_init(&ks.bar, 1);
-            mbar_expect_tx(&ks.bar, (6 * M + M) * 8);
+    // ---- stage the instance's model into shared memory (TMA 1-D bulk copies) ----
+    if (lane == 0) {
+        mbar_init(&ks.bar, 1);
+        uint32_t bytes = N * 54 * 8 + (M > 0 ? (6 * M + M) * 8 : 0);
+        mbar_expect_tx(&ks.bar, bytes);
+        const double* src = a.abc + (long long)b * a.abc_inst_stride;
+        if (a.abc_stage_stride == 54) {
+            bulk_g2s(&w.ABC[0][0], src, N * 54 * 8, &ks.bar);
+        } else {
+            for (int k = 0; k < N; ++k) bulk_g2s(&w.ABC[k][0], src + (long long)k * a.abc_stage_stride, 54 * 8, &ks.bar);
+        }
+        if (M > 0) {
             bulk_g2s(&w.SS[0], a.SS + (long long)b * 6 * M, 6 * M * 8, &ks.bar);
             bulk_g2s(&w.Qfun[0], a.Qfun + (long long)b * M, M * 8, &ks.bar);
         }
@@ -101,14 +108,11 @@ __global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 14 : 20) : 1)) ftocp_k
     for (int i = 0; i < 6; ++i) x0[i] = a.x0[(long long)b * 6 + i];
     if (lane < 2) w.uOld[lane] = a.uOld[(long long)b * 2 + lane];
     __syncwarp();
-    if (M > 0) mbar_wait(&ks.bar, 0);
-    ModelSrc ms;
-    ms.g = a.abc + (long long)b * a.abc_inst_stride;
-    ms.stage_stride = a.abc_stage_stride;
+    mbar_wait(&ks.bar, 0);
 
     // ---- solve ----
     SolveInfo info;
-    Pdip<N, M, NCX, NCU>::solve(w, c, x0, ms, info, (M > 0) ? w.d4i : nullptr, a.slack ? a.slack + (long long)b * N * NCX : nullptr);
+    Pdip<N, M, NCX, NCU>::solve(w, c, x0, info, (M > 0) ? w.d4i : nullptr, a.slack ? a.slack + (long long)b * N * NCX : nullptr);
 
     // ---- unpack (PC.py:364-384) ----
     for (int e = lane; e < (N + 1) * 6; e += 32) a.xPred[(long long)b * (N + 1) * 6 + e] = w.x[e];
@@ -148,24 +152,6 @@ __global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 14 : 20) : 1)) ftocp_k
     }
 }
 
-// Stage records as given by the caller: A (36, row major a*6+b) | B (12, a*2+q) | C (6).  The solver streams
-// TRANSPOSED records T[j*6+c] = [A B](c, j), j < 8, then C: this kernel writes them once per solve (coalesced stores).
-__global__ void abc_transpose_kernel(long long nrec, int N, const double* src, long long src_inst_stride, long long src_stage_stride,
-                                     double* dst) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nrec * 54) return;
-    const long long rec = e / 54;
-    const int i = (int)(e - rec * 54);
-    const long long b = rec / N;
-    const int k = (int)(rec - b * N);
-    const double* r = src + b * src_inst_stride + (long long)k * src_stage_stride;
-    double v;
-    if (i < 36) { const int j = i / 6, c = i - j * 6; v = r[c * 6 + j]; }
-    else if (i < 48) { const int q = (i - 36) / 6, c = (i - 36) - q * 6; v = r[36 + c * 2 + q]; }
-    else v = r[i];
-    dst[e] = v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -188,7 +174,7 @@ struct lmpc_handle {
     cudaStream_t cstream[4];   // chunk pipeline of the *_host entry points (H2D | kernel | D2H overlap)
     long long launches;
     // device buffers used by the *_host entry points
-    double *d_x0, *d_uOld, *d_abc, *d_abct, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
+    double *d_x0, *d_uOld, *d_abc, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
     double *d_xPred, *d_uPred, *d_slack, *d_lambd, *d_slackT, *d_zt, *d_ztu, *d_resid;
     int *d_status, *d_iters;
     // lap stores + controller state (lmpc_store_create)
@@ -269,33 +255,6 @@ static int launch_t(lmpc_handle* h, const FtocpArgs& a, cudaStream_t st) {
     return LMPC_OK;
 }
 
-// Write the transposed stage records of instances [lo, lo+nb) into h->d_abct and point `a` at them.
-static int prep_model(lmpc_handle* h, cudaStream_t st, const double* abc_nat, long long inst_stride, long long stage_stride,
-                      size_t lo, size_t nb, FtocpArgs& a) {
-    const long long N = h->N;
-    if (inst_stride == 0) {                    // one model shared by every instance (LTI: one record; LTV: N records)
-        const long long nrec = stage_stride == 0 ? 1 : N;
-        if (lo == 0) {
-            abc_transpose_kernel<<<(unsigned)((nrec * 54 + 127) / 128), 128, 0, st>>>(nrec, (int)nrec, abc_nat, 0, stage_stride, h->d_abct);
-            CK(cudaGetLastError());
-            h->launches += 1;
-        }
-        a.abc = h->d_abct;
-        a.abc_inst_stride = 0;
-        a.abc_stage_stride = stage_stride == 0 ? 0 : 54;
-    } else {
-        const long long nrec = (long long)nb * N;
-        abc_transpose_kernel<<<(unsigned)((nrec * 54 + 255) / 256), 256, 0, st>>>(nrec, (int)N, abc_nat + (long long)lo * inst_stride, inst_stride,
-                                                                                 stage_stride, h->d_abct + lo * N * 54);
-        CK(cudaGetLastError());
-        h->launches += 1;
-        a.abc = h->d_abct + lo * N * 54;
-        a.abc_inst_stride = N * 54;
-        a.abc_stage_stride = 54;
-    }
-    return LMPC_OK;
-}
-
 static int launch(lmpc_handle* h, const FtocpArgs& a, bool lmpc_mode, cudaStream_t st) {
     const int N = h->N, M = lmpc_mode ? h->M : 0;
 #define LCASE(n, m) if (N == n && M == m) return launch_t<n, m>(h, a, st);
@@ -342,7 +301,7 @@ int lmpc_create(const lmpc_params* p, int batch, int device, lmpc_handle** out) 
     for (int i = 0; i < 4; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
     const size_t B = batch, N = p->N, M = p->numSS_Points > 0 ? p->numSS_Points : 1;
 #define DALLOC(ptr, count) CK(cudaMalloc((void**)&h->ptr, sizeof(*h->ptr) * (count)))
-    DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54); DALLOC(d_abct, B * N * 54);
+    DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54);
     DALLOC(d_SS, B * 6 * M); DALLOC(d_Qfun, B * M); DALLOC(d_SuccSS, B * 6 * M); DALLOC(d_SuccU, B * 2 * M);
     DALLOC(d_xPred, B * (N + 1) * 6); DALLOC(d_uPred, B * N * 2); DALLOC(d_slack, B * N * 2);
     DALLOC(d_lambd, B * M); DALLOC(d_slackT, B * 6); DALLOC(d_zt, B * 6); DALLOC(d_ztu, B * 2);
@@ -366,7 +325,7 @@ int lmpc_destroy(lmpc_handle* h) {
                         h->d_ztFixed, h->d_OldInput, h->d_xPredPrev, h->d_tmpx, h->d_tmpu};
         for (void* q : ptrs) cudaFree(q);
     }
-    double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_abct, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
+    double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
                      h->d_slack, h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid};
     for (double* q : dbl) cudaFree(q);
     cudaFree(h->d_status);
@@ -391,10 +350,10 @@ static int check_align(const void* p, const char* what) {
     return LMPC_OK;
 }
 
-static int solve_dev_internal(lmpc_handle* h, bool abc_pretransposed, const double* x0, const double* uOld, const double* abc,
-                              long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel,
-                              const double* Succ_SS, const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
-                              double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
+int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
+                        long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel, const double* Succ_SS,
+                        const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
+                        double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
     if (!h || !x0 || !uOld || !abc || !xPred || !uPred || !status || !iters || !resid) return fail(LMPC_E_INVALID, "null argument");
     const bool lm = (SS_sel != nullptr);
     if (lm && (h->M <= 0 || !Qfun_sel)) return fail(LMPC_E_INVALID, "handle was created without a safe set (numSS_Points == 0)");
@@ -405,24 +364,12 @@ static int solve_dev_internal(lmpc_handle* h, bool abc_pretransposed, const doub
     CK(cudaSetDevice(h->device));
     FtocpArgs a;
     a.batch = h->batch;
-    a.x0 = x0; a.uOld = uOld;
-    if (abc_pretransposed) {
-        a.abc = abc; a.abc_inst_stride = abc_inst_stride; a.abc_stage_stride = abc_stage_stride;
-    } else {
-        if ((rc = prep_model(h, h->stream, abc, abc_inst_stride, abc_stage_stride, 0, h->batch, a)) != LMPC_OK) return rc;
-    }
+    a.x0 = x0; a.uOld = uOld; a.abc = abc;
+    a.abc_inst_stride = abc_inst_stride; a.abc_stage_stride = abc_stage_stride;
     a.SS = SS_sel; a.Qfun = Qfun_sel; a.SuccSS = Succ_SS; a.SuccU = Succ_uSS;
     a.xPred = xPred; a.uPred = uPred; a.slack = slack; a.lambd = lambd; a.slackT = slackTerminal;
     a.zt = zt; a.ztu = zt_u; a.status = status; a.iters = iters; a.resid = resid;
     return launch(h, a, lm, h->stream);
-}
-
-int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
-                        long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel, const double* Succ_SS,
-                        const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
-                        double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
-    return solve_dev_internal(h, false, x0, uOld, abc, abc_inst_stride, abc_stage_stride, SS_sel, Qfun_sel, Succ_SS, Succ_uSS, xPred,
-                              uPred, slack, lambd, slackTerminal, zt, zt_u, status, iters, resid);
 }
 
 int lmpc_solve_mpc_dev(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
@@ -449,11 +396,8 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
     else if (abc_inst_stride == 0 && abc_stage_stride == 54) { dis = 0; dss = 54; }                // one shared LTV model
     else return fail(LMPC_E_INVALID, "host entry supports abc strides (N*54,54), (0,54) or (0,0)");
     CK(cudaStreamSynchronize(h->stream));    // earlier work of this handle is done before the chunk streams start
-    FtocpArgs shared_model;
     if (!per_inst) {
         CK(cudaMemcpyAsync(h->d_abc, abc, (dss ? N * 54 : 54) * D, cudaMemcpyHostToDevice, h->cstream[0]));
-        int rcm = prep_model(h, h->cstream[0], h->d_abc, dis, dss, 0, B, shared_model);      // transposed once, before the chunks start
-        if (rcm != LMPC_OK) return rcm;
         CK(cudaStreamSynchronize(h->cstream[0]));
     }
     // Chunk pipeline: the batch is cut into up to four instance ranges, each on its own stream, so that the H2D copy
@@ -474,12 +418,8 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
         FtocpArgs a;
         a.batch = (int)nb;
         a.x0 = h->d_x0 + lo * 6; a.uOld = h->d_uOld + lo * 2;
-        if (per_inst) {
-            int rcm = prep_model(h, s, h->d_abc, dis, dss, lo, nb, a);
-            if (rcm != LMPC_OK) return rcm;
-        } else {
-            a.abc = shared_model.abc; a.abc_inst_stride = shared_model.abc_inst_stride; a.abc_stage_stride = shared_model.abc_stage_stride;
-        }
+        a.abc = per_inst ? h->d_abc + lo * N * 54 : h->d_abc;
+        a.abc_inst_stride = dis; a.abc_stage_stride = dss;
         a.SS = lm ? h->d_SS + lo * 6 * M : nullptr; a.Qfun = lm ? h->d_Qfun + lo * M : nullptr;
         a.SuccSS = (lm && Succ_SS) ? h->d_SuccSS + lo * 6 * M : nullptr; a.SuccU = (lm && Succ_uSS) ? h->d_SuccU + lo * 2 * M : nullptr;
         a.xPred = h->d_xPred + lo * (N + 1) * 6; a.uPred = h->d_uPred + lo * N * 2;
@@ -720,7 +660,7 @@ static int launch_k1(lmpc_handle* h) {
     a.batch = h->batch; a.N = h->N;
     a.wpb = h->N < 12 ? h->N : 12;
     a.pts_stride = k1_pts_stride(h->mc.trToUse);
-    a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.abct = h->d_abct; a.status = h->d_flags;
+    a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
     dim3 grid(h->batch, (h->N + a.wpb - 1) / a.wpb);
     size_t smem = sizeof(double) * ((size_t)5 * K1_TILE + (size_t)a.pts_stride * a.wpb);
     static thread_local int cfg_dev = -1;
@@ -792,7 +732,7 @@ int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) {
     CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
     if ((rc = launch_k1(h)) != LMPC_OK) return rc;                      // PC.py:117
     if (mode == 1 && (rc = launch_k2(h, x0_dev)) != LMPC_OK) return rc;  // PC.py:121
-    rc = solve_dev_internal(h, true, x0_dev, h->d_OldInput, h->d_abct, (long long)h->N * 54, 54, mode == 1 ? h->d_SS : nullptr,
+    rc = lmpc_solve_lmpc_dev(h, x0_dev, h->d_OldInput, h->d_abc, (long long)h->N * 54, 54, mode == 1 ? h->d_SS : nullptr,
                              mode == 1 ? h->d_Qfun : nullptr, mode == 1 ? h->d_SuccSS : nullptr, mode == 1 ? h->d_SuccU : nullptr,
                              h->d_xPred, h->d_uPred, h->d_slack, mode == 1 ? h->d_lambd : nullptr, mode == 1 ? h->d_slackT : nullptr,
                              mode == 1 ? h->d_zt : nullptr, mode == 1 ? h->d_ztu : nullptr, h->d_status, h->d_iters, h->d_resid);  // PC.py:124-125

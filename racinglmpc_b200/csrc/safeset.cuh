@@ -104,8 +104,7 @@ struct K1Args {
     const double* uLin;   // [B][N][2]
     LapPool pool;         // model pool
     const int* used;      // [B][trToUse] slot ids, in usedIt order
-    double* abc;          // [B][N][54]  A | B | C as the reference returns them
-    double* abct;         // [B][N][54]  transposed records for the solver (T[j*6+c] = [A B](c, j), then C)
+    double* abc;          // [B][N][54]
     int* status;          // [B] : 0 ok, else bit flags (1 = singular regression, 2 = curvature lookup failed,
                           //        4 = a single neighbour in a lap — cases where the reference raises)
 };
@@ -416,11 +415,6 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
             }
         }
         out[e] = v;
-        // same value into the transposed record the QP kernel streams
-        int te = e;
-        if (e < 36) te = (e % 6) * 6 + e / 6;
-        else if (e < 48) te = 36 + ((e - 36) & 1) * 6 + ((e - 36) >> 1);
-        a.abct[((size_t)b * a.N + i) * 54 + te] = v;
     }
     if (lane == 0 && flags) atomicOr(&a.status[b], flags);
 }

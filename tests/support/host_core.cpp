@@ -13,18 +13,7 @@ static int run(const FtocpConst* c, const double* abc, const double* ss, const d
                const double* uold, double* xpred, double* upred, double* lam, double* slack, double* info_out) {
     using P = Pdip<N, M, 2, 4>;
     typename P::W* w = new typename P::W();
-    // transposed stage records, as abc_transpose_kernel writes them on the device
-    double* abct = new double[N * 54];
-    for (int k = 0; k < N; ++k) {
-        const double* r = abc + k * 54;
-        double* t = abct + k * 54;
-        for (int j = 0; j < 6; ++j) for (int cc = 0; cc < 6; ++cc) t[j * 6 + cc] = r[cc * 6 + j];
-        for (int q = 0; q < 2; ++q) for (int cc = 0; cc < 6; ++cc) t[36 + q * 6 + cc] = r[36 + cc * 2 + q];
-        for (int i = 48; i < 54; ++i) t[i] = r[i];
-    }
-    ModelSrc ms;
-    ms.g = abct;
-    ms.stage_stride = 54;
+    std::memcpy(w->ABC, abc, sizeof(double) * N * 54);
     if (M > 0) {
         std::memcpy(w->SS, ss, sizeof(double) * 6 * M);
         std::memcpy(w->Qfun, qfun, sizeof(double) * M);
@@ -32,8 +21,7 @@ static int run(const FtocpConst* c, const double* abc, const double* ss, const d
     w->uOld[0] = uold[0];
     w->uOld[1] = uold[1];
     SolveInfo info;
-    P::solve(*w, *c, x0, ms, info, lam, slack);
-    delete[] abct;
+    P::solve(*w, *c, x0, info, lam, slack);
     std::memcpy(xpred, w->x, sizeof(double) * (N + 1) * 6);
     std::memcpy(upred, w->u, sizeof(double) * N * 2);
     info_out[0] = info.status; info_out[1] = info.iters; info_out[2] = info.r_prim; info_out[3] = info.r_dual; info_out[4] = info.gap;
