@@ -38,7 +38,7 @@ def test_golden_lti_ltv(gold):
     for i, (k, _) in enumerate(keys):
         assert np.max(np.abs(o["xPred"][i] - gold[k + "xPred"])) < 1e-6
         assert np.max(np.abs(o["uPred"][i] - gold[k + "uPred"])) < 1e-6
-    assert s.kernel_launches == 2          # stage-record transposition + the fused QP kernel
+    assert s.kernel_launches == 1
     s.close()
 
 
