@@ -50,8 +50,9 @@ typedef struct lmpc_params {
     int numSS_Points, numSS_it;   /* 0,0 for a plain MPC                       LMPC.__init__      */
     double QterminalSlack[36];    /*                                           LMPC.__init__      */
     /* interior-point settings (no reference counterpart; OSQP's eps are 1e-3 + polish, PC.py:275) */
-    double eps_res, eps_gap;      /* <= 0 selects the defaults 1e-8 / 1e-11 (unscaled inf-norms); an instance that runs
-                                     out of iterations is still reported solved if all three are <= 1e-6 */
+    double eps_res, eps_gap;      /* <= 0 selects the defaults 1e-9 / 1e-11 (unscaled inf-norms); an instance still
+                                     running at iteration 20 is reported solved once all three are <= 1e-6 (safety
+                                     net; not reached on any recorded workload) */
     int max_iter;                 /* <= 0 selects the default 40               */
 } lmpc_params;
 

@@ -16,13 +16,15 @@ Problem (same data the reference assembles at PredictiveControllers.py:166-257,3
 """
 import numpy as np
 
+W_REFINE = 1      # refinement steps of the 6x6 covariance-form solve, residual taken through the recovered dlam
 ADAPTIVE_FLOOR = False  # experiment (relax the floor on stall): helps some instances, hurts others -> off
 EXACT_TERMINAL_RECOVERY = False
 TERM_REFINE = 0   # terminal-block iterative refinement (experiment; the kernel does not need it)
 DEBUG_HOOK = False
-D4_MIN = 1e-4   # floor on the lambda barrier diagonal nu4/lambda (static primal regularisation).
-                # Below ~1e-6 the 6x6 covariance-form elimination of lambda loses the Newton direction
-                # (measured: tests/golden snapshots); 1e-5..1e-2 all converge in 9-16 iterations.
+D4_MIN = 1e-6   # floor on the lambda barrier diagonal nu4/lambda (static primal regularisation).
+                # Without W_REFINE the 6x6 covariance-form elimination of lambda loses the Newton direction below
+                # ~1e-5 (measured: tests/golden snapshots); with one refinement step 1e-4..1e-7 all converge in
+                # 9-16 iterations and 1e-6 removes the stall of LP-degenerate instances the 1e-4 floor caused.
 
 
 class StageQP:
@@ -238,6 +240,13 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                 dyT = Wi @ (dx[N] + c1)
                 dy1t = -beta / delta                        # multiplier of the centred simplex row
                 dlam = (rho_l + Sc.T @ dyT - dy1t) / d4
+                for _ in range(W_REFINE):
+                    # iterative refinement of the 6x6 covariance-form solve, residual evaluated THROUGH the recovered dlam:
+                    #   T^-1 dyT + S~ dlam = dx_N - sbar*b1   (b1 = -rone)
+                    e_T = dx[N] + sbar * rone - Tinv @ dyT - Sc @ dlam
+                    ddy = Wi @ e_T
+                    dyT = dyT + ddy
+                    dlam = dlam + (Sc.T @ ddy) / d4
                 d4_true = nu4 / lam
                 for _ in range(TERM_REFINE if np.min(d4_true) < d4_floor else 0):
                     # iterative refinement of (dlam, dy1) for the given dx_N: residual of the terminal block in

@@ -679,26 +679,56 @@ struct Pdip {
         }
     }
 
-    // terminal recovery after a forward sweep: dyT (shared), dlam (registers); returns dy1
-    static LMPC_HD double terminal_recover(W& w, RG& g, const double* c1, double beta, double delta) {
+    // terminal recovery after a forward sweep: dlam (registers); returns dy1.
+    // The 6x6 covariance-form solve loses ~cond(W)*eps in dyT, which the division by a small d4 amplifies in
+    // the dlam of active safe-set points.  One step of iterative refinement with the residual of
+    //     Tinv dyT + S~ dlam = dx_N - sbar*b1
+    // evaluated THROUGH the recovered dlam removes it (oracle/pdip_model.py W_REFINE).
+    static LMPC_HD double terminal_recover(W& w, RG& g, const FtocpConst& c, const double* c1, double beta,
+                                           double delta, double b1) {
         double v[6], dyT[6];
 #pragma unroll
         for (int a = 0; a < 6; ++a) v[a] = w.dx[N * 6 + a] + c1[a];
-        double sdy = 0.0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
             double t = 0.0;
 #pragma unroll
             for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * v[b];
             dyT[a] = t;
-            sdy += w.sbar[a] * t;
         }
         const double dy1t = -beta / delta;
+        double acc[6] = {0, 0, 0, 0, 0, 0};
         FOR_SLOTS(r, row, R4) {
             double t = g.rho[r] - dy1t;
 #pragma unroll
             for (int a = 0; a < 6; ++a) t += (w.SS[a * M + row] - w.sbar[a]) * dyT[a];
-            g.dlam[r] = t * w.d4i[row];
+            t *= w.d4i[row];
+            g.dlam[r] = t;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[a] += (w.SS[a * M + row] - w.sbar[a]) * t;
+        }
+        double e[6], ddy[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double t = w.dx[N * 6 + a] - w.sbar[a] * b1 - wsum(acc[a]);
+#pragma unroll
+            for (int b = 0; b < 6; ++b) t -= c.Tinv[a * 6 + b] * dyT[b];
+            e[a] = t;
+        }
+        double sdy = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * e[b];
+            ddy[a] = t;
+            sdy += w.sbar[a] * (dyT[a] + t);
+        }
+        FOR_SLOTS(r, row, R4) {
+            double t = 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) t += (w.SS[a * M + row] - w.sbar[a]) * ddy[a];
+            g.dlam[r] += t * w.d4i[row];
         }
         return dy1t + sdy;
     }
@@ -796,7 +826,7 @@ struct Pdip {
             // ---- predictor -----------------------------------------------------------------------
             forward(w);
             double dy1 = 0.0;
-            if (LMPC) dy1 = terminal_recover(w, g, c1, beta, delta);
+            if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
             double a_aff = 1.0;
             FOR_SLOTS(r, row, R1) {
                 int k = row / NCX, i = row % NCX;
@@ -872,7 +902,7 @@ struct Pdip {
             backward_start<false>(w, c, c1);
             backward_rhs(w, c);
             forward(w);
-            if (LMPC) dy1 = terminal_recover(w, g, c1, beta, delta);
+            if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
 
             // ---- step length and update ----------------------------------------------------------
             double amax = 1e300;

@@ -233,9 +233,9 @@ static int build_const(const lmpc_params& p, FtocpConst& c) {
     } else {
         for (int i = 0; i < 6; ++i) c.T[i * 6 + i] = c.Tinv[i * 6 + i] = 1.0;
     }
-    c.eps_res = p.eps_res > 0 ? p.eps_res : 1e-8;
+    c.eps_res = p.eps_res > 0 ? p.eps_res : 1e-9;
     c.eps_gap = p.eps_gap > 0 ? p.eps_gap : 1e-11;
-    c.d4_min = 1e-4;
+    c.d4_min = 1e-6;
     c.max_iter = p.max_iter > 0 ? p.max_iter : 40;
     return LMPC_OK;
 }

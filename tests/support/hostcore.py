@@ -23,7 +23,7 @@ class FtocpConst(C.Structure):
                 ("max_iter", C.c_int), ("pad_", C.c_int)]
 
 
-def make_const(p, Qts=None, eps_res=1e-8, eps_gap=1e-11, d4_min=1e-4, max_iter=40):
+def make_const(p, Qts=None, eps_res=1e-9, eps_gap=1e-11, d4_min=1e-6, max_iter=40):
     """p: any object with the reference's MPCParams field names."""
     c = FtocpConst()
     Q, R, Qf = np.asarray(p.Q, float), np.asarray(p.R, float), np.asarray(p.Qf, float)
