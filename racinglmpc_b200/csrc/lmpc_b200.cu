@@ -666,6 +666,7 @@ static int launch_k1(lmpc_handle* h) {
     static thread_local int cfg_dev = -1;
     if (cfg_dev != h->device) {
         CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         cfg_dev = h->device;
     }
     knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, h->stream>>>(h->mc, a);

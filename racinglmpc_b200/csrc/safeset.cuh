@@ -108,13 +108,15 @@ struct K1Args {
     int* status;          // [B] : 0 ok, else bit flags (1 = singular regression, 2 = curvature lookup failed,
                           //        4 = a single neighbour in a lap — cases where the reference raises)
 };
-// per-warp scratch: selected points [7*trToUse][9] | normal equations 45 (+3 pad) | two augmented systems 5x6 + 5x7 (+3 pad)
+// per-warp scratch: selected points [7*trToUse][10] (x0 x1 x2 u0 u1 K y0 y1 y2 1) | normal equations 45 (+3 pad)
+//                   | two augmented systems 5x6 + 5x7 (+3 pad)
 //                   | candidate buffer 64 distances + 64 row indices
-__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * 9 + 48 + 68 + 96; }
+constexpr int K1_PW = 10;        // doubles per selected point
+__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * K1_PW + 48 + 68 + 96; }
 
 // grid = (B, ceil(N / wpb)); one warp per horizon step; the CTA stages each lap tile in shared memory once
 // (feature-major, conflict-free) and every warp scans it for its own query point.
-__global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_constant__ ModelConst m, const K1Args a) {
+__global__ void __launch_bounds__(32 * 12, 3) knn_ltv_regress_kernel(const __grid_constant__ ModelConst m, const K1Args a) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     const int b = blockIdx.x;
     const int wib = threadIdx.x >> 5;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
     double* tile = reinterpret_cast<double*>(k1_smem);                 // [5][K1_TILE] : vx vy wz | delta a
     double* pts = tile + 5 * K1_TILE + (size_t)wib * a.pts_stride;     // this warp's scratch
     const int np_max = K1_MAXPTS * m.trToUse;
-    double* ne = pts + (size_t)np_max * 9;                             // 48
+    double* ne = pts + (size_t)np_max * K1_PW;                         // 48
     double* sys = ne + 48;                                             // 30 + 35 (+3)
     double* cbd = sys + 68;                                            // candidate distances [64]
     int* cbi = reinterpret_cast<int*>(cbd + 64);                       // candidate rows [64]
@@ -152,7 +154,10 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
         int nbuf = 0, cnt = 0;
         const int kk = m.MaxNumPoint;
         auto fold = [&]() {
-            // candidates: buffer entries lane, lane+32 (< nbuf <= 64) and the current top-k (lane < kk)
+            // candidates: buffer entries lane, lane+32 (< nbuf <= 64) and the current top-k (lane < kk).
+            // kk rounds of warp arg-min on the key (distance bits, row): distances are non-negative doubles, so their bit
+            // patterns order like unsigned integers and three 32-bit REDUX.MIN (high word, low word, row) find the
+            // winner; only the winning lane updates its local minimum.
             double c0d = (lane < nbuf) ? cbd[lane] : 1e300;
             int c0i = (lane < nbuf) ? cbi[lane] : 0x7fffffff;
             double c1d = (lane + 32 < nbuf) ? cbd[lane + 32] : 1e300;
@@ -161,20 +166,25 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
             int c2i = (lane < kk) ? topi : 0x7fffffff;
             double nd = 1e300;
             int ni = 0x7fffffff;
+            double ld = c0d;
+            int li = c0i;
+            if (cand_less(c1d, c1i, ld, li)) { ld = c1d; li = c1i; }
+            if (cand_less(c2d, c2i, ld, li)) { ld = c2d; li = c2i; }
             for (int r = 0; r < kk; ++r) {
-                double ld = c0d; int li = c0i;
-                if (cand_less(c1d, c1i, ld, li)) { ld = c1d; li = c1i; }
-                if (cand_less(c2d, c2i, ld, li)) { ld = c2d; li = c2i; }
-                double wd = ld; int wi = li;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double od = __shfl_xor_sync(0xffffffffu, wd, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-                    if (cand_less(od, oi, wd, wi)) { wd = od; wi = oi; }
+                const unsigned hi = (unsigned)__double2hiint(ld), lo = (unsigned)__double2loint(ld);
+                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+                const bool eq = (hi == mh) && (lo == ml);
+                const int wi = (int)__reduce_min_sync(0xffffffffu, eq ? (unsigned)li : 0xffffffffu);
+                const double wd = __hiloint2double((int)mh, (int)ml);
+                if (eq && li == wi) {                       // the winning lane drops the entry and re-ranks its three
+                    if (c0i == wi) { c0d = 1e300; c0i = 0x7fffffff; }
+                    else if (c1i == wi) { c1d = 1e300; c1i = 0x7fffffff; }
+                    else { c2d = 1e300; c2i = 0x7fffffff; }
+                    ld = c0d; li = c0i;
+                    if (cand_less(c1d, c1i, ld, li)) { ld = c1d; li = c1i; }
+                    if (cand_less(c2d, c2i, ld, li)) { ld = c2d; li = c2i; }
                 }
-                if (c0i == wi && c0d == wd) { c0d = 1e300; c0i = 0x7fffffff; }
-                else if (c1i == wi && c1d == wd) { c1d = 1e300; c1i = 0x7fffffff; }
-                else if (c2i == wi && c2d == wd) { c2d = 1e300; c2i = 0x7fffffff; }
                 if (lane == r) { nd = wd; ni = wi; }
                 if (r == kk - 1) { tau_d = wd; tau_i = wi; }
             }
@@ -233,16 +243,28 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
         // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside
         const int ksel = cnt >= m.MaxNumPoint ? m.MaxNumPoint : cnt;
         if (cnt == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
-        for (int r = 0; r < ksel; ++r) {
-            const double wd = __shfl_sync(0xffffffffu, topd, r);
-            const int wi = __shfl_sync(0xffffffffu, topi, r);
-            if (lane < 9) {               // x0,x1,x2,u0,u1,K,y0,y1,y2 of the selected row, one value per lane
-                double v;
-                if (lane < 3) v = X[(size_t)wi * 6 + lane];
-                else if (lane < 5) v = U[(size_t)wi * 2 + (lane - 3)];
-                else if (lane == 5) { const double rr = wd / m.h; v = (1.0 - rr * rr) * 3.0 / 4.0; }   // PM.py:193
-                else v = X[(size_t)(wi + 1) * 6 + (lane - 6)];
-                pts[(size_t)(npts + r) * 9 + lane] = v;
+        {
+            // lane r < ksel owns the r-th neighbour: kernel weight once per lane (PM.py:193), then the 10 values of every
+            // selected row are fetched by ksel*10 lanes in parallel
+            const double rr = topd / m.h;
+            const double kw = (1.0 - rr * rr) * 3.0 / 4.0;
+            const int nval = ksel * K1_PW;
+            for (int e0 = 0; e0 < nval; e0 += 32) {
+                const int e = e0 + lane;
+                int r = e / K1_PW;
+                const int f = e - r * K1_PW;
+                r = r < K1_MAXPTS ? r : K1_MAXPTS - 1;
+                const int wi = __shfl_sync(0xffffffffu, topi, r);
+                const double kr = __shfl_sync(0xffffffffu, kw, r);
+                if (e < nval) {
+                    double v;
+                    if (f < 3) v = X[(size_t)wi * 6 + f];
+                    else if (f < 5) v = U[(size_t)wi * 2 + (f - 3)];
+                    else if (f == 5) v = kr;
+                    else if (f < 9) v = X[(size_t)(wi + 1) * 6 + (f - 6)];
+                    else v = 1.0;
+                    pts[(size_t)npts * K1_PW + e] = v;
+                }
             }
         }
         npts += ksel;
@@ -252,29 +274,28 @@ __global__ void __launch_bounds__(32 * 16) knn_ltv_regress_kernel(const __grid_c
 
     // ---- normal equations (PM.py:141-168).  entries: Qvx(15) Qlat(15) bvx(5) bvy(5) bwz(5) ----
     for (int e = lane; e < 45; e += 32) {
-        double acc = 0.0;
+        // entry e = sum_p P[ir] * K * P[ic]; feature columns of a point row: 0..2 state, 3 delta, 4 a, 9 the constant 1
+        int ir, ic;
+        bool diag = false;
         if (e < 30) {
             const int lat = e >= 15;
             const int idx = lat ? e - 15 : e;
             // (r, cc), r <= cc, of the idx-th entry of the upper triangle of a 5 x 5 matrix
             const int r = (idx >= 5) + (idx >= 9) + (idx >= 12) + (idx >= 14);
             const int cc = idx - (r * 5 - r * (r - 1) / 2) + r;
-            for (int p = 0; p < npts; ++p) {
-                const double* P = pts + (size_t)p * 9;
-                const double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
-                const double mc = (cc < 3) ? P[cc] : (cc == 3 ? (lat ? P[3] : P[4]) : 1.0);
-                acc += mr * P[5] * mc;
-            }
-            if (r == cc) acc += m.lamb;
+            ir = (r < 3) ? r : (r == 3 ? (lat ? 3 : 4) : 9);
+            ic = (cc < 3) ? cc : (cc == 3 ? (lat ? 3 : 4) : 9);
+            diag = (r == cc);
         } else {
             const int which = (e - 30) / 5, r = (e - 30) % 5;   // 0 vx, 1 vy, 2 wz
             const int lat = which > 0;
-            for (int p = 0; p < npts; ++p) {
-                const double* P = pts + (size_t)p * 9;
-                const double mr = (r < 3) ? P[r] : (r == 3 ? (lat ? P[3] : P[4]) : 1.0);
-                acc += mr * P[5] * P[6 + which];
-            }
+            ir = (r < 3) ? r : (r == 3 ? (lat ? 3 : 4) : 9);
+            ic = 6 + which;
         }
+        double acc = 0.0;
+        const double* P = pts;
+        for (int p = 0; p < npts; ++p, P += K1_PW) acc += P[ir] * P[5] * P[ic];
+        if (diag) acc += m.lamb;
         ne[e] = acc;
     }
     __syncwarp();
