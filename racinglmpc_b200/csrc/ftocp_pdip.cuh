@@ -154,11 +154,12 @@ struct Regs {
     static constexpr int R1 = N * NCX, R2 = N * NCU, R4 = (M > 0 ? M : 1);
     // lane-constraint pair (k,i):  Fx_i x_k - s <= bx_i  and  s >= 0
     double s[NSLOT(R1)], nu1[NSLOT(R1)], nu3[NSLOT(R1)];
-    double w1[NSLOT(R1)], rs[NSLOT(R1)], d1[NSLOT(R1)], hs[NSLOT(R1)], p1[NSLOT(R1)], p3[NSLOT(R1)];
+    double w1[NSLOT(R1)], rs[NSLOT(R1)], d1[NSLOT(R1)], p1[NSLOT(R1)], p3[NSLOT(R1)];
+    double iw1[NSLOT(R1)], is_[NSLOT(R1)], ihs[NSLOT(R1)];   // reciprocals of w1, s, hs = qs2 + nu1/w1 + nu3/s (one division each per iteration)
     // input bound (k,j):  Fu_j u_k <= bu_j
-    double nu2[NSLOT(R2)], w2[NSLOT(R2)], p2[NSLOT(R2)];
+    double nu2[NSLOT(R2)], w2[NSLOT(R2)], iw2[NSLOT(R2)], p2[NSLOT(R2)];
     // simplex multiplier l:  lam_l >= 0
-    double lam[NSLOT(R4)], nu4[NSLOT(R4)], rl[NSLOT(R4)], p4[NSLOT(R4)], rho[NSLOT(R4)], dlam[NSLOT(R4)];
+    double lam[NSLOT(R4)], ilam[NSLOT(R4)], nu4[NSLOT(R4)], rl[NSLOT(R4)], p4[NSLOT(R4)], rho[NSLOT(R4)], dlam[NSLOT(R4)];
     double y1;
 };
 
@@ -201,10 +202,13 @@ LMPC_HD void tri8(int e, int& i, int& j) {
     while (e >= 8 - i) { e -= 8 - i; ++i; }
     j = e + i;
 }
-LMPC_HD double step_bound(double v, double dv, double a) {
-    // largest alpha keeping v + alpha dv >= 0
-    return (dv < 0.0) ? fmin(a, -v / dv) : a;
+// Ratio test without divisions: (rn, rd) is the largest -dv/v seen so far as a fraction (start 0/1; v, rd > 0).
+// The step bound of the lane is rd/rn, one division per test instead of one per constraint.
+LMPC_HD void ratio_update(double v, double dv, double& rn, double& rd) {
+    const double nn = -dv;
+    if (nn * rd > rn * v) { rn = nn; rd = v; }
 }
+LMPC_HD double ratio_bound(double rn, double rd, double a) { return (rn > 0.0) ? fmin(a, rd / rn) : a; }
 
 template <int N, int M, int NCX, int NCU>
 struct Pdip {
@@ -316,7 +320,7 @@ struct Pdip {
     static LMPC_HD double terminal_factor(W& w, RG& g, const FtocpConst& c, double d4_floor) {
         double acc[6] = {0, 0, 0, 0, 0, 0}, dl = 0.0;
         FOR_SLOTS(r, row, R4) {
-            double d4 = fmax(g.nu4[r] / g.lam[r], d4_floor);
+            double d4 = fmax(g.nu4[r] * g.ilam[r], d4_floor);
             double di = 1.0 / d4;
             w.d4i[row] = di;
             dl += di;
@@ -365,7 +369,7 @@ struct Pdip {
                 for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
                 if (i == j) {
                     if (!(v > 0.0)) { ok = false; v = 1.0; }
-                    L[i * (i + 1) / 2 + i] = 1.0 / sqrt(v);          // store the reciprocal pivot
+                    L[i * (i + 1) / 2 + i] = rsqrt_f64(v);           // store the reciprocal pivot
                 } else {
                     L[i * (i + 1) / 2 + j] = v * L[j * (j + 1) / 2 + j];
                 }
@@ -757,13 +761,16 @@ struct Pdip {
                 g.rs[r] = rs;
                 rd_loc = fmax(rd_loc, fabs(rs));
                 comp += w1 * g.nu1[r] + g.s[r] * g.nu3[r];
-                double d1 = g.nu1[r] / w1, d3 = g.nu3[r] / g.s[r];
-                double hs = c.qs2 + d1 + d3;
+                const double iw1 = 1.0 / w1, is = 1.0 / g.s[r];
+                g.iw1[r] = iw1;
+                g.is_[r] = is;
+                double d1 = g.nu1[r] * iw1, d3 = g.nu3[r] * is;
+                const double ihs = 1.0 / (c.qs2 + d1 + d3);
                 g.d1[r] = d1;
-                g.hs[r] = hs;
-                w.Dt[row] = d1 * (c.qs2 + d3) / hs;
+                g.ihs[r] = ihs;
+                w.Dt[row] = d1 * (c.qs2 + d3) * ihs;
                 // predictor: rc1 = w1 nu1, rc3 = s nu3  ->  e1 = -nu1, rs + rc3/s = rs + nu3
-                w.ex[row] = (-g.nu1[r] * (c.qs2 + d3) + d1 * (rs + g.nu3[r])) / hs;
+                w.ex[row] = (-g.nu1[r] * (c.qs2 + d3) + d1 * (rs + g.nu3[r])) * ihs;
                 w.dx[row] = g.nu1[r];
             }
             FOR_SLOTS(r, row, R2) {
@@ -771,7 +778,9 @@ struct Pdip {
                 double w2 = c.bu[j] - (c.Fu[j * 2] * w.u[k * 2] + c.Fu[j * 2 + 1] * w.u[k * 2 + 1]);
                 g.w2[r] = w2;
                 comp += w2 * g.nu2[r];
-                w.d2[row] = g.nu2[r] / w2;
+                const double iw2 = 1.0 / w2;
+                g.iw2[r] = iw2;
+                w.d2[row] = g.nu2[r] * iw2;
                 w.eu[row] = -g.nu2[r];           // predictor: -rc2/w2
                 w.dx[N * NCX + row] = g.nu2[r];
             }
@@ -785,6 +794,7 @@ struct Pdip {
                     g.rl[r] = rl;
                     rd_loc = fmax(rd_loc, fabs(rl));
                     comp += g.lam[r] * g.nu4[r];
+                    g.ilam[r] = 1.0 / g.lam[r];
                     g.rho[r] = -rl - g.nu4[r];   // predictor: rc4/lam = nu4
                 }
             } else {
@@ -827,39 +837,39 @@ struct Pdip {
             forward(w);
             double dy1 = 0.0;
             if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
-            double a_aff = 1.0;
+            double rn = 0.0, rd = 1.0;
             FOR_SLOTS(r, row, R1) {
                 int k = row / NCX, i = row % NCX;
                 double fdx = dot6(&c.Fx[i * 6], &w.dx[k * 6]);
                 double gs = -g.rs[r] - g.nu1[r] - g.nu3[r];
-                double ds = (gs + g.d1[r] * fdx) / g.hs[r];
+                double ds = (gs + g.d1[r] * fdx) * g.ihs[r];
                 double dw1 = -fdx + ds;
                 double dn1 = -g.nu1[r] - g.d1[r] * dw1;
-                double dn3 = -g.nu3[r] - (g.nu3[r] / g.s[r]) * ds;
-                a_aff = step_bound(g.w1[r], dw1, a_aff);
-                a_aff = step_bound(g.s[r], ds, a_aff);
-                a_aff = step_bound(g.nu1[r], dn1, a_aff);
-                a_aff = step_bound(g.nu3[r], dn3, a_aff);
+                double dn3 = -g.nu3[r] - (g.nu3[r] * g.is_[r]) * ds;
+                ratio_update(g.w1[r], dw1, rn, rd);
+                ratio_update(g.s[r], ds, rn, rd);
+                ratio_update(g.nu1[r], dn1, rn, rd);
+                ratio_update(g.nu3[r], dn3, rn, rd);
                 g.p1[r] = dw1 * dn1;
                 g.p3[r] = ds * dn3;
             }
             FOR_SLOTS(r, row, R2) {
                 int k = row / NCU, j = row % NCU;
                 double dw2 = -(c.Fu[j * 2] * w.du[k * 2] + c.Fu[j * 2 + 1] * w.du[k * 2 + 1]);
-                double dn2 = -g.nu2[r] - (g.nu2[r] / g.w2[r]) * dw2;
-                a_aff = step_bound(g.w2[r], dw2, a_aff);
-                a_aff = step_bound(g.nu2[r], dn2, a_aff);
+                double dn2 = -g.nu2[r] - (g.nu2[r] * g.iw2[r]) * dw2;
+                ratio_update(g.w2[r], dw2, rn, rd);
+                ratio_update(g.nu2[r], dn2, rn, rd);
                 g.p2[r] = dw2 * dn2;
             }
             if (LMPC) {
                 FOR_SLOTS(r, row, R4) {
-                    double dn4 = -g.nu4[r] - (g.nu4[r] / g.lam[r]) * g.dlam[r];
-                    a_aff = step_bound(g.lam[r], g.dlam[r], a_aff);
-                    a_aff = step_bound(g.nu4[r], dn4, a_aff);
+                    double dn4 = -g.nu4[r] - (g.nu4[r] * g.ilam[r]) * g.dlam[r];
+                    ratio_update(g.lam[r], g.dlam[r], rn, rd);
+                    ratio_update(g.nu4[r], dn4, rn, rd);
                     g.p4[r] = g.dlam[r] * dn4;
                 }
             }
-            a_aff = wmin(a_aff);
+            const double a_aff = wmin(ratio_bound(rn, rd, 1.0));
             // complementarity after the affine step.  With p = dw*dnu and dw*nu + w*dnu = -w*nu:
             //   (w + a dw)(nu + a dnu) = w nu (1 - a) + a^2 p
             double comp_aff = 0.0;
@@ -879,21 +889,21 @@ struct Pdip {
             FOR_SLOTS(r, row, R1) {
                 double rc1 = g.w1[r] * g.nu1[r] + g.p1[r] - sm;
                 double rc3 = g.s[r] * g.nu3[r] + g.p3[r] - sm;
-                double d3 = g.nu3[r] / g.s[r];
-                double e1 = -rc1 / g.w1[r];
-                w.ex[row] = (e1 * (c.qs2 + d3) + g.d1[r] * (g.rs[r] + rc3 / g.s[r])) / g.hs[r];
+                double d3 = g.nu3[r] * g.is_[r];
+                double e1 = -rc1 * g.iw1[r];
+                w.ex[row] = (e1 * (c.qs2 + d3) + g.d1[r] * (g.rs[r] + rc3 * g.is_[r])) * g.ihs[r];
                 g.p1[r] = rc1;   // keep rc for the final recovery
                 g.p3[r] = rc3;
             }
             FOR_SLOTS(r, row, R2) {
                 double rc2 = g.w2[r] * g.nu2[r] + g.p2[r] - sm;
-                w.eu[row] = -rc2 / g.w2[r];
+                w.eu[row] = -rc2 * g.iw2[r];
                 g.p2[r] = rc2;
             }
             if (LMPC) {
                 FOR_SLOTS(r, row, R4) {
                     double rc4 = g.lam[r] * g.nu4[r] + g.p4[r] - sm;
-                    g.rho[r] = -g.rl[r] - rc4 / g.lam[r];
+                    g.rho[r] = -g.rl[r] - rc4 * g.ilam[r];
                     g.p4[r] = rc4;
                 }
                 terminal_rhs(w, g, -rone, c1, beta);
@@ -905,40 +915,41 @@ struct Pdip {
             if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
 
             // ---- step length and update ----------------------------------------------------------
-            double amax = 1e300;
+            rn = 0.0;
+            rd = 1.0;
             double ds_[NSLOT(R1)], dw1_[NSLOT(R1)], dn1_[NSLOT(R1)], dn3_[NSLOT(R1)], dw2_[NSLOT(R2)], dn2_[NSLOT(R2)], dn4_[NSLOT(R4)];
             FOR_SLOTS(r, row, R1) {
                 int k = row / NCX, i = row % NCX;
                 double fdx = dot6(&c.Fx[i * 6], &w.dx[k * 6]);
                 double rc1 = g.p1[r], rc3 = g.p3[r];
-                double gs = -g.rs[r] - rc1 / g.w1[r] - rc3 / g.s[r];
-                double ds = (gs + g.d1[r] * fdx) / g.hs[r];
+                double gs = -g.rs[r] - rc1 * g.iw1[r] - rc3 * g.is_[r];
+                double ds = (gs + g.d1[r] * fdx) * g.ihs[r];
                 double dw1 = -fdx + ds;
-                double dn1 = (-rc1 - g.nu1[r] * dw1) / g.w1[r];
-                double dn3 = (-rc3 - g.nu3[r] * ds) / g.s[r];
-                amax = step_bound(g.w1[r], dw1, amax);
-                amax = step_bound(g.s[r], ds, amax);
-                amax = step_bound(g.nu1[r], dn1, amax);
-                amax = step_bound(g.nu3[r], dn3, amax);
+                double dn1 = (-rc1 - g.nu1[r] * dw1) * g.iw1[r];
+                double dn3 = (-rc3 - g.nu3[r] * ds) * g.is_[r];
+                ratio_update(g.w1[r], dw1, rn, rd);
+                ratio_update(g.s[r], ds, rn, rd);
+                ratio_update(g.nu1[r], dn1, rn, rd);
+                ratio_update(g.nu3[r], dn3, rn, rd);
                 ds_[r] = ds; dw1_[r] = dw1; dn1_[r] = dn1; dn3_[r] = dn3;
             }
             FOR_SLOTS(r, row, R2) {
                 int k = row / NCU, j = row % NCU;
                 double dw2 = -(c.Fu[j * 2] * w.du[k * 2] + c.Fu[j * 2 + 1] * w.du[k * 2 + 1]);
-                double dn2 = (-g.p2[r] - g.nu2[r] * dw2) / g.w2[r];
-                amax = step_bound(g.w2[r], dw2, amax);
-                amax = step_bound(g.nu2[r], dn2, amax);
+                double dn2 = (-g.p2[r] - g.nu2[r] * dw2) * g.iw2[r];
+                ratio_update(g.w2[r], dw2, rn, rd);
+                ratio_update(g.nu2[r], dn2, rn, rd);
                 dw2_[r] = dw2; dn2_[r] = dn2;
             }
             if (LMPC) {
                 FOR_SLOTS(r, row, R4) {
-                    double dn4 = (-g.p4[r] - g.nu4[r] * g.dlam[r]) / g.lam[r];
-                    amax = step_bound(g.lam[r], g.dlam[r], amax);
-                    amax = step_bound(g.nu4[r], dn4, amax);
+                    double dn4 = (-g.p4[r] - g.nu4[r] * g.dlam[r]) * g.ilam[r];
+                    ratio_update(g.lam[r], g.dlam[r], rn, rd);
+                    ratio_update(g.nu4[r], dn4, rn, rd);
                     dn4_[r] = dn4;
                 }
             }
-            amax = wmin(amax);
+            const double amax = wmin(ratio_bound(rn, rd, 1e300));
             double al = fmin(1.0, 0.995 * amax);
             if (!(al > 0.0) || !(al <= 1.0)) { status = ST_NUMERICAL; break; }
             // Stay in a wide neighbourhood of the central path, min_i w_i nu_i >= gamma * mean: without it

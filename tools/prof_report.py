@@ -53,3 +53,12 @@ tot=sum(a[0] for a in agg.values()); tote=sum(a[1] for a in agg.values())
 for k,a in sorted(agg.items(), key=lambda kv:-kv[1][0]):
     if a[0]/tot>0.004: print('%5.1f%% smp %5.1f%% inst thr/inst %4.1f  %s'%(100*a[0]/tot,100*a[1]/tote,a[2]/max(a[1],1),k))
 print(ops.most_common(14))
+# top source lines (helps to split the '?' bucket = helpers above the first marked function)
+byline=collections.defaultdict(lambda:[0,0])
+for k in range(n):
+    c=insts[k][0]
+    if c and c[0]=='ftocp_pdip.cuh':
+        byline[c[1]][0]+=int(data[k][ci]); byline[c[1]][1]+=int(data[k][ce])
+print('top lines (line, %samples, %inst, text):')
+for ln,(s_,e_) in sorted(byline.items(), key=lambda kv:-kv[1][0])[:int(os.environ.get('TOPLINES','25'))]:
+    print('%5d %5.1f%% %5.1f%%  %s'%(ln,100*s_/tot,100*e_/tote,src[ln-1].strip()[:100]))
