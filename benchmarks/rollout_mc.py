@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3]: LMPC Monte-Carlo rollouts sharded over the GPUs of one node, with the once-per-lap NCCL
-all-gather of the finished laps (pooled-safe-set exchange).
+all-gather of finished laps (pooled-safe-set exchange).
 
 Every instance is an independent LMPC controller + vehicle (seeded PID laps as initial safe set, Philox process noise),
 advanced entirely on the device: K1 regression -> K2 selection -> QP -> shift -> addPoint -> dynModel per step.
-Lap ends are handled per instance (device-side lap hand-over); after `--steps` closed-loop steps the laps driven so far
-are packed on the device and all-gathered over NCCL, and every rank ranks the pooled laps by lap time.
+Lap ends are handled per instance (device-side lap hand-over, host only keeps the lap-time lists).
 
-  python benchmarks/rollout_mc.py --batch 8192 --steps 260            (1 GPU)
+  --mode independent   reference semantics: no collective anywhere (replicas).
+  --mode pooled        once every instance of a rank is `--ship-after` steps into LMPC lap r+1, the rank packs lap r of each
+                       instance (with the rows LMPC.addPoint has appended past the finish line so far: the selection window
+                       of PC.py:492-495 plus the N-step look-ahead of the terminal guess needs about 20 of them) on the device,
+                       all ranks all-gather the packed laps and
+                       lap times over NCCL, rank them (stable argsort of LapTime, PC.py:395) and every instance receives
+                       the `--share` globally fastest laps it does not own as additional stored laps (safe set + model).
+
+  python benchmarks/rollout_mc.py --batch 8192 --laps 3            (1 GPU)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 benchmarks/rollout_mc.py --batch 8192
-Prints one JSON line (rank 0): closed-loop steps/s over all GPUs (device events, max over ranks), laps finished,
-lap-time statistics, all-gather time and bytes."""
+Prints one JSON line (rank 0): closed-loop steps/s over all GPUs (device events, max over ranks), lap-time statistics per
+LMPC lap, all-gather time and bytes."""
 import argparse
 import json
 import os
@@ -25,11 +32,18 @@ sys.path.insert(0, ROOT)
 from racinglmpc_b200 import workloads, sharding, reference_params as rp      # noqa: E402
 from racinglmpc_b200.controller import BatchedController                      # noqa: E402
 
+FIRST_LMPC_LAP = 4      # laps 0..3 are the PID seed laps (main.py:102-110)
+
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU")
-    ap.add_argument("--steps", type=int, default=260)
+    ap.add_argument("--laps", type=int, default=3, help="LMPC laps every instance has to finish")
+    ap.add_argument("--max-steps", type=int, default=0, help="0 = 300 per lap")
+    ap.add_argument("--mode", choices=["independent", "pooled"], default="pooled")
+    ap.add_argument("--share", type=int, default=2, help="pooled mode: globally fastest laps handed to every instance per exchange")
+    ap.add_argument("--tpad", type=int, default=288, help="rows per exchanged lap (lap + addPoint overrun)")
+    ap.add_argument("--ship-after", type=int, default=40, help="pooled mode: steps into the next lap before a lap is shipped")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -41,7 +55,7 @@ def main():
     xP, uP = g["pid_x"], g["pid_u"]
     numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
     c = BatchedController(par, B, workloads.track_seg_table(), rp.TRACK_LENGTH, trToUse=4, numSS_Points=numSS_Points,
-                          numSS_it=numSS_it, QterminalSlack=Qts, device=local, Tmax=1280, ss_cap=6, model_cap=5)
+                          numSS_it=numSS_it, QterminalSlack=Qts, device=local, Tmax=1280, ss_cap=7, model_cap=5)
     t0 = time.perf_counter()
     for b in range(B):                       # main.py:102-110: four copies of the PID lap seed both stores
         for _ in range(4):
@@ -60,43 +74,84 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    lap_times, host_s = [], 0.0
+    laps_done = np.zeros(B, np.int64)                   # LMPC laps finished per instance
+    lap_len = [[] for _ in range(args.laps)]            # lap_len[r] = lengths of everybody's r-th LMPC lap
+    since_lap = np.zeros(B, np.int64)
+    host_s, xchg_s, xchg_bytes, n_xchg, took_total = 0.0, 0.0, 0, 0, 0
+    next_round = 1                                      # exchange round r ships LMPC lap r early in lap r+1
+    rows = torch.zeros(B, args.tpad, 9, dtype=torch.float64, device=dev)
+    lens = torch.zeros(B, dtype=torch.int32, device=dev)
+    max_steps = args.max_steps or 300 * args.laps
+    steps = 0
     l0 = c.kernel_launches
     e0.record(stream)
-    for k in range(args.steps):
+    while steps < max_steps and laps_done.min() < args.laps:
         c.rollout_step(seed=1234 + rank)
+        steps += 1
+        since_lap += 1
         done, n = c.rollout_done()            # 2 x 4 B per instance back to the host: the only per-step traffic
         if done.any():
             th = time.perf_counter()
             fin = c.rollout_finish_laps(done, n)
-            lap_times += [int(n[b]) for b in fin]
+            for b in fin:
+                if laps_done[b] < args.laps:
+                    lap_len[laps_done[b]].append(int(n[b]))
+            laps_done[fin] += 1
+            since_lap[fin] = 0
             host_s += time.perf_counter() - th
+        if args.mode == "pooled" and next_round < args.laps and laps_done.min() >= next_round and \
+                since_lap[laps_done == next_round].min(initial=10 ** 9) >= args.ship_after:
+            # ---- once-per-lap exchange: pack on the device, all-gather over NCCL, rank, hand out -----------------------
+            tx = time.perf_counter()
+            # lap numbers shift by the laps an instance imported earlier (they sit before its own latest lap)
+            own = np.array([c.own_lap_number(b, FIRST_LMPC_LAP + next_round - 1) for b in range(B)])
+            c.export_laps(own, args.tpad, rows, lens)
+            times = torch.tensor([c.LapTime[b][own[b]] for b in range(B)], dtype=torch.int32, device=dev)
+            c.sync()
+            rows_all, lens_all = sharding.allgather_laps(rows, lens)
+            times_all = sharding.allgather_vec(times)
+            best = [int(i) for i in sharding.pooled_fastest(times_all, args.share + 1)]
+            times_np = times_all.cpu().numpy()
+            for j in range(args.share):                     # pass j hands every instance its j-th foreign lap
+                src = np.full(B, -1, np.int32)
+                lt = np.zeros(B, np.int64)
+                for b in range(B):
+                    cand = [gi for gi in best if gi != rank * B + b]
+                    if j < len(cand):
+                        src[b], lt[b] = cand[j], times_np[cand[j]]
+                took_total += len(c.import_laps(src, lt, args.tpad, rows_all, lens_all))
+            n_xchg += 1
+            xchg_bytes = int(rows.numel() * 8 + lens.numel() * 4 + times.numel() * 4)
+            torch.cuda.synchronize()
+            xchg_s += time.perf_counter() - tx
+            next_round += 1
     e1.record(stream)
     c.sync()
     launches = c.kernel_launches - l0
     ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    # ---- once-per-lap exchange of the laps in flight / finished: pack on the device, all-gather over NCCL ----
-    Tpad = 256
-    rows = torch.zeros(B, Tpad, 8, dtype=torch.float64, device=dev)
-    lens = torch.zeros(B, dtype=torch.int32, device=dev)
-    c.rollout_export_laps(Tpad, rows, lens)
-    c.sync()
-    torch.cuda.synchronize()
-    ta = time.perf_counter()
-    rows_all, lens_all = sharding.allgather_laps(rows, lens) if world > 1 else (rows, lens)
-    torch.cuda.synchronize()
-    ag_s = time.perf_counter() - ta
-    best = sharding.pooled_fastest(lens_all, 4)
+    steps_all = steps
+    if world > 1:
+        t = torch.tensor([steps], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        steps_all = int(t.item())
+    else:
+        steps_all = steps
     st = c.rollout_state()
+    flags_or, unsolved = c.rollout_health()
+    stats = []
+    for r in range(args.laps):
+        a = np.array(lap_len[r]) if lap_len[r] else np.array([0])
+        stats.append({"lap": r + 1, "n": int(len(lap_len[r])), "mean": float(a.mean()), "min": int(a.min()), "max": int(a.max())})
     if rank == 0:
-        lt = np.array(lap_times) if lap_times else np.array([0])
-        print(json.dumps({"benchmark": "configs[3] LMPC Monte-Carlo rollouts", "n_gpus": world, "batch_per_gpu": B,
-                          "closed_loop_steps": args.steps, "ms_total": ms, "controller_steps_per_s": B * world * args.steps / (ms * 1e-3),
-                          "kernel_launches": int(launches), "laps_finished_rank0": int(len(lap_times)),
-                          "lap_len_mean": float(lt.mean()), "lap_len_min": int(lt.min()), "lap_len_max": int(lt.max()),
+        print(json.dumps({"benchmark": "configs[3] LMPC Monte-Carlo rollouts", "mode": args.mode, "n_gpus": world, "batch_per_gpu": B,
+                          "closed_loop_steps_rank0": steps, "ms_total": ms,
+                          "controller_steps_per_s": B * steps_all / (ms * 1e-3),
+                          "kernel_launches_rank0": int(launches), "lap_stats_rank0": stats,
                           "host_lap_bookkeeping_s": host_s, "setup_s": setup_s,
-                          "allgather_ms": ag_s * 1e3, "allgather_bytes_per_rank": int(rows.numel() * 8 + lens.numel() * 4),
-                          "pooled_fastest_lens": [int(lens_all[i]) for i in best], "s_mean": float(st["x"][:, 4].mean())}))
+                          "exchanges": n_xchg, "exchange_s_total": xchg_s, "allgather_bytes_per_rank": xchg_bytes,
+                          "laps_handed_out_rank0": took_total, "share": args.share, "ship_after": args.ship_after,
+                          "instances_with_flags_rank0": int((flags_or != 0).sum()), "flag_bits_rank0": int(np.bitwise_or.reduce(flags_or)),
+                          "unsolved_steps_rank0": int(unsolved.sum()), "s_mean": float(st["x"][:, 4].mean())}))
     c.close()
     if world > 1:
         dist.destroy_process_group()

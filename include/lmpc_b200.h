@@ -169,6 +169,11 @@ int lmpc_step_host(lmpc_handle* h, int mode, const double* x0, double* xPred, do
                    double* zt_u, double* SS_sel, int* status, int* iters, double* resid, int* flags);
 /* Same with x0 already on the device; results stay in the handle's device buffers (lmpc_device_buffer). */
 int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev);
+/* QP status / iterations / residuals [B,3] / step flags of the most recent lmpc_step_dev or lmpc_rollout_step (any NULL). */
+int lmpc_step_results(lmpc_handle* h, int* status, int* iters, double* resid, int* flags);
+/* Inspection: copy `bytes` from the named device buffer (names as lmpc_device_buffer) at `offset_bytes` to host memory.
+ * The caller is responsible for staying inside the buffer (sizes follow from batch, N and numSS_Points). */
+int lmpc_read_buffer(lmpc_handle* h, const char* name, size_t offset_bytes, void* dst, size_t bytes);
 /* Device address of an internal buffer by name: "xPred","uPred","lambd","zt","zt_u","abc","SS_sel","Qfun_sel",
  * "Succ_SS","Succ_uSS","status","iters","resid","flags","xLin","uLin". */
 void* lmpc_device_buffer(lmpc_handle* h, const char* name);
@@ -183,13 +188,31 @@ int lmpc_rollout_create(lmpc_handle* h, int Tcl);
 int lmpc_rollout_set_state(lmpc_handle* h, const double* x, const double* xglob);              /* [B,6] host, may be NULL */
 int lmpc_rollout_get_state(lmpc_handle* h, double* x, double* xglob, int* done, int* cl_len);  /* any may be NULL      */
 int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned long long seed);
+/* Since lmpc_rollout_create: OR of the per-step flags (bits as in lmpc_step_host) and number of steps whose QP was not
+ * reported solved (the reference would have driven on with feasible = 0, PC.py:279-283), per instance; either may be NULL. */
+int lmpc_rollout_get_health(lmpc_handle* h, int* flags_or, int* unsolved_steps);                 /* [B] host             */
 int lmpc_rollout_get_lap(lmpc_handle* h, int inst, int* T, double* x, double* u);              /* closed-loop record   */
 /* Lap hand-over on the device = LMPC.addTrajectory + PredictiveModel.addTrajectory of the lap just driven (either slot may
  * be -1), then s -= TrackLength (SysModel.py:50), record restarted, timeStep = 0 (PC.py:445). */
 int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slot);
+/* The same for every instance with fin_host[b] != 0 in one launch; slots per instance as above ([B] host arrays). */
+int lmpc_rollout_commit_laps(lmpc_handle* h, const int* fin_host, const int* ss_slots_host, const int* model_slots_host);
 /* Pack all closed-loop records into rows_dev[B,Tpad,8] = (x | u), lens_dev[B] (device buffers of the caller): the send
  * buffer of the once-per-lap all-gather of the pooled-safe-set mode. */
 int lmpc_rollout_export_laps_dev(lmpc_handle* h, int Tpad, double* rows_dev, int* lens_dev);
+
+/* ---- pooled-safe-set exchange (no reference counterpart: the reference runs one controller) ------------------
+ * Send side: pack stored lap slots_host[b] (-1: none, lens = 0) of every instance, including the rows LMPC.addPoint
+ * appended after the finish line (PC.py:466-476), into rows_dev[B,Tpad,9] = (x 6 | u 2 | Qfun 1), lens_dev[B] -- device
+ * buffers of the caller, which all-gathers them (NCCL) across ranks.
+ * Receive side: instance b stores gathered lap src_host[b] (index into rows_dev[n_src,Tpad,9]; -1: nothing) in safe-set slot
+ * ss_slots_host[b] (-1: skip) with its Qfun, i.e. LMPC.addTrajectory (PC.py:418-445) of a lap driven by another
+ * controller, and in regression-model slot model_slots_host[b] (NULL or -1: skip; rows up to the finish line only), i.e.
+ * PredictiveModel.addTrajectory (PredictiveModel.py:35-46).  Which laps are "the numSS_it fastest" stays the caller's
+ * bookkeeping (lmpc_ss_set_selection / lmpc_model_set_used), exactly as for laps driven locally. */
+int lmpc_ss_export_laps_dev(lmpc_handle* h, const int* slots_host, int Tpad, double* rows_dev, int* lens_dev);
+int lmpc_ss_import_laps_dev(lmpc_handle* h, const int* ss_slots_host, const int* model_slots_host, const int* src_host, int n_src,
+                            int Tpad, const double* rows_dev, const int* lens_dev);
 
 int lmpc_sizeof_params(void);
 int lmpc_sizeof_model_params(void);

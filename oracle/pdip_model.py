@@ -16,6 +16,8 @@ Problem (same data the reference assembles at PredictiveControllers.py:166-257,3
 """
 import numpy as np
 
+RECENTER = True       # replace the corrector by a pure centring step when its step cannot re-enter the neighbourhood
+RECENTER_AFTER = 3    # ... within this many reductions (kernel: RECENTRE_AFTER)
 W_REFINE = 1      # refinement steps of the 6x6 covariance-form solve, residual taken through the recovered dlam
 ADAPTIVE_FLOOR = False  # experiment (relax the floor on stall): helps some instances, hurts others -> off
 EXACT_TERMINAL_RECOVERY = False
@@ -59,7 +61,8 @@ def from_params(p, A, B, C, x0, uOld, SS=None, Qfun=None, Qts=None):
                    p.Fu, np.squeeze(p.bu), A, B, C, x0, np.asarray(uOld, float).ravel(), SS, Qfun, Qts)
 
 
-def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0=0.3, gamma=0.01):
+def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0=0.3, gamma=0.01, warm=None, snap_mu=None,
+          warm_theta=0.5):
     """Returns dict(x[N+1,n], u[N,d], s[N,ncx], lam[m], xi[n], iters, r_prim, r_dual, gap, status)."""
     N, n, d = qp.N, 6, 2
     Fx, bx, Fu, bu = qp.Fx, qp.bx, qp.Fu, qp.bu
@@ -80,6 +83,15 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
         if g[j] > 0.9 * bu[j]:
             tau = min(tau, 0.9 * bu[j] / g[j])
     u = np.tile(tau * qp.uOld, (N, 1))
+    if warm is not None and warm.get("primal_only"):
+        u = warm["u"].copy()
+        for k in range(N):            # keep the input rows strictly inside their bounds
+            g = Fu @ u[k]
+            t = 1.0
+            for j in range(ncu):
+                if g[j] > 0.9 * bu[j]:
+                    t = min(t, 0.9 * bu[j] / g[j])
+            u[k] *= t
     x = np.zeros((N + 1, n))
     x[0] = qp.x0
     for k in range(N):
@@ -110,6 +122,22 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
         y1 = -np.min(red) + (1.0 if mu0 is None else mu0 * m)
         nu4 = red + y1
     n_ineq = N * (2 * ncx + ncu) + m
+    if warm is not None and not warm.get("primal_only"):
+        # warm start from an intermediate iterate of the previous (shifted) problem: inputs, lane slacks and all
+        # multipliers are taken over, states are rolled out from the new x0, derived slacks kept >= theta * old
+        u = warm["u"].copy()
+        for k in range(N):
+            x[k + 1] = A[k] @ x[k] + B[k] @ u[k] + C[k]
+        s = warm["s"].copy()
+        w1 = np.array([bx - Fx @ x[k] + s[k] for k in range(N)])
+        low = w1 < warm_theta * warm["w1"]
+        s = np.where(low, s + warm_theta * warm["w1"] - w1, s)
+        w1 = np.array([bx - Fx @ x[k] + s[k] for k in range(N)])
+        w2 = np.array([bu - Fu @ u[k] for k in range(N)])
+        nu1, nu2, nu3 = warm["nu1"].copy(), warm["nu2"].copy(), warm["nu3"].copy()
+        if lmpc:
+            lam, nu4, y1 = warm["lam"].copy(), warm["nu4"].copy(), float(warm["y1"])
+    snap = None
 
     def u_rate_grad(u):
         gr = np.zeros((N, d))
@@ -149,6 +177,10 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                      (max(np.abs(rxi).max(), np.abs(rlam).max()) if lmpc else 0.0))
         if verbose:
             print("it %2d  rp %.2e rd %.2e mu %.2e" % (it, r_prim, r_dual, mu))
+        if snap_mu is not None and snap is None and (mu <= snap_mu):
+            snap = dict(u=u.copy(), s=s.copy(), w1=w1.copy(), nu1=nu1.copy(), nu2=nu2.copy(), nu3=nu3.copy(), mu=mu, it=it)
+            if lmpc:
+                snap.update(lam=lam.copy(), nu4=nu4.copy(), y1=y1)
         if r_prim <= eps and r_dual <= eps and mu <= (eps if eps_gap is None else eps_gap):
             status = 1
             break
@@ -276,8 +308,8 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                 out.update(dy1=dy1, dyT=dyT, dlam=dlam, dxi=dxi, dnu4=dnu4)
             return out
 
-        def max_step(st):
-            al = 1.0
+        def max_step(st, cap=1.0):
+            al = cap
             pairs = [(w1, st["dw1"]), (w2, st["dw2"]), (s, st["ds"]), (nu1, st["dnu1"]),
                      (nu2, st["dnu2"]), (nu3, st["dnu3"])]
             if lmpc:
@@ -302,7 +334,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
         cc = solve_rhs(w1 * nu1 + aff["dw1"] * aff["dnu1"] - sm, w2 * nu2 + aff["dw2"] * aff["dnu2"] - sm,
                        s * nu3 + aff["ds"] * aff["dnu3"] - sm,
                        (lam * nu4 + aff["dlam"] * aff["dnu4"] - sm) if lmpc else None)
-        al = min(1.0, 0.995 * max_step(cc))
+        al = min(1.0, 0.995 * max_step(cc, 1e300))        # as the kernel: full step when the boundary is > 1/0.995 away
         if gamma > 0.0:
             # stay in a wide neighbourhood of the central path: min_i w_i nu_i >= gamma * mu
             def prods(a):
@@ -311,11 +343,29 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                 if lmpc:
                     pr.append((lam + a * cc["dlam"]) * (nu4 + a * cc["dnu4"]))
                 return np.concatenate(pr)
-            for _ in range(12):
+            ok_nb = False
+            for tr in range(12):
                 pr = prods(al)
                 if pr.min() >= gamma * pr.mean():
+                    ok_nb = True
+                    break
+                if RECENTER and tr >= RECENTER_AFTER:
                     break
                 al *= 0.8
+            if verbose and not ok_nb:
+                p0 = prods(0.0)
+                print("      neighbourhood backtracking failed: current min/mean %.3e, tries %d" % (p0.min() / p0.mean(), tr))
+            if RECENTER and not ok_nb:
+                # pure centring step from the same factorisation: sigma = 1, no second-order term
+                cc = solve_rhs(w1 * nu1 - mu, w2 * nu2 - mu, s * nu3 - mu, (lam * nu4 - mu) if lmpc else None)
+                al = min(1.0, 0.995 * max_step(cc, 1e300))
+                for tr in range(12):
+                    pr = prods(al)
+                    if pr.min() >= gamma * pr.mean():
+                        break
+                    al *= 0.8
+                if verbose:
+                    print("      recentring step alpha %.3f  -> min/mean %.3e" % (al, pr.min() / pr.mean()))
         if DEBUG_HOOK:
             # residual of the u-rows and lambda-rows of the Newton system for the corrector step
             dx_, du_ = cc["dx"], cc["du"]
@@ -353,7 +403,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
             lam, xi = lam + al * cc["dlam"], xi + al * cc["dxi"]
             yT, y1, nu4 = yT + al * cc["dyT"], y1 + al * cc["dy1"], nu4 + al * cc["dnu4"]
 
-    out = dict(x=x, u=u, s=s, iters=it, r_prim=r_prim, r_dual=r_dual, gap=mu, status=status)
+    out = dict(x=x, u=u, s=s, iters=it, r_prim=r_prim, r_dual=r_dual, gap=mu, status=status, snap=snap)
     if lmpc:
         out.update(lam=lam, xi=xi)
     return out

@@ -77,15 +77,21 @@ def lib():
     L.lmpc_select_host.argtypes = [_vp] + [_vp] * 7
     L.lmpc_step_host.argtypes = [_vp, C.c_int] + [_vp] * 11
     L.lmpc_step_dev.argtypes = [_vp, C.c_int, _vp]
+    L.lmpc_step_results.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    L.lmpc_read_buffer.argtypes = [_vp, C.c_char_p, C.c_size_t, _vp, C.c_size_t]
     L.lmpc_device_buffer.argtypes = [_vp, C.c_char_p]
     L.lmpc_device_buffer.restype = _vp
     L.lmpc_rollout_create.argtypes = [_vp, C.c_int]
     L.lmpc_rollout_set_state.argtypes = [_vp, _vp, _vp]
     L.lmpc_rollout_get_state.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.lmpc_rollout_step.argtypes = [_vp, C.c_int, _vp, C.c_ulonglong]
+    L.lmpc_rollout_get_health.argtypes = [_vp, _vp, _vp]
     L.lmpc_rollout_get_lap.argtypes = [_vp, C.c_int, ip, _vp, _vp]
     L.lmpc_rollout_commit_lap.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+    L.lmpc_rollout_commit_laps.argtypes = [_vp, _vp, _vp, _vp]
     L.lmpc_rollout_export_laps_dev.argtypes = [_vp, C.c_int, _vp, _vp]
+    L.lmpc_ss_export_laps_dev.argtypes = [_vp, _vp, C.c_int, _vp, _vp]
+    L.lmpc_ss_import_laps_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]
     L.lmpc_sizeof_params.restype = C.c_int
     L.lmpc_sizeof_model_params.restype = C.c_int
     assert L.lmpc_sizeof_params() == C.sizeof(Params), "lmpc_params ABI mismatch"

@@ -57,7 +57,9 @@ class BatchedController:
         self.LapTime = [[] for _ in range(self.B)]          # LMPC.LapTime
         self.ss_book = [_LapBook(max(self.ss_cap, 1)) for _ in range(self.B)]
         self.it = [0] * self.B
+        self.own_laps = [[] for _ in range(self.B)]         # lap numbers of the laps the instance drove itself
         self._sel_dirty = True
+        self._used_dirty = False
 
     def close(self):
         if getattr(self, "_h", None):
@@ -81,7 +83,7 @@ class BatchedController:
         slot = self._model_slot_for(inst, x.shape[0])
         if slot >= 0:
             nat.check(self._lib.lmpc_model_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u)))
-        self._push_used(inst)
+        self._used_dirty = True          # usedIt is pushed once, before the next kernel that reads it
 
     def _model_slot_for(self, inst, T):
         """Ordering rule of PredictiveModel.py:35-46 for a new lap of T rows; returns the device slot or -1 when the lap
@@ -104,6 +106,7 @@ class BatchedController:
         return -1
 
     def _push_used(self, inst=None):
+        self._used_dirty = False
         used = np.zeros((self.B, self.trToUse), np.int32)
         for b in range(self.B):
             laps = self.model_laps[b]
@@ -133,6 +136,7 @@ class BatchedController:
         """LMPC.addTrajectory bookkeeping (PC.py:425-428): new lap number = it; keep the numSS_it fastest + lap it-1."""
         lapno = self.it[inst]
         self.LapTime[inst].append(int(lap_time))
+        self.own_laps[inst].append(lapno)
         book = self.ss_book[inst]
         if not book.free:
             order = list(np.argsort(np.array(self.LapTime[inst]), kind="stable"))
@@ -142,6 +146,13 @@ class BatchedController:
                 raise RuntimeError("safe-set pool too small")
             book.drop(max(victims, key=lambda ln: self.LapTime[inst][ln]))
         return book.take(lapno)
+
+    def _flush(self):
+        """Push pending lap bookkeeping (usedIt, the numSS_it fastest laps) to the device before a kernel reads it."""
+        if self._used_dirty:
+            self._push_used()
+        if self.lmpc and self._sel_dirty:
+            self._push_selection()
 
     def _push_selection(self):
         nit = max(self.numSS_it, 1)
@@ -160,8 +171,7 @@ class BatchedController:
 
     def add_point(self, x, u):
         """PC.py:466-476 for all instances: x[B,6], u[B,2]."""
-        if self._sel_dirty:
-            self._push_selection()
+        self._flush()
         x = np.ascontiguousarray(np.asarray(x, float).reshape(self.B, 6))
         u = np.ascontiguousarray(np.asarray(u, float).reshape(self.B, 2))
         nat.check(self._lib.lmpc_ss_add_point(self._h, nat.ptr(x), nat.ptr(u)))
@@ -198,14 +208,14 @@ class BatchedController:
     # ------------------------------------------------------------------ kernels
     def identify(self):
         """K1 only: MPC.computeLTVdynamics (PC.py:140-145).  Returns abc[B,N,54], flags[B]."""
+        self._flush()
         abc = np.zeros((self.B, self.N, 54)); flags = np.zeros(self.B, np.int32)
         nat.check(self._lib.lmpc_identify_host(self._h, nat.ptr(abc), nat.ptr(flags)))
         return abc, flags
 
     def select(self, x0):
         """K2 only: LMPC.addTerminalComponents (PC.py:386-416)."""
-        if self._sel_dirty:
-            self._push_selection()
+        self._flush()
         B, M = self.B, self.M
         x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(B, 6))
         o = dict(SS_sel=np.zeros((B, 6, M)), Qfun_sel=np.zeros((B, M)), Succ_SS=np.zeros((B, 6, M)),
@@ -222,8 +232,7 @@ class BatchedController:
 
     def step(self, x0, out=None, want_ss=True):
         """One MPC.solve / LMPC.solve for every instance (PC.py:110-137)."""
-        if self.lmpc and self._sel_dirty:
-            self._push_selection()
+        self._flush()
         x0 = np.ascontiguousarray(np.asarray(x0, float).reshape(self.B, 6))
         o = out if out is not None else self.alloc_step_outputs()
         nat.check(self._lib.lmpc_step_host(self._h, 1 if self.lmpc else 0, nat.ptr(x0), nat.ptr(o["xPred"]), nat.ptr(o["uPred"]),
@@ -233,9 +242,21 @@ class BatchedController:
         return o
 
     def step_dev(self, x0_dev):
-        if self.lmpc and self._sel_dirty:
-            self._push_selection()
+        self._flush()
         nat.check(self._lib.lmpc_step_dev(self._h, 1 if self.lmpc else 0, nat.ptr(x0_dev)))
+
+    def read_buffer(self, name, inst, shape, dtype=np.float64):
+        """Inspection: the slice of instance `inst` of a per-instance device buffer ("abc", "SS_sel", "Qfun_sel", ...)."""
+        out = np.zeros(shape, dtype)
+        nat.check(self._lib.lmpc_read_buffer(self._h, name.encode(), int(inst) * out.nbytes, nat.ptr(out), out.nbytes))
+        return out
+
+    def step_results(self):
+        """status, iters, resid[B,3], flags of the most recent step_dev / rollout_step."""
+        o = dict(status=np.zeros(self.B, np.int32), iters=np.zeros(self.B, np.int32), resid=np.zeros((self.B, 3)),
+                 flags=np.zeros(self.B, np.int32))
+        nat.check(self._lib.lmpc_step_results(self._h, nat.ptr(o["status"]), nat.ptr(o["iters"]), nat.ptr(o["resid"]), nat.ptr(o["flags"])))
+        return o
 
     # ------------------------------------------------------------------ device-resident closed loop
     def enable_rollout(self, Tcl=512):
@@ -255,8 +276,7 @@ class BatchedController:
     def rollout_step(self, z=None, seed=0):
         """Simulator.sim loop body (SysModel.py:34-48) for every instance on the device.  z[B,3]: standard-normal draws for
         the process noise (reference order vx, vy, wz); None = Philox on the device."""
-        if self.lmpc and self._sel_dirty:
-            self._push_selection()
+        self._flush()
         zz = None if z is None else np.ascontiguousarray(np.asarray(z, float).reshape(self.B, 3))
         nat.check(self._lib.lmpc_rollout_step(self._h, 1 if self.lmpc else 0, nat.ptr(zz), int(seed)))
 
@@ -264,6 +284,12 @@ class BatchedController:
         d = np.zeros(self.B, np.int32); n = np.zeros(self.B, np.int32)
         nat.check(self._lib.lmpc_rollout_get_state(self._h, None, None, nat.ptr(d), nat.ptr(n)))
         return d, n
+
+    def rollout_health(self):
+        """(OR of the step flags, number of steps whose QP was not reported solved) per instance since enable_rollout."""
+        f = np.zeros(self.B, np.int32); n = np.zeros(self.B, np.int32)
+        nat.check(self._lib.lmpc_rollout_get_health(self._h, nat.ptr(f), nat.ptr(n)))
+        return f, n
 
     def rollout_get_lap(self, inst):
         T = C.c_int(0)
@@ -275,22 +301,81 @@ class BatchedController:
         """main.py:113-119 for every instance whose lap just ended: lmpc.addTrajectory + predictiveModel.addTrajectory of the
         lap recorded on the device (no host copy of the lap), then the next lap starts from xF (SysModel.py:50)."""
         finished = np.nonzero(done)[0]
+        if not len(finished):
+            return finished
+        fin = np.zeros(self.B, np.int32); ss_slots = np.full(self.B, -1, np.int32); m_slots = np.full(self.B, -1, np.int32)
         for b in finished:
             T = int(cl_len[b])
-            ss_slot = self._ss_slot_for(b, T) if self.lmpc else -1
-            m_slot = self._model_slot_for(b, T) if to_model else -1
-            nat.check(self._lib.lmpc_rollout_commit_lap(self._h, int(b), int(ss_slot), int(m_slot)))
+            fin[b] = 1
+            ss_slots[b] = self._ss_slot_for(b, T) if self.lmpc else -1
+            m_slots[b] = self._model_slot_for(b, T) if to_model else -1
             if self.lmpc:
                 self.it[b] += 1
+        nat.check(self._lib.lmpc_rollout_commit_laps(self._h, nat.ptr(fin), nat.ptr(ss_slots), nat.ptr(m_slots)))
         if len(finished):
             self._sel_dirty = True
             if to_model:
-                self._push_used()
+                self._used_dirty = True
         return finished
 
     def rollout_export_laps(self, Tpad, rows_dev, lens_dev):
         """Pack the closed-loop records into caller-owned device tensors rows[B,Tpad,8], lens[B] (int32)."""
         nat.check(self._lib.lmpc_rollout_export_laps_dev(self._h, int(Tpad), nat.ptr(rows_dev), nat.ptr(lens_dev)))
+
+    # ------------------------------------------------------------------ pooled-safe-set exchange (SURVEY §8e)
+    def own_lap_number(self, inst, j):
+        """Current lap number of the j-th lap the instance drove itself (imported laps shift later numbers)."""
+        return self.own_laps[inst][j]
+
+    def export_laps(self, lapnos, Tpad, rows_dev, lens_dev):
+        """Pack stored lap ``lapnos[b]`` (-1 or not stored: none) of every instance into caller-owned device tensors
+        rows[B,Tpad,9] = (x | u | Qfun), lens[B] (int32): the send buffer of the per-lap all-gather."""
+        slots = np.full(self.B, -1, np.int32)
+        for b in range(self.B):
+            slots[b] = self.ss_book[b].slot_of.get(int(lapnos[b]), -1)
+        nat.check(self._lib.lmpc_ss_export_laps_dev(self._h, nat.ptr(slots), int(Tpad), nat.ptr(rows_dev), nat.ptr(lens_dev)))
+
+    def import_laps(self, src, lap_times, Tpad, rows_dev, lens_dev, to_model=True):
+        """Give instance b the gathered lap ``src[b]`` (index into rows[n_src,Tpad,9]; -1: nothing) as a lap driven BEFORE its
+        own most recent one: LMPC.addTrajectory + PredictiveModel.addTrajectory (main.py:117-119) of a lap another controller
+        drove.  The lap keeps its own Qfun and lap time ``lap_times[b]``; the instance's latest lap stays lap it-1 (the one
+        LMPC.addPoint extends, PC.py:466-476).  An instance for which the lap would not be among its numSS_it fastest is
+        skipped.  Returns the instances that took a lap."""
+        src = np.asarray(src, np.int32).reshape(self.B)
+        n_src = int(lens_dev.shape[0])
+        ss_slots = np.full(self.B, -1, np.int32); m_slots = np.full(self.B, -1, np.int32); use = np.full(self.B, -1, np.int32)
+        for b in range(self.B):
+            if src[b] < 0 or self.it[b] < 1:
+                continue
+            lt, last = int(lap_times[b]), self.it[b] - 1
+            times = self.LapTime[b][:last] + [lt] + self.LapTime[b][last:]
+            order = list(np.argsort(np.array(times), kind="stable"))[:self.numSS_it]
+            if last not in order:
+                continue                                  # never selected (PC.py:395) -> not stored
+            book = self.ss_book[b]
+            self.LapTime[b] = times
+            if last in book.slot_of:                      # own latest lap moves up one lap number
+                book.slot_of[last + 1] = book.slot_of.pop(last)
+            if self.own_laps[b] and self.own_laps[b][-1] == last:
+                self.own_laps[b][-1] = last + 1
+            if not book.free:
+                keep = set(order) | {last, last + 1}
+                victims = [ln for ln in book.slot_of if ln not in keep]
+                if not victims:
+                    raise RuntimeError("safe-set pool too small")
+                book.drop(max(victims, key=lambda ln: times[ln]))
+            ss_slots[b] = book.take(last)
+            self.it[b] += 1
+            use[b] = src[b]
+            if to_model:
+                m_slots[b] = self._model_slot_for(b, lt)
+        took = np.nonzero(use >= 0)[0]
+        if len(took):
+            nat.check(self._lib.lmpc_ss_import_laps_dev(self._h, nat.ptr(ss_slots), nat.ptr(m_slots) if to_model else None,
+                                                        nat.ptr(use), n_src, int(Tpad), nat.ptr(rows_dev), nat.ptr(lens_dev)))
+            self._sel_dirty = True
+            self._used_dirty = self._used_dirty or to_model
+        return took
 
     def device_buffer(self, name):
         return int(self._lib.lmpc_device_buffer(self._h, name.encode()) or 0)

@@ -165,6 +165,7 @@ struct Regs {
 
 constexpr double CENTRALITY_GAMMA = 0.01;
 constexpr int LATE_ACCEPT_IT = 20;
+constexpr int RECENTRE_AFTER = 3;   // step reductions before the corrector is replaced by a centring step
 
 struct SolveInfo {
     int status, iters;
@@ -885,100 +886,118 @@ struct Pdip {
             sig = sig * sig * sig;
             const double sm = sig * mu;
 
-            // ---- corrector right-hand sides --------------------------------------------------------
-            FOR_SLOTS(r, row, R1) {
-                double rc1 = g.w1[r] * g.nu1[r] + g.p1[r] - sm;
-                double rc3 = g.s[r] * g.nu3[r] + g.p3[r] - sm;
-                double d3 = g.nu3[r] * g.is_[r];
-                double e1 = -rc1 * g.iw1[r];
-                w.ex[row] = (e1 * (c.qs2 + d3) + g.d1[r] * (g.rs[r] + rc3 * g.is_[r])) * g.ihs[r];
-                g.p1[r] = rc1;   // keep rc for the final recovery
-                g.p3[r] = rc3;
-            }
-            FOR_SLOTS(r, row, R2) {
-                double rc2 = g.w2[r] * g.nu2[r] + g.p2[r] - sm;
-                w.eu[row] = -rc2 * g.iw2[r];
-                g.p2[r] = rc2;
-            }
-            if (LMPC) {
-                FOR_SLOTS(r, row, R4) {
-                    double rc4 = g.lam[r] * g.nu4[r] + g.p4[r] - sm;
-                    g.rho[r] = -g.rl[r] - rc4 * g.ilam[r];
-                    g.p4[r] = rc4;
-                }
-                terminal_rhs(w, g, -rone, c1, beta);
-            }
-            wsync();
-            backward_start<false>(w, c, c1);
-            backward_rhs(w, c);
-            forward(w);
-            if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
-
-            // ---- step length and update ----------------------------------------------------------
-            rn = 0.0;
-            rd = 1.0;
+            // ---- corrector (pass 0), recentring (pass 1, rare) -----------------------------------------
+            // Pass 0 is Mehrotra's corrector.  If its step cannot be brought back into the central-path neighbourhood within
+            // RECENTRE_AFTER reductions, the iterate sits on the neighbourhood boundary and an aggressive sigma would only allow
+            // tiny steps from now on (0.002 % of closed-loop LMPC steps stalled like that): pass 1 re-uses the factorisation
+            // for a pure centring direction (sigma = 1, no second-order term) instead.
+            double al = 0.0;
             double ds_[NSLOT(R1)], dw1_[NSLOT(R1)], dn1_[NSLOT(R1)], dn3_[NSLOT(R1)], dw2_[NSLOT(R2)], dn2_[NSLOT(R2)], dn4_[NSLOT(R4)];
-            FOR_SLOTS(r, row, R1) {
-                int k = row / NCX, i = row % NCX;
-                double fdx = dot6(&c.Fx[i * 6], &w.dx[k * 6]);
-                double rc1 = g.p1[r], rc3 = g.p3[r];
-                double gs = -g.rs[r] - rc1 * g.iw1[r] - rc3 * g.is_[r];
-                double ds = (gs + g.d1[r] * fdx) * g.ihs[r];
-                double dw1 = -fdx + ds;
-                double dn1 = (-rc1 - g.nu1[r] * dw1) * g.iw1[r];
-                double dn3 = (-rc3 - g.nu3[r] * ds) * g.is_[r];
-                ratio_update(g.w1[r], dw1, rn, rd);
-                ratio_update(g.s[r], ds, rn, rd);
-                ratio_update(g.nu1[r], dn1, rn, rd);
-                ratio_update(g.nu3[r], dn3, rn, rd);
-                ds_[r] = ds; dw1_[r] = dw1; dn1_[r] = dn1; dn3_[r] = dn3;
-            }
-            FOR_SLOTS(r, row, R2) {
-                int k = row / NCU, j = row % NCU;
-                double dw2 = -(c.Fu[j * 2] * w.du[k * 2] + c.Fu[j * 2 + 1] * w.du[k * 2 + 1]);
-                double dn2 = (-g.p2[r] - g.nu2[r] * dw2) * g.iw2[r];
-                ratio_update(g.w2[r], dw2, rn, rd);
-                ratio_update(g.nu2[r], dn2, rn, rd);
-                dw2_[r] = dw2; dn2_[r] = dn2;
-            }
-            if (LMPC) {
-                FOR_SLOTS(r, row, R4) {
-                    double dn4 = (-g.p4[r] - g.nu4[r] * g.dlam[r]) * g.ilam[r];
-                    ratio_update(g.lam[r], g.dlam[r], rn, rd);
-                    ratio_update(g.nu4[r], dn4, rn, rd);
-                    dn4_[r] = dn4;
-                }
-            }
-            const double amax = wmin(ratio_bound(rn, rd, 1e300));
-            double al = fmin(1.0, 0.995 * amax);
-            if (!(al > 0.0) || !(al <= 1.0)) { status = ST_NUMERICAL; break; }
-            // Stay in a wide neighbourhood of the central path, min_i w_i nu_i >= gamma * mean: without it
-            // Mehrotra steps can 2-cycle against a blocking bound (seen on 3 of 4096 workload QPs).
-            for (int tries = 0; tries < 12; ++tries) {
-                double pmin = 1e300, psum = 0.0;
+            bool bad_step = false;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const double tgt = pass ? mu : sm;      // complementarity target
+                const double so = pass ? 0.0 : 1.0;     // second-order (dw*dnu) term on/off
                 FOR_SLOTS(r, row, R1) {
-                    double a1 = (g.w1[r] + al * dw1_[r]) * (g.nu1[r] + al * dn1_[r]);
-                    double a3 = (g.s[r] + al * ds_[r]) * (g.nu3[r] + al * dn3_[r]);
-                    pmin = fmin(pmin, fmin(a1, a3));
-                    psum += a1 + a3;
+                    double rc1 = g.w1[r] * g.nu1[r] + so * g.p1[r] - tgt;
+                    double rc3 = g.s[r] * g.nu3[r] + so * g.p3[r] - tgt;
+                    double d3 = g.nu3[r] * g.is_[r];
+                    double e1 = -rc1 * g.iw1[r];
+                    w.ex[row] = (e1 * (c.qs2 + d3) + g.d1[r] * (g.rs[r] + rc3 * g.is_[r])) * g.ihs[r];
+                    g.p1[r] = rc1;   // keep rc for the final recovery
+                    g.p3[r] = rc3;
                 }
                 FOR_SLOTS(r, row, R2) {
-                    double a2 = (g.w2[r] + al * dw2_[r]) * (g.nu2[r] + al * dn2_[r]);
-                    pmin = fmin(pmin, a2);
-                    psum += a2;
+                    double rc2 = g.w2[r] * g.nu2[r] + so * g.p2[r] - tgt;
+                    w.eu[row] = -rc2 * g.iw2[r];
+                    g.p2[r] = rc2;
                 }
                 if (LMPC) {
                     FOR_SLOTS(r, row, R4) {
-                        double a4 = (g.lam[r] + al * g.dlam[r]) * (g.nu4[r] + al * dn4_[r]);
-                        pmin = fmin(pmin, a4);
-                        psum += a4;
+                        double rc4 = g.lam[r] * g.nu4[r] + so * g.p4[r] - tgt;
+                        g.rho[r] = -g.rl[r] - rc4 * g.ilam[r];
+                        g.p4[r] = rc4;
+                    }
+                    terminal_rhs(w, g, -rone, c1, beta);
+                }
+                wsync();
+                backward_start<false>(w, c, c1);
+                backward_rhs(w, c);
+                forward(w);
+                if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
+
+                // ---- step length ---------------------------------------------------------------------
+                rn = 0.0;
+                rd = 1.0;
+                FOR_SLOTS(r, row, R1) {
+                    int k = row / NCX, i = row % NCX;
+                    double fdx = dot6(&c.Fx[i * 6], &w.dx[k * 6]);
+                    double rc1 = g.p1[r], rc3 = g.p3[r];
+                    double gs = -g.rs[r] - rc1 * g.iw1[r] - rc3 * g.is_[r];
+                    double ds = (gs + g.d1[r] * fdx) * g.ihs[r];
+                    double dw1 = -fdx + ds;
+                    double dn1 = (-rc1 - g.nu1[r] * dw1) * g.iw1[r];
+                    double dn3 = (-rc3 - g.nu3[r] * ds) * g.is_[r];
+                    ratio_update(g.w1[r], dw1, rn, rd);
+                    ratio_update(g.s[r], ds, rn, rd);
+                    ratio_update(g.nu1[r], dn1, rn, rd);
+                    ratio_update(g.nu3[r], dn3, rn, rd);
+                    ds_[r] = ds; dw1_[r] = dw1; dn1_[r] = dn1; dn3_[r] = dn3;
+                }
+                FOR_SLOTS(r, row, R2) {
+                    int k = row / NCU, j = row % NCU;
+                    double dw2 = -(c.Fu[j * 2] * w.du[k * 2] + c.Fu[j * 2 + 1] * w.du[k * 2 + 1]);
+                    double dn2 = (-g.p2[r] - g.nu2[r] * dw2) * g.iw2[r];
+                    ratio_update(g.w2[r], dw2, rn, rd);
+                    ratio_update(g.nu2[r], dn2, rn, rd);
+                    dw2_[r] = dw2; dn2_[r] = dn2;
+                }
+                if (LMPC) {
+                    FOR_SLOTS(r, row, R4) {
+                        double dn4 = (-g.p4[r] - g.nu4[r] * g.dlam[r]) * g.ilam[r];
+                        ratio_update(g.lam[r], g.dlam[r], rn, rd);
+                        ratio_update(g.nu4[r], dn4, rn, rd);
+                        dn4_[r] = dn4;
                     }
                 }
-                pmin = wmin(pmin);
-                psum = wsum(psum);
-                if (pmin >= CENTRALITY_GAMMA * psum / n_ineq) break;
-                al *= 0.8;
+                const double amax = wmin(ratio_bound(rn, rd, 1e300));
+                al = fmin(1.0, 0.995 * amax);
+                if (!(al > 0.0) || !(al <= 1.0)) { bad_step = true; break; }
+                // Stay in a wide neighbourhood of the central path, min_i w_i nu_i >= gamma * mean: without it
+                // Mehrotra steps can 2-cycle against a blocking bound (seen on 3 of 4096 workload QPs).
+                bool inside = false;
+                for (int tries = 0; tries < 12; ++tries) {
+                    double pmin = 1e300, psum = 0.0;
+                    FOR_SLOTS(r, row, R1) {
+                        double a1 = (g.w1[r] + al * dw1_[r]) * (g.nu1[r] + al * dn1_[r]);
+                        double a3 = (g.s[r] + al * ds_[r]) * (g.nu3[r] + al * dn3_[r]);
+                        pmin = fmin(pmin, fmin(a1, a3));
+                        psum += a1 + a3;
+                    }
+                    FOR_SLOTS(r, row, R2) {
+                        double a2 = (g.w2[r] + al * dw2_[r]) * (g.nu2[r] + al * dn2_[r]);
+                        pmin = fmin(pmin, a2);
+                        psum += a2;
+                    }
+                    if (LMPC) {
+                        FOR_SLOTS(r, row, R4) {
+                            double a4 = (g.lam[r] + al * g.dlam[r]) * (g.nu4[r] + al * dn4_[r]);
+                            pmin = fmin(pmin, a4);
+                            psum += a4;
+                        }
+                    }
+                    pmin = wmin(pmin);
+                    psum = wsum(psum);
+                    if (pmin >= CENTRALITY_GAMMA * psum / n_ineq) { inside = true; break; }
+                    if (pass == 0 && tries >= RECENTRE_AFTER) break;
+                    al *= 0.8;
+                }
+                if (inside) break;
             }
+            if (bad_step) { status = ST_NUMERICAL; break; }
+#if defined(LMPC_HOST_TRACE) && !defined(__CUDA_ARCH__)
+            printf("it %2d rp %.2e rd %.2e mu %.2e a_aff %.4f sig %.2e al %.4e\n", it, r_prim, r_dual, mu, a_aff, sig, al);
+#endif
             FOR_SLOTS(r, row, R1) {
                 g.s[r] += al * ds_[r];
                 g.nu1[r] += al * dn1_[r];

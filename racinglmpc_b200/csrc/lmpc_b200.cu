@@ -181,7 +181,7 @@ struct lmpc_handle {
     bool has_store;
     ModelConst mc;
     LapPool ss, mdl;
-    int *d_used, *d_sel, *d_isprev, *d_prevslot, *d_timeStep, *d_hasPred, *d_flags, *d_minidx;
+    int *d_used, *d_sel, *d_isprev, *d_prevslot, *d_timeStep, *d_hasPred, *d_flags, *d_minidx, *d_xchg, *d_health;
     double *d_xLin, *d_uLin, *d_ztState, *d_ztFixed, *d_OldInput, *d_xPredPrev, *d_tmpx, *d_tmpu;
     // device-resident closed loop (lmpc_rollout_create)
     bool has_rollout;
@@ -316,13 +316,13 @@ int lmpc_destroy(lmpc_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->has_rollout) {
-        void* rp[] = {h->d_rx[0], h->d_rx[1], h->d_rg[0], h->d_rg[1], h->d_clx, h->d_clu, h->d_z, h->d_cllen, h->d_done};
+        void* rp[] = {h->d_rx[0], h->d_rx[1], h->d_rg[0], h->d_rg[1], h->d_clx, h->d_clu, h->d_z, h->d_cllen, h->d_done, h->d_health};
         for (void* q : rp) cudaFree(q);
     }
     if (h->has_store) {
         void* ptrs[] = {h->ss.x, h->ss.u, h->ss.q, h->ss.len, h->mdl.x, h->mdl.u, h->mdl.len, h->d_used, h->d_sel, h->d_isprev,
                         h->d_prevslot, h->d_timeStep, h->d_hasPred, h->d_flags, h->d_minidx, h->d_xLin, h->d_uLin, h->d_ztState,
-                        h->d_ztFixed, h->d_OldInput, h->d_xPredPrev, h->d_tmpx, h->d_tmpu};
+                        h->d_ztFixed, h->d_OldInput, h->d_xPredPrev, h->d_tmpx, h->d_tmpu, h->d_xchg};
         for (void* q : ptrs) cudaFree(q);
     }
     double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
@@ -489,7 +489,7 @@ int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, i
     DA(h->d_timeStep, int, B); DA(h->d_hasPred, int, B); DA(h->d_flags, int, B); DA(h->d_minidx, int, B * 8);
     DA(h->d_xLin, double, B * (N + 1) * 6); DA(h->d_uLin, double, B * N * 2); DA(h->d_ztState, double, B * 6);
     DA(h->d_ztFixed, double, B * 6); DA(h->d_OldInput, double, B * 2); DA(h->d_xPredPrev, double, B * (N + 1) * 6);
-    DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2);
+    DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2); DA(h->d_xchg, int, B * 3);
 #undef DA
     CK(cudaMemsetAsync(h->ss.len, 0, sizeof(int) * B * h->ss.cap, h->stream));
     CK(cudaMemsetAsync(h->mdl.len, 0, sizeof(int) * B * model_cap, h->stream));
@@ -553,7 +553,7 @@ int lmpc_ss_put_lap(lmpc_handle* h, int inst, int slot, int T, const double* x, 
     if (qfun) {
         CK(cudaMemcpyAsync(h->ss.q + lap * h->ss.Tmax, qfun, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
     } else {
-        rollout_cost_kernel<<<1, 32, 0, h->stream>>>(h->ss, inst, slot, h->mc.TrackLength);
+        rollout_cost_kernel<<<1, 256, 0, h->stream>>>(h->ss, inst, slot, h->mc.TrackLength);
         CK(cudaGetLastError());
         h->launches += 1;
     }
@@ -776,6 +776,29 @@ int lmpc_step_host(lmpc_handle* h, int mode, const double* x0, double* xPred, do
     return LMPC_OK;
 }
 
+int lmpc_read_buffer(lmpc_handle* h, const char* name, size_t offset_bytes, void* dst, size_t bytes) {
+    if (!h || !name || !dst) return fail(LMPC_E_INVALID, "null argument");
+    const char* p = (const char*)lmpc_device_buffer(h, name);
+    if (!p) return fail(LMPC_E_INVALID, "unknown buffer name");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, p + offset_bytes, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+int lmpc_step_results(lmpc_handle* h, int* status, int* iters, double* resid, int* flags) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch;
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (resid) CK(cudaMemcpyAsync(resid, h->d_resid, sizeof(double) * B * 3, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, h->d_flags, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
 void* lmpc_device_buffer(lmpc_handle* h, const char* name) {
     if (!h || !name) return nullptr;
     struct { const char* n; void* p; } tab[] = {
@@ -806,6 +829,8 @@ int lmpc_rollout_create(lmpc_handle* h, int Tcl) {
     CK(cudaMalloc((void**)&h->d_z, sizeof(double) * B * 3));
     CK(cudaMalloc((void**)&h->d_cllen, sizeof(int) * B));
     CK(cudaMalloc((void**)&h->d_done, sizeof(int) * B));
+    CK(cudaMalloc((void**)&h->d_health, sizeof(int) * B * 2));
+    CK(cudaMemsetAsync(h->d_health, 0, sizeof(int) * B * 2, h->stream));
     CK(cudaMemsetAsync(h->d_cllen, 0, sizeof(int) * B, h->stream));
     CK(cudaMemsetAsync(h->d_done, 0, sizeof(int) * B, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -843,6 +868,17 @@ int lmpc_rollout_get_state(lmpc_handle* h, double* x, double* xglob, int* done, 
     return LMPC_OK;
 }
 
+int lmpc_rollout_get_health(lmpc_handle* h, int* flags_or, int* unsolved_steps) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch;
+    if (flags_or) CK(cudaMemcpyAsync(flags_or, h->d_health, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (unsolved_steps) CK(cudaMemcpyAsync(unsolved_steps, h->d_health + B, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
 // One closed-loop step for every instance, all on the device (SysModel.py:34-48):
 //   Controller.solve(x) -> u = uPred[0] -> Controller.addPoint(x, u) (LMPC) -> x+ = dynModel(x, x_glob, u); done = s+ > TrackLength
 int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned long long seed) {
@@ -864,6 +900,7 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
     sa.z = z_host ? h->d_z : nullptr; sa.seed = seed; sa.step = h->sim_step;
     sa.xn = h->d_rx[h->cur ^ 1]; sa.xgn = h->d_rg[h->cur ^ 1];
     sa.cl_x = h->d_clx; sa.cl_u = h->d_clu; sa.cl_len = h->d_cllen; sa.Tcl = h->Tcl; sa.done = h->d_done; sa.active = nullptr;
+    sa.flags = h->d_flags; sa.status = h->d_status; sa.health = h->d_health;
     sim_step_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->mc, sa);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -895,7 +932,7 @@ int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slo
     CK(cudaSetDevice(h->device));
     if (ss_slot >= 0) {
         commit_lap_kernel<<<1, 256, 0, h->stream>>>(h->ss, inst, ss_slot, h->d_clx, h->d_clu, h->d_cllen, h->Tcl);
-        rollout_cost_kernel<<<1, 32, 0, h->stream>>>(h->ss, inst, ss_slot, h->mc.TrackLength);
+        rollout_cost_kernel<<<1, 256, 0, h->stream>>>(h->ss, inst, ss_slot, h->mc.TrackLength);
         h->launches += 2;
     }
     if (model_slot >= 0) {
@@ -917,6 +954,28 @@ int lmpc_rollout_commit_lap(lmpc_handle* h, int inst, int ss_slot, int model_slo
     return LMPC_OK;
 }
 
+// The same hand-over for every instance with fin[b] != 0 in ONE launch (a Monte-Carlo batch finishes hundreds of laps in
+// the same step).
+int lmpc_rollout_commit_laps(lmpc_handle* h, const int* fin, const int* ss_slots, const int* model_slots) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (!fin || !ss_slots || !model_slots) return fail(LMPC_E_INVALID, "null argument");
+    for (int b = 0; b < h->batch; ++b)
+        if (fin[b] && (ss_slots[b] >= h->ss.cap || model_slots[b] >= h->mdl.cap)) return fail(LMPC_E_INVALID, "slot out of range");
+    const size_t B = h->batch;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_xchg, fin, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_xchg + B, ss_slots, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_xchg + 2 * B, model_slots, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    commit_laps_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, h->d_xchg, h->d_xchg + B, h->d_xchg + 2 * B, h->d_clx,
+                                                        h->d_clu, h->d_cllen, h->Tcl, h->d_rx[h->cur], h->d_timeStep, h->d_done,
+                                                        h->mc.TrackLength);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaStreamSynchronize(h->stream));   // the three host arrays are pageable memory of the caller
+    return LMPC_OK;
+}
+
 int lmpc_rollout_export_laps_dev(lmpc_handle* h, int Tpad, double* rows_dev, int* lens_dev) {
     int rc = need_rollout(h);
     if (rc) return rc;
@@ -925,6 +984,43 @@ int lmpc_rollout_export_laps_dev(lmpc_handle* h, int Tpad, double* rows_dev, int
     export_laps_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->d_clx, h->d_clu, h->d_cllen, h->Tcl, Tpad, rows_dev, lens_dev);
     CK(cudaGetLastError());
     h->launches += 1;
+    return LMPC_OK;
+}
+
+int lmpc_ss_export_laps_dev(lmpc_handle* h, const int* slots, int Tpad, double* rows_dev, int* lens_dev) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!slots || !rows_dev || !lens_dev || Tpad < 1) return fail(LMPC_E_INVALID, "bad export arguments");
+    for (int b = 0; b < h->batch; ++b)
+        if (slots[b] >= h->ss.cap) return fail(LMPC_E_INVALID, "safe-set slot out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_xchg, slots, sizeof(int) * h->batch, cudaMemcpyHostToDevice, h->stream));
+    ss_export_laps_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->d_xchg, Tpad, rows_dev, lens_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaStreamSynchronize(h->stream));   // `slots` is pageable host memory of the caller
+    return LMPC_OK;
+}
+
+int lmpc_ss_import_laps_dev(lmpc_handle* h, const int* ss_slots, const int* model_slots, const int* src, int n_src, int Tpad,
+                            const double* rows_dev, const int* lens_dev) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!ss_slots || !src || !rows_dev || !lens_dev || Tpad < 1 || n_src < 1) return fail(LMPC_E_INVALID, "bad import arguments");
+    for (int b = 0; b < h->batch; ++b) {
+        if (ss_slots[b] >= h->ss.cap || (model_slots && model_slots[b] >= h->mdl.cap)) return fail(LMPC_E_INVALID, "slot out of range");
+        if (src[b] >= n_src) return fail(LMPC_E_INVALID, "source lap index out of range");
+    }
+    const size_t B = h->batch;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_xchg, ss_slots, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_xchg + B, src, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    if (model_slots) CK(cudaMemcpyAsync(h->d_xchg + 2 * B, model_slots, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    ss_import_laps_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, h->d_xchg, model_slots ? h->d_xchg + 2 * B : nullptr,
+                                                           h->d_xchg + B, Tpad, rows_dev, lens_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaStreamSynchronize(h->stream));
     return LMPC_OK;
 }
 

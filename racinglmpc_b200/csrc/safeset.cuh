@@ -589,18 +589,132 @@ __global__ void export_laps_kernel(int batch, const double* cl_x, const double* 
     if (threadIdx.x == 0) lens[b] = T;
 }
 
-// LMPC.computeCost (PC.py:447-464) for one (instance, slot): backward count of steps to the finish line.
-__global__ void rollout_cost_kernel(LapPool pool, int b, int slot, double TrackLength) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const size_t lap = pool.lap_index(b, slot);
+// Pooled-safe-set exchange: pack one stored lap per instance, slot[b] (< 0: none), into
+// rows[B][Tpad][9] = (x 6 | u 2 | Qfun 1) + lens[B] -- the send buffer of the once-per-lap all-gather ...
+__global__ void ss_export_laps_kernel(int batch, LapPool pool, const int* slot, int Tpad, double* rows, int* lens) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int sl = slot[b];
+    const size_t lap = pool.lap_index(b, sl < 0 ? 0 : sl);
+    const int T = sl < 0 ? 0 : min(pool.len[lap], Tpad);
+    const double* X = pool.x + lap * pool.Tmax * 6;
+    const double* U = pool.u + lap * pool.Tmax * 2;
+    const double* Q = pool.q + lap * pool.Tmax;
+    for (int e = threadIdx.x; e < Tpad * 9; e += blockDim.x) {
+        const int t = e / 9, j = e - t * 9;
+        double v = 0.0;
+        if (t < T) v = (j < 6) ? X[t * 6 + j] : (j < 8 ? U[t * 2 + (j - 6)] : Q[t]);
+        rows[(size_t)b * Tpad * 9 + e] = v;
+    }
+    if (threadIdx.x == 0) lens[b] = T;
+}
+
+// ... and its receive side: instance b stores gathered lap src[b] (index into rows[G][Tpad][9], < 0: skip) in safe-set slot
+// ss_slot[b] and, when model_slot[b] >= 0, in the regression-model pool too (main.py:117-119 adds a lap to both).
+__global__ void ss_import_laps_kernel(int batch, LapPool ss, LapPool model, const int* ss_slot, const int* model_slot, const int* src,
+                                      int Tpad, const double* rows, const int* lens) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int g = src[b];
+    if (g < 0) return;
+    const double* R = rows + (size_t)g * Tpad * 9;
+    const int T = min(lens[g], min(Tpad, ss.Tmax));
+    if (ss_slot[b] >= 0) {
+        const size_t lap = ss.lap_index(b, ss_slot[b]);
+        for (int e = threadIdx.x; e < T * 9; e += blockDim.x) {
+            const int t = e / 9, j = e - t * 9;
+            const double v = R[e];
+            if (j < 6) ss.x[(lap * ss.Tmax + t) * 6 + j] = v;
+            else if (j < 8) ss.u[(lap * ss.Tmax + t) * 2 + (j - 6)] = v;
+            else ss.q[lap * ss.Tmax + t] = v;
+        }
+        if (threadIdx.x == 0) ss.len[lap] = T;
+    }
+    if (model_slot && model_slot[b] >= 0) {
+        // the model stores the lap as driven (rows up to the finish line, Qfun > 0 ... = 0), not the addPoint overrun
+        int Tm = 0;
+        for (int t = 0; t < T; ++t) { if (R[t * 9 + 8] >= 0.0) Tm = t + 1; }
+        Tm = min(Tm, model.Tmax);
+        const size_t lap = model.lap_index(b, model_slot[b]);
+        for (int e = threadIdx.x; e < Tm * 8; e += blockDim.x) {
+            const int t = e >> 3, j = e & 7;
+            const double v = R[t * 9 + j];
+            if (j < 6) model.x[(lap * model.Tmax + t) * 6 + j] = v;
+            else model.u[(lap * model.Tmax + t) * 2 + (j - 6)] = v;
+        }
+        if (threadIdx.x == 0) model.len[lap] = Tm;
+    }
+}
+
+// LMPC.computeCost (PC.py:447-464) for one stored lap, block-parallel: the reference counts backwards
+//   Q[T-1] = 0;  Q[j] = Q[j+1] + 1 if s_j < TrackLength else 0
+// i.e. Q[j] = (first row r >= j that is the last row or has s_r >= TrackLength) - j.  Chunks of blockDim rows are walked from
+// the end; inside a chunk the nearest such row is a suffix-minimum (Hillis-Steele in shared memory).  blockDim.x == 256.
+__device__ void lap_cost_block(const LapPool& pool, size_t lap, double TrackLength) {
+    __shared__ int nxt[256];
+    __shared__ int carry_s;
     const int T = pool.len[lap];
     const double* X = pool.x + lap * pool.Tmax * 6;
     double* Q = pool.q + lap * pool.Tmax;
-    for (int i = 0; i < T; ++i) {
-        const int j = T - 1 - i;
-        if (i == 0) Q[j] = 0.0;
-        else if (X[(size_t)j * 6 + 4] < TrackLength) Q[j] = Q[j + 1] + 1.0;
-        else Q[j] = 0.0;
+    if (threadIdx.x == 0) carry_s = 0x7fffffff;
+    __syncthreads();
+    for (int hi = T; hi > 0; hi -= 256) {
+        const int lo = max(hi - 256, 0);
+        const int j = lo + threadIdx.x;
+        int v = 0x7fffffff;
+        if (j < hi && (j == T - 1 || !(X[(size_t)j * 6 + 4] < TrackLength))) v = j;
+        nxt[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const int w = (threadIdx.x + o < 256) ? nxt[threadIdx.x + o] : 0x7fffffff;
+            __syncthreads();
+            if (w < nxt[threadIdx.x]) nxt[threadIdx.x] = w;
+            __syncthreads();
+        }
+        const int carry = carry_s;
+        const int r = min(nxt[threadIdx.x], carry);
+        if (j < hi) Q[j] = (double)(r - j);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = min(nxt[0], carry);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) rollout_cost_kernel(LapPool pool, int b, int slot, double TrackLength) {
+    lap_cost_block(pool, pool.lap_index(b, slot), TrackLength);
+}
+
+// Lap hand-over of every instance with fin[b] != 0, one CTA per instance (main.py:113-119 + SysModel.py:50 + PC.py:445):
+// the closed-loop record goes to safe-set slot ss_slot[b] (>= 0) with its cost-to-go and to regression slot model_slot[b]
+// (>= 0); then the record restarts, s -= TrackLength, timeStep = 0, done = 0.
+__global__ void __launch_bounds__(256) commit_laps_kernel(int batch, LapPool ss, LapPool model, const int* fin, const int* ss_slot,
+                                                          const int* model_slot, const double* cl_x, const double* cl_u, int* cl_len,
+                                                          int Tcl, double* x_cur, int* timeStep, int* done, double TrackLength) {
+    const int b = blockIdx.x;
+    if (b >= batch || !fin[b]) return;
+    const int Trec = cl_len[b];
+    if (ss_slot[b] >= 0) {
+        const int T = min(Trec, ss.Tmax);
+        const size_t lap = ss.lap_index(b, ss_slot[b]);
+        for (int e = threadIdx.x; e < T * 6; e += blockDim.x) ss.x[lap * ss.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
+        for (int e = threadIdx.x; e < T * 2; e += blockDim.x) ss.u[lap * ss.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
+        if (threadIdx.x == 0) ss.len[lap] = T;
+        __syncthreads();
+        lap_cost_block(ss, lap, TrackLength);
+    }
+    if (model_slot[b] >= 0) {
+        const int T = min(Trec, model.Tmax);
+        const size_t lap = model.lap_index(b, model_slot[b]);
+        for (int e = threadIdx.x; e < T * 6; e += blockDim.x) model.x[lap * model.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
+        for (int e = threadIdx.x; e < T * 2; e += blockDim.x) model.u[lap * model.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
+        if (threadIdx.x == 0) model.len[lap] = T;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cl_len[b] = 0;
+        x_cur[(size_t)b * 6 + 4] -= TrackLength;
+        timeStep[b] = 0;
+        done[b] = 0;
     }
 }
 
@@ -666,6 +780,9 @@ struct SimArgs {
     int Tcl;
     int* done;             // [B] 1 when s_next > TrackLength
     const int* active;     // [B] or nullptr: instances with active == 0 are left untouched
+    const int* flags;      // [B] step flags (K1/K2/addPoint) and QP status of the step that produced u, or nullptr;
+    const int* status;     //     accumulated into health[b] (OR of flags) and health[B + b] (steps with status != 1)
+    int* health;
 };
 
 }  // namespace lmpc
@@ -676,6 +793,10 @@ __global__ void sim_step_kernel(const __grid_constant__ ModelConst m, const SimA
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.batch) return;
     if (a.active && !a.active[b]) return;
+    if (a.health) {
+        if (a.flags && a.flags[b]) a.health[b] |= a.flags[b];
+        if (a.status && a.status[b] != 1) a.health[a.batch + b] += 1;
+    }
     // vehicle parameters, SysModel.py:61-70
     const double mass = 1.98, lf = 0.125, lr = 0.125, Iz = 0.024;
     const double Df = 0.8 * mass * 9.81 / 2.0, Cf = 1.25, Bf = 1.0;

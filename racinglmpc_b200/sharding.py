@@ -39,7 +39,7 @@ def allgather_laps(rows, lens, group=None):
     rows: tensor [n_local, Tmax, 8] (CUDA for NCCL, CPU for gloo), lens: int32 tensor [n_local];
     n_local must be equal on all ranks (pad with zero-length laps).  Returns (rows_all [world*n_local, Tmax, 8],
     lens_all [world*n_local]) in rank order, i.e. global instance order under `shard_range`."""
-    world = dist.get_world_size(group)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return rows, lens
     out_rows = torch.empty((world * rows.shape[0],) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
@@ -47,6 +47,16 @@ def allgather_laps(rows, lens, group=None):
     dist.all_gather_into_tensor(out_rows, rows.contiguous(), group=group)
     dist.all_gather_into_tensor(out_lens, lens.contiguous(), group=group)
     return out_rows, out_lens
+
+
+def allgather_vec(v, group=None):
+    """All-gather a 1-D tensor of equal length on every rank, in rank order."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return v
+    out = torch.empty(world * v.shape[0], dtype=v.dtype, device=v.device)
+    dist.all_gather_into_tensor(out, v.contiguous(), group=group)
+    return out
 
 
 def pooled_fastest(lens_all, k, valid_min=2):

@@ -277,3 +277,49 @@ def test_device_resident_closed_loop_matches_host_driven_loop(gold, track):
     xs_, us_, q_ = cb.get_lap(0, 5)
     assert np.array_equal(xs_, lapsB[1][0]) and q_[0] == lapsB[1][0].shape[0] - 1
     cb.close()
+
+
+def test_pooled_lap_exchange_export_import(track):
+    """SURVEY §8e pooled-safe-set mode: a stored lap packed on the device (send buffer of the all-gather) and handed to another
+    instance arrives bit-exact, sits BEFORE that instance's own latest lap (which stays the lap LMPC.addPoint extends), is ranked
+    by its lap time like any other lap (PC.py:395) and is skipped where it would never be selected."""
+    _need_gpu()
+    from racinglmpc_b200 import workloads
+    N, B, Tpad = 12, 4, 512
+    data = workloads.lmpc_batch(B)
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    c = BatchedController(par, B, track.seg_table(), track.TrackLength, trToUse=5, numSS_Points=numSS_Points,
+                          numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536, ss_cap=7, model_cap=7)
+    workloads.restore_lmpc_batch(c, data)
+    assert c.it == [4] * B
+    rows = torch.zeros(B, Tpad, 9, dtype=torch.float64, device="cuda")
+    lens = torch.zeros(B, dtype=torch.int32, device="cuda")
+    c.export_laps([1, 1, 1, -1], Tpad, rows, lens)
+    rows_h, lens_h = rows.cpu().numpy(), lens.cpu().numpy()
+    x1, u1, q1 = c.get_lap(0, 1)
+    T = x1.shape[0]
+    assert lens_h[0] == T and lens_h[3] == 0 and not rows_h[3].any()
+    assert np.array_equal(rows_h[0, :T, 0:6], x1) and np.array_equal(rows_h[0, :T, 6:8], u1) and np.array_equal(rows_h[0, :T, 8], q1)
+    assert not rows_h[0, T:].any()
+    own_latest = c.get_lap(2, 3)
+    # instance 2 gets instance 0's lap with a winning lap time, instance 3 with a hopeless one, 0 and 1 nothing
+    took = c.import_laps(np.array([-1, -1, 0, 0]), np.array([0, 0, 100, 100000]), Tpad, rows, lens)
+    assert list(took) == [2] and c.it == [4, 4, 5, 4]
+    xf, uf, qf = c.get_lap(2, 3)                     # the foreign lap took lap number it-1 (old) ...
+    assert np.array_equal(xf, x1) and np.array_equal(uf, u1) and np.array_equal(qf, q1)
+    xo, uo, qo = c.get_lap(2, 4)                     # ... and the own latest lap moved up
+    assert np.array_equal(xo, own_latest[0]) and np.array_equal(qo, own_latest[2])
+    assert c.own_lap_number(2, 3) == 4 and c.LapTime[2][3] == 100
+    # selection: the imported lap is the fastest -> its points fill the first numSS_Points/numSS_it columns (PC.py:402-407)
+    sel = c.select(data["x0"])
+    P = numSS_Points // numSS_it
+    for j in range(P):
+        col = sel["SS_sel"][2][:, j]
+        assert np.any(np.all(x1 == col[None, :], axis=1)), j
+    assert np.array_equal(sel["SS_sel"][0], c.select(data["x0"])["SS_sel"][0])
+    o = c.step(data["x0"])
+    assert np.all(o["status"] == 1) and np.all(o["flags"] == 0), (o["status"], o["flags"])
+    # addPoint still extends the instance's OWN latest lap
+    c.add_point(data["x0"], o["uPred"][:, 0])
+    assert c.get_lap(2, 4)[0].shape[0] == own_latest[0].shape[0] + 1 and c.get_lap(2, 3)[0].shape[0] == T
+    c.close()
