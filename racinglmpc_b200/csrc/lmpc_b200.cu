@@ -171,7 +171,7 @@ struct lmpc_handle {
     FtocpConst c;
     int batch, device, N, M;
     cudaStream_t stream;
-    cudaStream_t cstream[4];   // chunk pipeline of the *_host entry points (H2D | kernel | D2H overlap)
+    cudaStream_t cstream[8];   // chunk pipeline of the *_host entry points (H2D | kernel | D2H overlap)
     long long launches;
     // device buffers used by the *_host entry points
     double *d_x0, *d_uOld, *d_abc, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
@@ -298,7 +298,7 @@ int lmpc_create(const lmpc_params* p, int batch, int device, lmpc_handle** out) 
     if (rc != LMPC_OK) { delete h; return rc; }
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
     const size_t B = batch, N = p->N, M = p->numSS_Points > 0 ? p->numSS_Points : 1;
 #define DALLOC(ptr, count) CK(cudaMalloc((void**)&h->ptr, sizeof(*h->ptr) * (count)))
     DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54);
@@ -331,7 +331,7 @@ int lmpc_destroy(lmpc_handle* h) {
     cudaFree(h->d_status);
     cudaFree(h->d_iters);
     cudaStreamDestroy(h->stream);
-    for (int i = 0; i < 4; ++i) cudaStreamDestroy(h->cstream[i]);
+    for (int i = 0; i < 8; ++i) cudaStreamDestroy(h->cstream[i]);
     delete h;
     return LMPC_OK;
 }
@@ -402,7 +402,8 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
     }
     // Chunk pipeline: the batch is cut into up to four instance ranges, each on its own stream, so that the H2D copy
     // of range i+1, the solve of range i and the D2H copy of range i-1 overlap (PCIe is full duplex).
-    const int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    if (const char* e = getenv("LMPC_B200_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 8 && (size_t)v <= B) nchunk = v; }   // tuning knob
     for (int ci = 0; ci < nchunk; ++ci) {
         const size_t lo = B * ci / nchunk, hi = B * (ci + 1) / nchunk, nb = hi - lo;
         cudaStream_t s = h->cstream[ci];
