@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <new>
 
@@ -404,6 +406,13 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
     // of range i+1, the solve of range i and the D2H copy of range i-1 overlap (PCIe is full duplex).
     int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
     if (const char* e = getenv("LMPC_B200_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 8 && (size_t)v <= B) nchunk = v; }   // tuning knob
+    const bool trace = getenv("LMPC_B200_TRACE") != nullptr;
+    cudaEvent_t tev[8][3], t0ev;
+    if (trace) {
+        cudaEventCreate(&t0ev);
+        for (int i = 0; i < nchunk; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&tev[i][j]);
+        cudaEventRecord(t0ev, h->cstream[0]);
+    }
     for (int ci = 0; ci < nchunk; ++ci) {
         const size_t lo = B * ci / nchunk, hi = B * (ci + 1) / nchunk, nb = hi - lo;
         cudaStream_t s = h->cstream[ci];
@@ -429,8 +438,10 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
         a.slackT = (lm && slackTerminal) ? h->d_slackT + lo * 6 : nullptr;
         a.zt = (lm && zt) ? h->d_zt + lo * 6 : nullptr; a.ztu = (lm && zt_u) ? h->d_ztu + lo * 2 : nullptr;
         a.status = h->d_status + lo; a.iters = h->d_iters + lo; a.resid = h->d_resid + lo * 3;
+        if (trace) cudaEventRecord(tev[ci][0], s);
         int rc = launch(h, a, lm, s);
         if (rc != LMPC_OK) return rc;
+        if (trace) cudaEventRecord(tev[ci][1], s);
         CK(cudaMemcpyAsync(xPred + lo * (N + 1) * 6, h->d_xPred + lo * (N + 1) * 6, nb * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(uPred + lo * N * 2, h->d_uPred + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
         if (slack) CK(cudaMemcpyAsync(slack + lo * N * 2, h->d_slack + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
@@ -441,8 +452,18 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
         CK(cudaMemcpyAsync(status + lo, h->d_status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(iters + lo, h->d_iters + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(resid + lo * 3, h->d_resid + lo * 3, nb * 3 * D, cudaMemcpyDeviceToHost, s));
+        if (trace) cudaEventRecord(tev[ci][2], s);
     }
     for (int ci = 0; ci < nchunk; ++ci) CK(cudaStreamSynchronize(h->cstream[ci]));
+    if (trace) {
+        for (int i = 0; i < nchunk; ++i) {
+            float a_ = 0, b_ = 0, c_ = 0;
+            cudaEventElapsedTime(&a_, t0ev, tev[i][0]); cudaEventElapsedTime(&b_, t0ev, tev[i][1]); cudaEventElapsedTime(&c_, t0ev, tev[i][2]);
+            fprintf(stderr, "chunk %d: h2d done %.3f ms, kernel done %.3f, d2h done %.3f\n", i, a_, b_, c_);
+            for (int j = 0; j < 3; ++j) cudaEventDestroy(tev[i][j]);
+        }
+        cudaEventDestroy(t0ev);
+    }
     return LMPC_OK;
 }
 
