@@ -2,7 +2,7 @@
 """Small-batch run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
     compute-sanitizer --tool racecheck python tools/sanitize.py
 Exercises: ftocp_kernel<12,0> and <12,48> (host + device entry points), knn_ltv_regress, ss_select, shift_state,
-ss_add_point, rollout_cost, sim_step, commit_lap, export_laps."""
+ss_add_point, rollout_cost, sim_step, commit_laps, export_laps, ss_export_laps, ss_import_laps."""
 import os
 import sys
 import numpy as np
@@ -22,7 +22,7 @@ s.close()
 data = workloads.lmpc_batch(B)
 numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
 c = BatchedController(par, B, workloads.track_seg_table(), rp.TRACK_LENGTH, trToUse=5, numSS_Points=numSS_Points,
-                      numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1280, ss_cap=6, model_cap=6)
+                      numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1280, ss_cap=8, model_cap=7)
 workloads.restore_lmpc_batch(c, data)
 o = c.step(data["x0"])
 assert np.all(o["status"] == 1) and np.all(o["flags"] == 0)
@@ -37,5 +37,15 @@ rows = torch.zeros(B, 16, 8, dtype=torch.float64, device="cuda")
 lens = torch.zeros(B, dtype=torch.int32, device="cuda")
 c.rollout_export_laps(16, rows, lens)
 c.sync()
+# pooled-safe-set exchange: export a stored lap of every instance, hand instance 0's lap to the others
+rows9 = torch.zeros(B, 512, 9, dtype=torch.float64, device="cuda")
+c.export_laps([1] * B, 512, rows9, lens)
+took = c.import_laps(np.array([-1] + [0] * (B - 1)), np.full(B, 100), 512, rows9, lens)
+assert len(took) == B - 1
+o = c.step(data["x0"])
+# instance 0 was handed a fake 3-row lap above (flag 8: selection window past the lap end); all others must be clean
+assert np.all(o["status"][1:] == 1) and np.all(o["flags"][1:] == 0), (o["status"], o["flags"])
+f, n_uns = c.rollout_health()
+r = c.step_results()
 c.close()
 print("sanitize workload done")
