@@ -140,12 +140,21 @@ def cpu_model():
     return "unknown"
 
 
+def host_cores():
+    """Threads for the CPU arm: the cores this process may run on.  NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which would silently turn the reference arm into a single-core run."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
     from oracle import osqp_port
-    cores = osqp_port.max_threads()
+    cores = host_cores()
     nsample = 1024
     prob = oracle_problem_set(nsample)
     for _ in range(args.warmup):
@@ -298,8 +307,7 @@ def run_gpu(args):
                          "fp64_gflops": gflops, "algorithmic_bytes_per_solve": ALGO_BYTES_PER_SOLVE},
         }
         if not args.no_cpu_baseline:
-            from oracle import osqp_port
-            cores = osqp_port.max_threads()
+            cores = host_cores()
             nsample = 1024
             prob = oracle_problem_set(nsample)
             oracle_time(prob, cores)
