@@ -110,6 +110,20 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
                          const double* Qfun_sel, const double* Succ_SS, const double* Succ_uSS, double* xPred,
                          double* uPred, double* slack, double* lambd, double* slackTerminal, double* zt,
                          double* zt_u, int* status, int* iters, double* resid);
+/* Asynchronous forms of the two *_host entry points, for streaming batch after batch: the call enqueues the copies and the
+ * solve on buffer set `slot` (0 or 1; the second set of device buffers is allocated on first use) and returns;
+ * lmpc_host_wait(h, slot) returns once the results of that slot are in the caller's output arrays.  With two batches in
+ * flight the H2D copy of one overlaps the solve of the other.  All host arrays must stay valid (and should be pinned) until
+ * the wait; a slot must be waited for before it is reused.  lmpc_solve_*_host == *_async(slot 0) + lmpc_host_wait(0). */
+int lmpc_solve_mpc_host_async(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
+                              long long abc_inst_stride, long long abc_stage_stride, double* xPred, double* uPred,
+                              double* slack, int* status, int* iters, double* resid);
+int lmpc_solve_lmpc_host_async(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
+                               long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel,
+                               const double* Qfun_sel, const double* Succ_SS, const double* Succ_uSS, double* xPred,
+                               double* uPred, double* slack, double* lambd, double* slackTerminal, double* zt,
+                               double* zt_u, int* status, int* iters, double* resid);
+int lmpc_host_wait(lmpc_handle* h, int slot);
 int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, const double* abc,
                         long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel,
                         const double* Qfun_sel, const double* Succ_SS, const double* Succ_uSS, double* xPred,

@@ -90,6 +90,32 @@ class BatchedFTOCP:
                 nat.ptr(o["status"]), nat.ptr(o["iters"]), nat.ptr(o["resid"])))
         return o
 
+    def solve_async(self, slot, x0, uOld, abc, out, SS_sel=None, Qfun_sel=None, Succ_SS=None, Succ_uSS=None):
+        """Enqueue a host-path solve on buffer set ``slot`` (0 or 1) and return at once; ``wait(slot)`` completes it.
+        Every array (inputs and the ``out`` dict of ``alloc_outputs``) must be C-contiguous float64/int32, should be pinned,
+        and must stay alive and untouched until the wait.  Two slots in flight overlap the copies of one batch with the solve
+        of the other."""
+        B, N, M = self.B, self.N, self.M
+        for a in (x0, uOld, abc):
+            if not (isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype == np.float64):
+                raise ValueError("solve_async takes C-contiguous float64 arrays (no hidden copies that could die before wait())")
+        abc, s_i, s_k = self._abc_layout(abc)
+        o = out
+        if SS_sel is None:
+            nat.check(self._lib.lmpc_solve_mpc_host_async(self._h, int(slot), nat.ptr(x0), nat.ptr(uOld), nat.ptr(abc), s_i, s_k,
+                                                          nat.ptr(o["xPred"]), nat.ptr(o["uPred"]), nat.ptr(o["slack"]),
+                                                          nat.ptr(o["status"]), nat.ptr(o["iters"]), nat.ptr(o["resid"])))
+        else:
+            nat.check(self._lib.lmpc_solve_lmpc_host_async(
+                self._h, int(slot), nat.ptr(x0), nat.ptr(uOld), nat.ptr(abc), s_i, s_k, nat.ptr(SS_sel), nat.ptr(Qfun_sel),
+                nat.ptr(Succ_SS), nat.ptr(Succ_uSS), nat.ptr(o["xPred"]), nat.ptr(o["uPred"]), nat.ptr(o["slack"]),
+                nat.ptr(o["lambd"]), nat.ptr(o["slackTerminal"]), nat.ptr(o["zt"]), nat.ptr(o["zt_u"]),
+                nat.ptr(o["status"]), nat.ptr(o["iters"]), nat.ptr(o["resid"])))
+        return o
+
+    def wait(self, slot):
+        nat.check(self._lib.lmpc_host_wait(self._h, int(slot)))
+
     def alloc_outputs(self, lmpc=False):
         B, N, M = self.B, self.N, max(self.M, 1)
         o = dict(xPred=np.zeros((B, N + 1, 6)), uPred=np.zeros((B, N, 2)), slack=np.zeros((B, N * self.ncx)),

@@ -173,12 +173,21 @@ struct lmpc_handle {
     FtocpConst c;
     int batch, device, N, M;
     cudaStream_t stream;
-    cudaStream_t cstream[8];   // chunk pipeline of the *_host entry points (H2D | kernel | D2H overlap)
+    cudaStream_t cstream[8];   // chunk pipelines of the *_host entry points (H2D | kernel | D2H overlap), 4 streams per slot
+    int hb_chunks[2];
+    bool trace_on;
+    cudaEvent_t tev[4][3], t0ev;
     long long launches;
     // device buffers used by the *_host entry points
     double *d_x0, *d_uOld, *d_abc, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
     double *d_xPred, *d_uPred, *d_slack, *d_lambd, *d_slackT, *d_zt, *d_ztu, *d_resid;
     int *d_status, *d_iters;
+    // second buffer set of the asynchronous host entry points (slot 1; allocated on first use)
+    struct HostBufs {
+        double *x0, *uOld, *abc, *SS, *Qfun, *SuccSS, *SuccU, *xPred, *uPred, *slack, *lambd, *slackT, *zt, *ztu, *resid;
+        int *status, *iters;
+    } hb1;
+    bool has_hb1;
     // lap stores + controller state (lmpc_store_create)
     bool has_store;
     ModelConst mc;
@@ -327,6 +336,11 @@ int lmpc_destroy(lmpc_handle* h) {
                         h->d_ztFixed, h->d_OldInput, h->d_xPredPrev, h->d_tmpx, h->d_tmpu, h->d_xchg};
         for (void* q : ptrs) cudaFree(q);
     }
+    if (h->has_hb1) {
+        void* q1[] = {h->hb1.x0, h->hb1.uOld, h->hb1.abc, h->hb1.SS, h->hb1.Qfun, h->hb1.SuccSS, h->hb1.SuccU, h->hb1.xPred, h->hb1.uPred,
+                      h->hb1.slack, h->hb1.lambd, h->hb1.slackT, h->hb1.zt, h->hb1.ztu, h->hb1.resid, h->hb1.status, h->hb1.iters};
+        for (void* q : q1) cudaFree(q);
+    }
     double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
                      h->d_slack, h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid};
     for (double* q : dbl) cudaFree(q);
@@ -381,16 +395,44 @@ int lmpc_solve_mpc_dev(lmpc_handle* h, const double* x0, const double* uOld, con
                                uPred, slack, nullptr, nullptr, nullptr, nullptr, status, iters, resid);
 }
 
-int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
-                         long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel, const double* Succ_SS,
-                         const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
-                         double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
+static int host_bufs(lmpc_handle* h, int slot, lmpc_handle::HostBufs& b) {
+    if (slot == 0) {
+        b = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred, h->d_slack,
+             h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid, h->d_status, h->d_iters};
+        return LMPC_OK;
+    }
+    if (!h->has_hb1) {
+        const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
+        lmpc_handle::HostBufs& q = h->hb1;
+#define DA1(ptr, count) CK(cudaMalloc((void**)&q.ptr, sizeof(*q.ptr) * (count)))
+        DA1(x0, B * 6); DA1(uOld, B * 2); DA1(abc, B * N * 54);
+        DA1(SS, B * 6 * M); DA1(Qfun, B * M); DA1(SuccSS, B * 6 * M); DA1(SuccU, B * 2 * M);
+        DA1(xPred, B * (N + 1) * 6); DA1(uPred, B * N * 2); DA1(slack, B * N * 2);
+        DA1(lambd, B * M); DA1(slackT, B * 6); DA1(zt, B * 6); DA1(ztu, B * 2);
+        DA1(resid, B * 3); DA1(status, B); DA1(iters, B);
+#undef DA1
+        h->has_hb1 = true;
+    }
+    b = h->hb1;
+    return LMPC_OK;
+}
+
+// Enqueue one host-buffer solve on buffer set / stream group `slot` (0 or 1) WITHOUT waiting for it.
+static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
+                              long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel,
+                              const double* Succ_SS, const double* Succ_uSS, double* xPred, double* uPred, double* slack,
+                              double* lambd, double* slackTerminal, double* zt, double* zt_u, int* status, int* iters,
+                              double* resid) {
     if (!h || !x0 || !uOld || !abc || !xPred || !uPred || !status || !iters || !resid) return fail(LMPC_E_INVALID, "null argument");
     const bool lm = (SS_sel != nullptr);
     if (lm && (h->M <= 0 || !Qfun_sel)) return fail(LMPC_E_INVALID, "handle was created without a safe set (numSS_Points == 0)");
+    if (slot < 0 || slot > 1) return fail(LMPC_E_INVALID, "slot must be 0 or 1");
     CK(cudaSetDevice(h->device));
     const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
     const size_t D = sizeof(double);
+    lmpc_handle::HostBufs hb;
+    { int rcb = host_bufs(h, slot, hb); if (rcb) return rcb; }
+    cudaStream_t* cs = h->cstream + 4 * slot;
     long long dis, dss;
     bool per_inst = false;
     if (abc_inst_stride == 0 && abc_stage_stride == 0) { dis = 0; dss = 0; }                       // one shared LTI model
@@ -399,72 +441,107 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
     else return fail(LMPC_E_INVALID, "host entry supports abc strides (N*54,54), (0,54) or (0,0)");
     CK(cudaStreamSynchronize(h->stream));    // earlier work of this handle is done before the chunk streams start
     if (!per_inst) {
-        CK(cudaMemcpyAsync(h->d_abc, abc, (dss ? N * 54 : 54) * D, cudaMemcpyHostToDevice, h->cstream[0]));
-        CK(cudaStreamSynchronize(h->cstream[0]));
+        CK(cudaMemcpyAsync(hb.abc, abc, (dss ? N * 54 : 54) * D, cudaMemcpyHostToDevice, cs[0]));
+        CK(cudaStreamSynchronize(cs[0]));
     }
     // Chunk pipeline: the batch is cut into up to four instance ranges, each on its own stream, so that the H2D copy
     // of range i+1, the solve of range i and the D2H copy of range i-1 overlap (PCIe is full duplex).
     int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
-    if (const char* e = getenv("LMPC_B200_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 8 && (size_t)v <= B) nchunk = v; }   // tuning knob
-    const bool trace = getenv("LMPC_B200_TRACE") != nullptr;
-    cudaEvent_t tev[8][3], t0ev;
+    if (const char* e = getenv("LMPC_B200_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 4 && (size_t)v <= B) nchunk = v; }   // tuning knob
+    const bool trace = slot == 0 && getenv("LMPC_B200_TRACE") != nullptr;
     if (trace) {
-        cudaEventCreate(&t0ev);
-        for (int i = 0; i < nchunk; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&tev[i][j]);
-        cudaEventRecord(t0ev, h->cstream[0]);
+        cudaEventCreate(&h->t0ev);
+        for (int i = 0; i < nchunk; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&h->tev[i][j]);
+        cudaEventRecord(h->t0ev, cs[0]);
     }
+    h->trace_on = trace;
     for (int ci = 0; ci < nchunk; ++ci) {
         const size_t lo = B * ci / nchunk, hi = B * (ci + 1) / nchunk, nb = hi - lo;
-        cudaStream_t s = h->cstream[ci];
-        CK(cudaMemcpyAsync(h->d_x0 + lo * 6, x0 + lo * 6, nb * 6 * D, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(h->d_uOld + lo * 2, uOld + lo * 2, nb * 2 * D, cudaMemcpyHostToDevice, s));
-        if (per_inst) CK(cudaMemcpyAsync(h->d_abc + lo * N * 54, abc + lo * N * 54, nb * N * 54 * D, cudaMemcpyHostToDevice, s));
+        cudaStream_t s = cs[ci];
+        CK(cudaMemcpyAsync(hb.x0 + lo * 6, x0 + lo * 6, nb * 6 * D, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(hb.uOld + lo * 2, uOld + lo * 2, nb * 2 * D, cudaMemcpyHostToDevice, s));
+        if (per_inst) CK(cudaMemcpyAsync(hb.abc + lo * N * 54, abc + lo * N * 54, nb * N * 54 * D, cudaMemcpyHostToDevice, s));
         if (lm) {
-            CK(cudaMemcpyAsync(h->d_SS + lo * 6 * M, SS_sel + lo * 6 * M, nb * 6 * M * D, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(h->d_Qfun + lo * M, Qfun_sel + lo * M, nb * M * D, cudaMemcpyHostToDevice, s));
-            if (Succ_SS) CK(cudaMemcpyAsync(h->d_SuccSS + lo * 6 * M, Succ_SS + lo * 6 * M, nb * 6 * M * D, cudaMemcpyHostToDevice, s));
-            if (Succ_uSS) CK(cudaMemcpyAsync(h->d_SuccU + lo * 2 * M, Succ_uSS + lo * 2 * M, nb * 2 * M * D, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(hb.SS + lo * 6 * M, SS_sel + lo * 6 * M, nb * 6 * M * D, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(hb.Qfun + lo * M, Qfun_sel + lo * M, nb * M * D, cudaMemcpyHostToDevice, s));
+            if (Succ_SS) CK(cudaMemcpyAsync(hb.SuccSS + lo * 6 * M, Succ_SS + lo * 6 * M, nb * 6 * M * D, cudaMemcpyHostToDevice, s));
+            if (Succ_uSS) CK(cudaMemcpyAsync(hb.SuccU + lo * 2 * M, Succ_uSS + lo * 2 * M, nb * 2 * M * D, cudaMemcpyHostToDevice, s));
         }
         FtocpArgs a;
         a.batch = (int)nb;
-        a.x0 = h->d_x0 + lo * 6; a.uOld = h->d_uOld + lo * 2;
-        a.abc = per_inst ? h->d_abc + lo * N * 54 : h->d_abc;
+        a.x0 = hb.x0 + lo * 6; a.uOld = hb.uOld + lo * 2;
+        a.abc = per_inst ? hb.abc + lo * N * 54 : hb.abc;
         a.abc_inst_stride = dis; a.abc_stage_stride = dss;
-        a.SS = lm ? h->d_SS + lo * 6 * M : nullptr; a.Qfun = lm ? h->d_Qfun + lo * M : nullptr;
-        a.SuccSS = (lm && Succ_SS) ? h->d_SuccSS + lo * 6 * M : nullptr; a.SuccU = (lm && Succ_uSS) ? h->d_SuccU + lo * 2 * M : nullptr;
-        a.xPred = h->d_xPred + lo * (N + 1) * 6; a.uPred = h->d_uPred + lo * N * 2;
-        a.slack = slack ? h->d_slack + lo * N * 2 : nullptr;
-        a.lambd = (lm && lambd) ? h->d_lambd + lo * M : nullptr;
-        a.slackT = (lm && slackTerminal) ? h->d_slackT + lo * 6 : nullptr;
-        a.zt = (lm && zt) ? h->d_zt + lo * 6 : nullptr; a.ztu = (lm && zt_u) ? h->d_ztu + lo * 2 : nullptr;
-        a.status = h->d_status + lo; a.iters = h->d_iters + lo; a.resid = h->d_resid + lo * 3;
-        if (trace) cudaEventRecord(tev[ci][0], s);
+        a.SS = lm ? hb.SS + lo * 6 * M : nullptr; a.Qfun = lm ? hb.Qfun + lo * M : nullptr;
+        a.SuccSS = (lm && Succ_SS) ? hb.SuccSS + lo * 6 * M : nullptr; a.SuccU = (lm && Succ_uSS) ? hb.SuccU + lo * 2 * M : nullptr;
+        a.xPred = hb.xPred + lo * (N + 1) * 6; a.uPred = hb.uPred + lo * N * 2;
+        a.slack = slack ? hb.slack + lo * N * 2 : nullptr;
+        a.lambd = (lm && lambd) ? hb.lambd + lo * M : nullptr;
+        a.slackT = (lm && slackTerminal) ? hb.slackT + lo * 6 : nullptr;
+        a.zt = (lm && zt) ? hb.zt + lo * 6 : nullptr; a.ztu = (lm && zt_u) ? hb.ztu + lo * 2 : nullptr;
+        a.status = hb.status + lo; a.iters = hb.iters + lo; a.resid = hb.resid + lo * 3;
+        if (trace) cudaEventRecord(h->tev[ci][0], s);
         int rc = launch(h, a, lm, s);
         if (rc != LMPC_OK) return rc;
-        if (trace) cudaEventRecord(tev[ci][1], s);
-        CK(cudaMemcpyAsync(xPred + lo * (N + 1) * 6, h->d_xPred + lo * (N + 1) * 6, nb * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(uPred + lo * N * 2, h->d_uPred + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
-        if (slack) CK(cudaMemcpyAsync(slack + lo * N * 2, h->d_slack + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
-        if (lm && lambd) CK(cudaMemcpyAsync(lambd + lo * M, h->d_lambd + lo * M, nb * M * D, cudaMemcpyDeviceToHost, s));
-        if (lm && slackTerminal) CK(cudaMemcpyAsync(slackTerminal + lo * 6, h->d_slackT + lo * 6, nb * 6 * D, cudaMemcpyDeviceToHost, s));
-        if (lm && zt && Succ_SS) CK(cudaMemcpyAsync(zt + lo * 6, h->d_zt + lo * 6, nb * 6 * D, cudaMemcpyDeviceToHost, s));
-        if (lm && zt_u && Succ_uSS) CK(cudaMemcpyAsync(zt_u + lo * 2, h->d_ztu + lo * 2, nb * 2 * D, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + lo, h->d_status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(iters + lo, h->d_iters + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(resid + lo * 3, h->d_resid + lo * 3, nb * 3 * D, cudaMemcpyDeviceToHost, s));
-        if (trace) cudaEventRecord(tev[ci][2], s);
+        if (trace) cudaEventRecord(h->tev[ci][1], s);
+        CK(cudaMemcpyAsync(xPred + lo * (N + 1) * 6, hb.xPred + lo * (N + 1) * 6, nb * (N + 1) * 6 * D, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(uPred + lo * N * 2, hb.uPred + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
+        if (slack) CK(cudaMemcpyAsync(slack + lo * N * 2, hb.slack + lo * N * 2, nb * N * 2 * D, cudaMemcpyDeviceToHost, s));
+        if (lm && lambd) CK(cudaMemcpyAsync(lambd + lo * M, hb.lambd + lo * M, nb * M * D, cudaMemcpyDeviceToHost, s));
+        if (lm && slackTerminal) CK(cudaMemcpyAsync(slackTerminal + lo * 6, hb.slackT + lo * 6, nb * 6 * D, cudaMemcpyDeviceToHost, s));
+        if (lm && zt && Succ_SS) CK(cudaMemcpyAsync(zt + lo * 6, hb.zt + lo * 6, nb * 6 * D, cudaMemcpyDeviceToHost, s));
+        if (lm && zt_u && Succ_uSS) CK(cudaMemcpyAsync(zt_u + lo * 2, hb.ztu + lo * 2, nb * 2 * D, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + lo, hb.status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(iters + lo, hb.iters + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(resid + lo * 3, hb.resid + lo * 3, nb * 3 * D, cudaMemcpyDeviceToHost, s));
+        if (trace) cudaEventRecord(h->tev[ci][2], s);
     }
-    for (int ci = 0; ci < nchunk; ++ci) CK(cudaStreamSynchronize(h->cstream[ci]));
-    if (trace) {
+    h->hb_chunks[slot] = nchunk;
+    return LMPC_OK;
+}
+
+
+int lmpc_host_wait(lmpc_handle* h, int slot) {
+    if (!h || slot < 0 || slot > 1) return fail(LMPC_E_INVALID, "bad handle or slot");
+    CK(cudaSetDevice(h->device));
+    const int nchunk = h->hb_chunks[slot] > 0 ? h->hb_chunks[slot] : 4;
+    for (int ci = 0; ci < nchunk; ++ci) CK(cudaStreamSynchronize(h->cstream[4 * slot + ci]));
+    if (slot == 0 && h->trace_on) {
         for (int i = 0; i < nchunk; ++i) {
             float a_ = 0, b_ = 0, c_ = 0;
-            cudaEventElapsedTime(&a_, t0ev, tev[i][0]); cudaEventElapsedTime(&b_, t0ev, tev[i][1]); cudaEventElapsedTime(&c_, t0ev, tev[i][2]);
+            cudaEventElapsedTime(&a_, h->t0ev, h->tev[i][0]); cudaEventElapsedTime(&b_, h->t0ev, h->tev[i][1]); cudaEventElapsedTime(&c_, h->t0ev, h->tev[i][2]);
             fprintf(stderr, "chunk %d: h2d done %.3f ms, kernel done %.3f, d2h done %.3f\n", i, a_, b_, c_);
-            for (int j = 0; j < 3; ++j) cudaEventDestroy(tev[i][j]);
+            for (int j = 0; j < 3; ++j) cudaEventDestroy(h->tev[i][j]);
         }
-        cudaEventDestroy(t0ev);
+        cudaEventDestroy(h->t0ev);
+        h->trace_on = false;
     }
     return LMPC_OK;
+}
+
+int lmpc_solve_lmpc_host_async(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
+                               long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel, const double* Succ_SS,
+                               const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
+                               double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
+    return enqueue_host_solve(h, slot, x0, uOld, abc, abc_inst_stride, abc_stage_stride, SS_sel, Qfun_sel, Succ_SS, Succ_uSS, xPred, uPred,
+                              slack, lambd, slackTerminal, zt, zt_u, status, iters, resid);
+}
+
+int lmpc_solve_mpc_host_async(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
+                              long long abc_stage_stride, double* xPred, double* uPred, double* slack, int* status, int* iters,
+                              double* resid) {
+    return enqueue_host_solve(h, slot, x0, uOld, abc, abc_inst_stride, abc_stage_stride, nullptr, nullptr, nullptr, nullptr, xPred, uPred,
+                              slack, nullptr, nullptr, nullptr, nullptr, status, iters, resid);
+}
+
+int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,
+                         long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel, const double* Succ_SS,
+                         const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
+                         double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
+    int rc = enqueue_host_solve(h, 0, x0, uOld, abc, abc_inst_stride, abc_stage_stride, SS_sel, Qfun_sel, Succ_SS, Succ_uSS, xPred, uPred,
+                                slack, lambd, slackTerminal, zt, zt_u, status, iters, resid);
+    if (rc) return rc;
+    return lmpc_host_wait(h, 0);
 }
 
 int lmpc_solve_mpc_host(lmpc_handle* h, const double* x0, const double* uOld, const double* abc, long long abc_inst_stride,

@@ -149,3 +149,28 @@ def test_device_pointer_entry_matches_host_entry():
     assert np.array_equal(uP.cpu().numpy(), oh["uPred"])
     assert np.array_equal(xP.cpu().numpy(), oh["xPred"])
     s.close()
+
+
+def test_async_host_entry_two_slots_match_the_synchronous_call():
+    """lmpc_solve_mpc_host_async on buffer sets 0 and 1 (two batches in flight) returns exactly what the synchronous entry
+    point returns for the same inputs, also when a slot is reused."""
+    _need_gpu()
+    B, N = 256, 12
+    x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
+    s = BatchedFTOCP(rp.mpc_params(N), batch=B)
+    ref = s.solve(x0, uold, abc)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    ins = [(pin(x0), pin(uold), pin(abc)), (pin(x0[::-1]), pin(uold[::-1]), pin(abc[::-1]))]
+    outs = [{k: pin(v) for k, v in s.alloc_outputs(False).items()} for _ in range(2)]
+    for rep in range(3):
+        for slot in (0, 1):
+            if rep:
+                s.wait(slot)
+            s.solve_async(slot, *ins[slot], outs[slot])
+    s.wait(0); s.wait(1)
+    for k in ("xPred", "uPred", "slack", "status", "iters", "resid"):
+        assert np.array_equal(outs[0][k], ref[k]), k
+        assert np.array_equal(outs[1][k], ref[k][::-1]), k
+    with pytest.raises(ValueError):
+        s.solve_async(0, x0[::2], uold, abc, outs[0])          # non-contiguous view: refused, not silently copied
+    s.close()
