@@ -201,10 +201,23 @@ void* lmpc_device_buffer(lmpc_handle* h, const char* name);
 int lmpc_rollout_create(lmpc_handle* h, int Tcl);
 int lmpc_rollout_set_state(lmpc_handle* h, const double* x, const double* xglob);              /* [B,6] host, may be NULL */
 int lmpc_rollout_get_state(lmpc_handle* h, double* x, double* xglob, int* done, int* cl_len);  /* any may be NULL      */
-int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned long long seed);
+int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned long long seed);   /* mode 0 LTV-MPC, 1 LMPC, 2 LTI-MPC */
 /* Since lmpc_rollout_create: OR of the per-step flags (bits as in lmpc_step_host) and number of steps whose QP was not
  * reported solved (the reference would have driven on with feasible = 0, PC.py:279-283), per instance; either may be NULL. */
 int lmpc_rollout_get_health(lmpc_handle* h, int* flags_or, int* unsolved_steps);                 /* [B] host             */
+/* The rest of main.py's pipeline on the device.
+ * lmpc_rollout_pid_step: one closed-loop step under the PID path follower (Utilities.py:42-68, target speed vt); z_pid_host[B,2]
+ *   and z_sim_host[B,3] are the reference's standard-normal draws in its order, NULL = Philox.  1000 such steps from
+ *   x = [0.5,0,0,0,0,0] are main.py:65-66's PID lap (the record must hold them: lmpc_rollout_create(h, Tcl >= 1000)).
+ * lmpc_rollout_sysid: Regression(x, u, lamb) (Utilities.py:5-28) of every record -> device buffer "abc_lti" [B,54] = A | B | 0
+ *   (and abc_host / flags_host when given; flag bit 1 = singular normal matrix).  lmpc_rollout_step(mode 2) then runs the LTI
+ *   MPC of main.py:72-80 with it.
+ * lmpc_rollout_seed_from_record: main.py:99-110 -- the record becomes `copies` identical laps in the safe set and in the
+ *   regression model (the caller's lap books must say the same: lmpc_ss_set_selection / lmpc_model_set_used), xLin/uLin/zt/
+ *   OldInput/timeStep are initialised as LMPC.__init__/addTrajectory do, the record restarts. */
+int lmpc_rollout_pid_step(lmpc_handle* h, double vt, const double* z_pid_host, const double* z_sim_host, unsigned long long seed);
+int lmpc_rollout_sysid(lmpc_handle* h, double lamb, double* abc_host, int* flags_host);
+int lmpc_rollout_seed_from_record(lmpc_handle* h, int copies, int ss_slot0, int model_slot0);
 int lmpc_rollout_get_lap(lmpc_handle* h, int inst, int* T, double* x, double* u);              /* closed-loop record   */
 /* Lap hand-over on the device = LMPC.addTrajectory + PredictiveModel.addTrajectory of the lap just driven (either slot may
  * be -1), then s -= TrackLength (SysModel.py:50), record restarted, timeStep = 0 (PC.py:445). */

@@ -89,6 +89,9 @@ def lib():
     L.lmpc_rollout_get_state.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.lmpc_rollout_step.argtypes = [_vp, C.c_int, _vp, C.c_ulonglong]
     L.lmpc_rollout_get_health.argtypes = [_vp, _vp, _vp]
+    L.lmpc_rollout_pid_step.argtypes = [_vp, C.c_double, _vp, _vp, C.c_ulonglong]
+    L.lmpc_rollout_sysid.argtypes = [_vp, C.c_double, _vp, _vp]
+    L.lmpc_rollout_seed_from_record.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
     L.lmpc_rollout_get_lap.argtypes = [_vp, C.c_int, ip, _vp, _vp]
     L.lmpc_rollout_commit_lap.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
     L.lmpc_rollout_commit_laps.argtypes = [_vp, _vp, _vp, _vp]

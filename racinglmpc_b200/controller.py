@@ -273,12 +273,50 @@ class BatchedController:
         nat.check(self._lib.lmpc_rollout_get_state(self._h, nat.ptr(o["x"]), nat.ptr(o["xglob"]), nat.ptr(o["done"]), nat.ptr(o["cl_len"])))
         return o
 
-    def rollout_step(self, z=None, seed=0):
+    def rollout_step(self, z=None, seed=0, mode=None):
         """Simulator.sim loop body (SysModel.py:34-48) for every instance on the device.  z[B,3]: standard-normal draws for
-        the process noise (reference order vx, vy, wz); None = Philox on the device."""
+        the process noise (reference order vx, vy, wz); None = Philox on the device.  mode: 0 LTV-MPC, 1 LMPC (defaults by
+        how the controller was built), 2 LTI-MPC with the model of ``rollout_sysid``."""
         self._flush()
         zz = None if z is None else np.ascontiguousarray(np.asarray(z, float).reshape(self.B, 3))
-        nat.check(self._lib.lmpc_rollout_step(self._h, 1 if self.lmpc else 0, nat.ptr(zz), int(seed)))
+        m = (1 if self.lmpc else 0) if mode is None else int(mode)
+        nat.check(self._lib.lmpc_rollout_step(self._h, m, nat.ptr(zz), int(seed)))
+
+    def rollout_pid_step(self, vt, z_pid=None, z_sim=None, seed=0):
+        """One closed-loop step under the PID path follower (Utilities.py:42-68) for every instance: main.py:65-66's seeding lap
+        is 1000 of these.  z_pid[B,2], z_sim[B,3]: the reference's standard-normal draws (None = Philox)."""
+        zp = None if z_pid is None else np.ascontiguousarray(np.asarray(z_pid, float).reshape(self.B, 2))
+        zs = None if z_sim is None else np.ascontiguousarray(np.asarray(z_sim, float).reshape(self.B, 3))
+        nat.check(self._lib.lmpc_rollout_pid_step(self._h, float(vt), nat.ptr(zp), nat.ptr(zs), int(seed)))
+
+    def rollout_sysid(self, lamb=1e-7):
+        """Regression(x, u, lamb) (Utilities.py:5-28) of every instance's record.  Returns A[B,6,6], B[B,6,2], flags[B]; the model
+        also stays on the device for ``rollout_step(mode=2)``."""
+        abc = np.zeros((self.B, 54)); flags = np.zeros(self.B, np.int32)
+        nat.check(self._lib.lmpc_rollout_sysid(self._h, float(lamb), nat.ptr(abc), nat.ptr(flags)))
+        return abc[:, 0:36].reshape(self.B, 6, 6).copy(), abc[:, 36:48].reshape(self.B, 6, 2).copy(), flags
+
+    def rollout_seed_from_record(self, cl_len, copies=4):
+        """main.py:99-110 on the device: the record every instance just drove (cl_len[b] rows, e.g. its PID lap) becomes
+        ``copies`` identical laps of the safe set and of the regression model, and the controller state is initialised from it."""
+        ss0 = m0 = None
+        for b in range(self.B):
+            T = int(cl_len[b])
+            for c in range(copies):
+                ms = self._model_slot_for(b, T)
+                sl = self._ss_slot_for(b, T) if self.lmpc else -1
+                if self.lmpc:
+                    self.it[b] += 1
+                if c == 0:
+                    if ss0 is None:
+                        ss0, m0 = sl, ms
+                    if (sl, ms) != (ss0, m0):
+                        raise RuntimeError("seeding needs the same free slots on every instance (fresh controller)")
+                elif (sl, ms) != (ss0 + c, m0 + c):
+                    raise RuntimeError("seeding needs consecutive free slots (fresh controller)")
+        nat.check(self._lib.lmpc_rollout_seed_from_record(self._h, int(copies), int(max(ss0, 0)), int(m0)))
+        self._sel_dirty = True
+        self._used_dirty = True
 
     def rollout_done(self):
         d = np.zeros(self.B, np.int32); n = np.zeros(self.B, np.int32)

@@ -198,7 +198,7 @@ struct lmpc_handle {
     bool has_rollout;
     int Tcl;
     unsigned long long sim_step;
-    double *d_rx[2], *d_rg[2], *d_clx, *d_clu, *d_z;
+    double *d_rx[2], *d_rg[2], *d_clx, *d_clu, *d_z, *d_zpid, *d_abc_lti;
     int *d_cllen, *d_done, cur;
 };
 
@@ -327,7 +327,7 @@ int lmpc_destroy(lmpc_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->has_rollout) {
-        void* rp[] = {h->d_rx[0], h->d_rx[1], h->d_rg[0], h->d_rg[1], h->d_clx, h->d_clu, h->d_z, h->d_cllen, h->d_done, h->d_health};
+        void* rp[] = {h->d_rx[0], h->d_rx[1], h->d_rg[0], h->d_rg[1], h->d_clx, h->d_clu, h->d_z, h->d_zpid, h->d_abc_lti, h->d_cllen, h->d_done, h->d_health};
         for (void* q : rp) cudaFree(q);
     }
     if (h->has_store) {
@@ -904,7 +904,7 @@ void* lmpc_device_buffer(lmpc_handle* h, const char* name) {
         {"xPred", h->d_xPred}, {"uPred", h->d_uPred}, {"lambd", h->d_lambd}, {"zt", h->d_zt}, {"zt_u", h->d_ztu},
         {"abc", h->d_abc}, {"SS_sel", h->d_SS}, {"Qfun_sel", h->d_Qfun}, {"Succ_SS", h->d_SuccSS}, {"Succ_uSS", h->d_SuccU},
         {"status", h->d_status}, {"iters", h->d_iters}, {"resid", h->d_resid}, {"flags", h->d_flags}, {"xLin", h->d_xLin},
-        {"uLin", h->d_uLin}, {"x0", h->d_x0}, {"OldInput", h->d_OldInput}};
+        {"uLin", h->d_uLin}, {"x0", h->d_x0}, {"OldInput", h->d_OldInput}, {"abc_lti", h->has_rollout ? h->d_abc_lti : nullptr}};
     for (auto& e : tab) if (strcmp(e.n, name) == 0) return e.p;
     return nullptr;
 }
@@ -926,6 +926,9 @@ int lmpc_rollout_create(lmpc_handle* h, int Tcl) {
     CK(cudaMalloc((void**)&h->d_clx, sizeof(double) * B * Tcl * 6));
     CK(cudaMalloc((void**)&h->d_clu, sizeof(double) * B * Tcl * 2));
     CK(cudaMalloc((void**)&h->d_z, sizeof(double) * B * 3));
+    CK(cudaMalloc((void**)&h->d_zpid, sizeof(double) * B * 2));
+    CK(cudaMalloc((void**)&h->d_abc_lti, sizeof(double) * B * 54));
+    CK(cudaMemsetAsync(h->d_abc_lti, 0, sizeof(double) * B * 54, h->stream));
     CK(cudaMalloc((void**)&h->d_cllen, sizeof(int) * B));
     CK(cudaMalloc((void**)&h->d_done, sizeof(int) * B));
     CK(cudaMalloc((void**)&h->d_health, sizeof(int) * B * 2));
@@ -985,7 +988,15 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     const double* xc = h->d_rx[h->cur];
-    rc = lmpc_step_dev(h, mode, xc);
+    if (mode == 2) {
+        CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
+        // LTI MPC with the per-instance model identified by lmpc_rollout_sysid (main.py:72-80); like the reference's LTI
+        // controller it never refreshes the input-rate reference (OldInput keeps its initial value, PC.py:113-115)
+        rc = lmpc_solve_mpc_dev(h, xc, h->d_OldInput, h->d_abc_lti, 54, 0, h->d_xPred, h->d_uPred, h->d_slack, h->d_status, h->d_iters,
+                                h->d_resid);
+    } else {
+        rc = lmpc_step_dev(h, mode, xc);
+    }
     if (rc) return rc;
     if (mode == 1) {
         ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, xc, h->d_uPred,
@@ -1005,6 +1016,67 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
     h->launches += 1;
     h->cur ^= 1;
     h->sim_step += 1;
+    return LMPC_OK;
+}
+
+// One closed-loop step with the PID path follower as the controller (main.py:65-66: the lap that seeds everything else).
+// z_pid_host[B,2] / z_sim_host[B,3]: the reference's standard-normal draws in its order (PID steer, PID accel | vx, vy, wz);
+// NULL = Philox on the device.
+int lmpc_rollout_pid_step(lmpc_handle* h, double vt, const double* z_pid_host, const double* z_sim_host, unsigned long long seed) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const double* xc = h->d_rx[h->cur];
+    if (z_pid_host) CK(cudaMemcpyAsync(h->d_zpid, z_pid_host, sizeof(double) * h->batch * 2, cudaMemcpyHostToDevice, h->stream));
+    if (z_sim_host) CK(cudaMemcpyAsync(h->d_z, z_sim_host, sizeof(double) * h->batch * 3, cudaMemcpyHostToDevice, h->stream));
+    PidArgs pa;
+    pa.batch = h->batch; pa.x = xc; pa.vt = vt; pa.z = z_pid_host ? h->d_zpid : nullptr; pa.seed = seed; pa.step = h->sim_step;
+    pa.u = h->d_uPred; pa.u_stride = (long long)h->N * 2;
+    pid_input_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(pa);
+    SimArgs sa;
+    sa.batch = h->batch; sa.x = xc; sa.xg = h->d_rg[h->cur]; sa.u = h->d_uPred; sa.u_stride = (long long)h->N * 2;
+    sa.z = z_sim_host ? h->d_z : nullptr; sa.seed = seed; sa.step = h->sim_step;
+    sa.xn = h->d_rx[h->cur ^ 1]; sa.xgn = h->d_rg[h->cur ^ 1];
+    sa.cl_x = h->d_clx; sa.cl_u = h->d_clu; sa.cl_len = h->d_cllen; sa.Tcl = h->Tcl; sa.done = h->d_done; sa.active = nullptr;
+    sa.flags = nullptr; sa.status = nullptr; sa.health = nullptr;
+    sim_step_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->mc, sa);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    h->cur ^= 1;
+    h->sim_step += 1;
+    if (z_pid_host || z_sim_host) CK(cudaStreamSynchronize(h->stream));   // pageable host arrays of the caller
+    return LMPC_OK;
+}
+
+// Regression(x, u, lamb) of Utilities.py:5-28 on every instance's closed-loop record: per-instance LTI model in the device
+// buffer "abc_lti" ([B][54] = A | B | C = 0, the layout lmpc_solve_mpc_dev takes with strides (54, 0)); abc_host may be NULL.
+int lmpc_rollout_sysid(lmpc_handle* h, double lamb, double* abc_host, int* flags_host) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
+    ridge_sysid_kernel<<<h->batch, 32, 0, h->stream>>>(h->batch, h->d_clx, h->d_clu, h->d_cllen, h->Tcl, lamb, h->d_abc_lti, h->d_flags);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (abc_host) CK(cudaMemcpyAsync(abc_host, h->d_abc_lti, sizeof(double) * h->batch * 54, cudaMemcpyDeviceToHost, h->stream));
+    if (flags_host) CK(cudaMemcpyAsync(flags_host, h->d_flags, sizeof(int) * h->batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+// main.py:99-110 on the device: every instance's record becomes `copies` identical laps in safe-set slots ss_slot0.. and
+// regression slots model_slot0.., the controller state is initialised from it and the record restarts.
+int lmpc_rollout_seed_from_record(lmpc_handle* h, int copies, int ss_slot0, int model_slot0) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (copies < 1 || ss_slot0 < 0 || model_slot0 < 0 || ss_slot0 + copies > h->ss.cap || model_slot0 + copies > h->mdl.cap)
+        return fail(LMPC_E_INVALID, "seed copies do not fit the lap pools");
+    CK(cudaSetDevice(h->device));
+    seed_from_record_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, copies, ss_slot0, model_slot0, h->d_clx, h->d_clu,
+                                                             h->d_cllen, h->Tcl, h->N, h->d_xLin, h->d_uLin, h->d_ztState, h->d_OldInput,
+                                                             h->d_timeStep, h->d_hasPred, h->d_done, h->mc.TrackLength);
+    CK(cudaGetLastError());
+    h->launches += 1;
     return LMPC_OK;
 }
 

@@ -845,7 +845,7 @@ __global__ void sim_step_kernel(const __grid_constant__ ModelConst m, const SimA
         z0 = a.z[(size_t)b * 3]; z1 = a.z[(size_t)b * 3 + 1]; z2 = a.z[(size_t)b * 3 + 2];
     } else {
         curandStatePhilox4_32_10_t st;
-        curand_init(a.seed, (unsigned long long)b, a.step, &st);
+        curand_init(a.seed, (unsigned long long)b, a.step * 8ull, &st);   // 8 raw 32-bit draws per step: disjoint blocks
         const double2 n01 = curand_normal2_double(&st);
         const double2 n23 = curand_normal2_double(&st);
         z0 = n01.x; z1 = n01.y; z2 = n23.x;
@@ -860,6 +860,138 @@ __global__ void sim_step_kernel(const __grid_constant__ ModelConst m, const SimA
     xn[0] = vx + 0.01 * n_vx; xn[1] = vy + 0.01 * n_vy; xn[2] = wz + 0.01 * n_wz;
     xn[3] = epsi; xn[4] = s; xn[5] = ey;
     if (a.done) a.done[b] = (s > m.TrackLength) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PID path-following controller, Utilities.py:42-68 (PID.solve): u = [-0.6 ey - 0.9 epsi + clip(0.25 z0, +-0.9),
+// 1.5 (vt - vx) + clip(0.10 z1, +-0.2)], z ~ N(0,1) drawn in that order.  Writes uPred[b][0] so that sim_step_kernel
+// consumes it like a controller's first predicted input.
+struct PidArgs {
+    int batch;
+    const double* x;       // [B][6]
+    double vt;
+    const double* z;       // [B][2] or nullptr (Philox)
+    unsigned long long seed, step;
+    double* u;             // [B][u_stride]
+    long long u_stride;
+};
+__global__ void pid_input_kernel(const PidArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    double z0, z1;
+    if (a.z) {
+        z0 = a.z[(size_t)b * 2]; z1 = a.z[(size_t)b * 2 + 1];
+    } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(a.seed ^ 0x9E3779B97F4A7C15ull, (unsigned long long)b, a.step * 8ull, &st);
+        const double2 n01 = curand_normal2_double(&st);
+        z0 = n01.x; z1 = n01.y;
+    }
+    const double* x = a.x + (size_t)b * 6;
+    a.u[(size_t)b * a.u_stride] = -0.6 * x[5] - 0.9 * x[3] + fmax(-0.9, fmin(z0 * 0.25, 0.9));
+    a.u[(size_t)b * a.u_stride + 1] = 1.5 * (a.vt - x[0]) + fmax(-0.2, fmin(z1 * 0.10, 0.2));
+}
+
+// LTI system identification by ridge regression, Utilities.py:5-28 (Regression): rows t = 1 .. T-2 of the closed-loop
+// record, z_t = [x_t u_t] (8), y_t = x_{t+1} (6); W = (Z'Z + lamb I)^-1 Z'Y; A = W'[:, 0:6], B = W'[:, 6:8].
+// One warp per instance: lane e < 36 owns one entry of the upper triangle of Z'Z, lanes own the 48 entries of Z'Y in two
+// rounds; the 8 x 8 system with 6 right-hand sides is solved by Gaussian elimination with partial pivoting in shared memory.
+// Output abc[b][54] = A (36, row-major) | B (12) | C = 0 (6): the per-instance LTI model in the layout ftocp_kernel reads.
+__global__ void __launch_bounds__(32) ridge_sysid_kernel(int batch, const double* cl_x, const double* cl_u, const int* cl_len, int Tcl,
+                                                         double lamb, double* abc, int* status) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int lane = threadIdx.x;
+    __shared__ double S[8][14];      // [Z'Z + lamb I | Z'Y]
+    const int T = cl_len[b];
+    const double* X = cl_x + (size_t)b * Tcl * 6;
+    const double* U = cl_u + (size_t)b * Tcl * 2;
+    auto zval = [&](int t, int j) { return j < 6 ? X[(size_t)t * 6 + j] : U[(size_t)t * 2 + (j - 6)]; };
+    for (int e = lane; e < 36 + 48; e += 32) {
+        int r, c;
+        if (e < 36) { r = 0; int k = e; while (k >= 8 - r) { k -= 8 - r; ++r; } c = k + r; }
+        else { r = (e - 36) / 6; c = 8 + (e - 36) % 6; }
+        double acc = 0.0;
+        for (int t = 1; t <= T - 2; ++t) {
+            const double zr = zval(t, r);
+            const double other = (c < 8) ? zval(t, c) : X[(size_t)(t + 1) * 6 + (c - 8)];
+            acc += zr * other;
+        }
+        if (c < 8) {
+            if (r == c) acc += lamb;
+            S[r][c] = acc; S[c][r] = acc;
+        } else {
+            S[r][c] = acc;
+        }
+    }
+    __syncwarp();
+    bool ok = T >= 12;
+    for (int p = 0; p < 8; ++p) {
+        int piv = p;
+        double best = fabs(S[p][p]);
+        for (int r = p + 1; r < 8; ++r) { const double v = fabs(S[r][p]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0)) ok = false;
+        __syncwarp();
+        if (lane < 14 && piv != p) { const double t = S[p][lane]; S[p][lane] = S[piv][lane]; S[piv][lane] = t; }
+        __syncwarp();
+        const double inv = (S[p][p] != 0.0) ? 1.0 / S[p][p] : 0.0;
+        double f[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) f[r] = S[r][p] * inv;
+        const double prow = lane < 14 ? S[p][lane] : 0.0;
+        __syncwarp();
+        if (lane < 14 && lane > p) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (r != p) S[r][lane] -= f[r] * prow;     // Gauss-Jordan: eliminate above and below
+        }
+        __syncwarp();
+    }
+    // W[r][c] = S[r][8 + c] / S[r][r];  A = W'[:, 0:6] -> A[i][j] = W[j][i];  B[i][k] = W[6 + k][i]
+    double* out = abc + (size_t)b * 54;
+    for (int e = lane; e < 54; e += 32) {
+        double v = 0.0;
+        if (e < 36) { const int i = e / 6, j = e % 6; v = S[j][8 + i] / S[j][j]; }
+        else if (e < 48) { const int i = (e - 36) / 2, k = (e - 36) % 2; v = S[6 + k][8 + i] / S[6 + k][6 + k]; }
+        out[e] = v;
+    }
+    if (lane == 0 && !ok) atomicOr(&status[b], 1);
+}
+
+// Seed a controller from the closed-loop record the way main.py:99-110 does from the PID lap: the record is stored `copies`
+// times in the safe set (slots ss_slot0 ..) and in the regression model (slots model_slot0 ..), cost-to-go by computeCost,
+// xLin/uLin = rows 1..N+1 / 1..N of the lap (PC.py:432-433), zt = [0,0,0,0,10,0] (PC.py:330), OldInput = 0, timeStep = 0,
+// no previous prediction; the record restarts.  One CTA per instance.
+__global__ void __launch_bounds__(256) seed_from_record_kernel(int batch, LapPool ss, LapPool model, int copies, int ss_slot0, int model_slot0,
+                                                              const double* cl_x, const double* cl_u, int* cl_len, int Tcl, int N,
+                                                              double* xLin, double* uLin, double* zt, double* OldInput, int* timeStep,
+                                                              int* hasPred, int* done, double TrackLength) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int Trec = cl_len[b];
+    for (int c = 0; c < copies; ++c) {
+        {
+            const int T = min(Trec, ss.Tmax);
+            const size_t lap = ss.lap_index(b, ss_slot0 + c);
+            for (int e = threadIdx.x; e < T * 6; e += blockDim.x) ss.x[lap * ss.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
+            for (int e = threadIdx.x; e < T * 2; e += blockDim.x) ss.u[lap * ss.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
+            if (threadIdx.x == 0) ss.len[lap] = T;
+            __syncthreads();
+            lap_cost_block(ss, lap, TrackLength);
+        }
+        {
+            const int T = min(Trec, model.Tmax);
+            const size_t lap = model.lap_index(b, model_slot0 + c);
+            for (int e = threadIdx.x; e < T * 6; e += blockDim.x) model.x[lap * model.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
+            for (int e = threadIdx.x; e < T * 2; e += blockDim.x) model.u[lap * model.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
+            if (threadIdx.x == 0) model.len[lap] = T;
+        }
+    }
+    for (int e = threadIdx.x; e < (N + 1) * 6; e += blockDim.x) xLin[(size_t)b * (N + 1) * 6 + e] = cl_x[(size_t)b * Tcl * 6 + 6 + e];
+    for (int e = threadIdx.x; e < N * 2; e += blockDim.x) uLin[(size_t)b * N * 2 + e] = cl_u[(size_t)b * Tcl * 2 + 2 + e];
+    __syncthreads();
+    if (threadIdx.x < 6) zt[(size_t)b * 6 + threadIdx.x] = (threadIdx.x == 4) ? 10.0 : 0.0;
+    if (threadIdx.x < 2) OldInput[(size_t)b * 2 + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) { timeStep[b] = 0; hasPred[b] = 0; cl_len[b] = 0; done[b] = 0; }
 }
 
 }  // namespace lmpc

@@ -323,3 +323,82 @@ def test_pooled_lap_exchange_export_import(track):
     c.add_point(data["x0"], o["uPred"][:, 0])
     assert c.get_lap(2, 4)[0].shape[0] == own_latest[0].shape[0] + 1 and c.get_lap(2, 3)[0].shape[0] == T
     c.close()
+
+
+def test_device_pid_lap_sysid_lti_mpc_and_seeding(gold, track):
+    """main.py's seeding pipeline on the device against the oracle's restatement of Simulator.sim + PID
+    (SysModel.py:22-54, Utilities.py:42-68), Regression (Utilities.py:5-28), the LTI MPC lap (main.py:72-80) and the seeding of
+    LMPC + PredictiveModel with four copies of the PID lap (main.py:99-110) — same standard-normal draws on both sides."""
+    _need_gpu()
+    from oracle import vehicle, osqp_port, ftocp
+    N, K = 12, 300
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    c = BatchedController(par, 2, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points, numSS_it=numSS_it,
+                          QterminalSlack=Qts, Tmax=1536, ss_cap=6, model_cap=5)
+    c.enable_rollout(Tcl=1024)
+    x0 = np.array([0.5, 0, 0, 0, 0, 0.0])
+    c.rollout_set_state(np.tile(x0, (2, 1)), np.tile(x0, (2, 1)))
+    rng = np.random.default_rng(99)
+    zs = rng.standard_normal((2, K, 5))
+    for k in range(K):
+        c.rollout_pid_step(0.8, z_pid=zs[:, k, 0:2], z_sim=zs[:, k, 2:5])
+    done, n = c.rollout_done()
+    assert list(n) == [K, K]
+    laps, recs = [], []
+    for b in range(2):
+        it = iter(zs[b].ravel())
+        fake = type("R", (), {"standard_normal": lambda self, it=it: next(it)})()
+        xo, uo, _, _ = vehicle.closed_loop(track, [x0, x0], vehicle.PIDFollower(0.8, rng=fake), multi_lap=True, rng=fake, max_steps=K)
+        xg, ug = c.rollout_get_lap(b)
+        assert xg.shape == (K, 6) and np.max(np.abs(xg - xo)) < 1e-9 and np.max(np.abs(ug - uo)) < 1e-9, b
+        laps.append((xo, uo))
+        recs.append((xg, ug))
+    # ---- ridge system identification of each record
+    A, Bm, flags = c.rollout_sysid(1e-7)
+    assert np.all(flags == 0)
+    for b in range(2):
+        oA, oB, _ = vehicle.ridge_sysid(laps[b][0], laps[b][1], 1e-7)
+        assert np.max(np.abs(A[b] - oA)) < 1e-6 and np.max(np.abs(Bm[b] - oB)) < 1e-6, (np.max(np.abs(A[b] - oA)), np.max(np.abs(Bm[b] - oB)))
+    # ---- a few LTI-MPC closed-loop steps with the identified model (mode 2, main.py:72-80 with initMPCParams) against the
+    #      oracle controller holding the SAME model: a second controller with the MPC cost drives the same PID lap first
+    cm = BatchedController(rp.mpc_params(N), 2, track.seg_table(), track.TrackLength, trToUse=1, Tmax=1536, model_cap=2)
+    cm.enable_rollout(Tcl=1024)
+    cm.rollout_set_state(np.tile(x0, (2, 1)), np.tile(x0, (2, 1)))
+    for k in range(K):
+        cm.rollout_pid_step(0.8, z_pid=zs[:, k, 0:2], z_sim=zs[:, k, 2:5])
+    A2, B2, _ = cm.rollout_sysid(1e-7)
+    assert np.array_equal(A2, A) and np.array_equal(B2, Bm)
+    cm.rollout_set_state(np.tile(x0, (2, 1)), np.tile(x0, (2, 1)))
+    z2 = rng.standard_normal((2, 30, 3))
+    for k in range(30):
+        cm.rollout_step(z=z2[:, k], mode=2)
+    assert np.all(cm.step_results()["status"] == 1)
+    for b in range(2):
+        omp, _ = ftocp.mpc_params(6, 2, N, 0.8)
+        omp.A, omp.B = A[b], Bm[b]
+        it = iter(z2[b].ravel())
+        fake = type("R", (), {"standard_normal": lambda self, it=it: next(it)})()
+        xo, uo, _, _ = vehicle.closed_loop(track, [x0, x0], ftocp.OracleMPC(omp, qp=osqp_port.tight_qp), multi_lap=True, rng=fake, max_steps=30)
+        xg, ug = cm.rollout_get_lap(b)
+        assert xg.shape[0] == K + 30
+        assert np.max(np.abs(xg[K:] - xo)) < 1e-6 and np.max(np.abs(ug[K:] - uo)) < 1e-6, b
+    cm.close()
+    # ---- seeding: four copies of the PID record in both stores, controller state as LMPC.__init__/addTrajectory leave it
+    c.rollout_seed_from_record(n, copies=4)
+    assert c.it == [4, 4] and c.LapTime[0] == [K] * 4
+    for b in range(2):
+        for lapno in range(4):
+            xs_, us_, q_ = c.get_lap(b, lapno)
+            assert np.array_equal(xs_, recs[b][0]) and np.array_equal(us_, recs[b][1])      # the device record, bit for bit
+            assert np.array_equal(q_, ftocp.rollout_cost(recs[b][0], track.TrackLength))
+    st = c.get_state()
+    for b in range(2):
+        assert np.array_equal(st["xLin"][b], recs[b][0][1:N + 2]) and np.array_equal(st["uLin"][b], recs[b][1][1:N + 1])
+        assert np.array_equal(st["zt"][b], [0, 0, 0, 0, 10.0, 0]) and st["timeStep"][b] == 0
+    assert list(c.rollout_done()[1]) == [0, 0]
+    # and the first LMPC step from the start line solves with these stores
+    c.rollout_set_state(np.tile(x0, (2, 1)), np.tile(x0, (2, 1)))
+    c.rollout_step(z=np.zeros((2, 3)))
+    r = c.step_results()
+    assert np.all(r["status"] == 1) and np.all(r["flags"] == 0), (r["status"], r["flags"])
+    c.close()
