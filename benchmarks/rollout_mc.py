@@ -2,7 +2,7 @@
 """BASELINE.json configs[3]: LMPC Monte-Carlo rollouts sharded over the GPUs of one node, with the once-per-lap NCCL
 all-gather of finished laps (pooled-safe-set exchange).
 
-Every instance is an independent LMPC controller + vehicle (seeded PID laps as initial safe set, Philox process noise),
+Every instance is an independent LMPC controller + vehicle (its own PID lap as initial safe set, Philox process noise),
 advanced entirely on the device: K1 regression -> K2 selection -> QP -> shift -> addPoint -> dynModel per step.
 Lap ends are handled per instance (device-side lap hand-over, host only keeps the lap-time lists).
 
@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--share", type=int, default=2, help="pooled mode: globally fastest laps handed to every instance per exchange")
     ap.add_argument("--tpad", type=int, default=288, help="rows per exchanged lap (lap + addPoint overrun)")
     ap.add_argument("--ship-after", type=int, default=40, help="pooled mode: steps into the next lap before a lap is shipped")
+    ap.add_argument("--seed-laps", choices=["golden", "device"], default="device",
+                    help="golden: every instance is seeded with the reference's seed-0 PID lap (host upload); device: every "
+                         "instance drives its OWN 1000-step PID lap on the device (main.py:65-66, Philox noise) and is seeded from it")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -57,17 +60,29 @@ def main():
     c = BatchedController(par, B, workloads.track_seg_table(), rp.TRACK_LENGTH, trToUse=4, numSS_Points=numSS_Points,
                           numSS_it=numSS_it, QterminalSlack=Qts, device=local, Tmax=1280, ss_cap=7, model_cap=5)
     t0 = time.perf_counter()
-    for b in range(B):                       # main.py:102-110: four copies of the PID lap seed both stores
-        for _ in range(4):
-            c.model_add_trajectory(b, xP, uP)
-        for _ in range(4):
-            c.add_trajectory(b, xP, uP)
-    c.set_state(xLin=np.tile(xP[1:N + 2], (B, 1, 1)), uLin=np.tile(uP[1:N + 1], (B, 1, 1)),
-                zt=np.tile(np.array([0.0, 0, 0, 0, 10.0, 0]), (B, 1)), OldInput=np.zeros((B, 2)),
-                timeStep=np.zeros(B, np.int32), has_pred=np.zeros(B, np.int32))
-    setup_s = time.perf_counter() - t0
-    c.enable_rollout(Tcl=512)
     x0 = np.tile(np.array([0.5, 0, 0, 0, 0, 0.0]), (B, 1))
+    pid_s = 0.0
+    if args.seed_laps == "golden":
+        for b in range(B):                   # main.py:102-110: four copies of the PID lap seed both stores
+            for _ in range(4):
+                c.model_add_trajectory(b, xP, uP)
+            for _ in range(4):
+                c.add_trajectory(b, xP, uP)
+        c.set_state(xLin=np.tile(xP[1:N + 2], (B, 1, 1)), uLin=np.tile(uP[1:N + 1], (B, 1, 1)),
+                    zt=np.tile(np.array([0.0, 0, 0, 0, 10.0, 0]), (B, 1)), OldInput=np.zeros((B, 2)),
+                    timeStep=np.zeros(B, np.int32), has_pred=np.zeros(B, np.int32))
+        c.enable_rollout(Tcl=512)
+    else:
+        c.enable_rollout(Tcl=1024)
+        c.rollout_set_state(x0, x0)
+        tp = time.perf_counter()
+        for _ in range(1000):                # main.py:65-66: the PID lap is the full 100 s simulation
+            c.rollout_pid_step(0.8, seed=4321 + rank)
+        _, n = c.rollout_done()
+        c.rollout_seed_from_record(n, copies=4)
+        c.sync()
+        pid_s = time.perf_counter() - tp
+    setup_s = time.perf_counter() - t0
     c.rollout_set_state(x0, x0)
     stream = torch.cuda.ExternalStream(c.stream, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -147,7 +162,7 @@ def main():
                           "closed_loop_steps_rank0": steps, "ms_total": ms,
                           "controller_steps_per_s": B * steps_all / (ms * 1e-3),
                           "kernel_launches_rank0": int(launches), "lap_stats_rank0": stats,
-                          "host_lap_bookkeeping_s": host_s, "setup_s": setup_s,
+                          "host_lap_bookkeeping_s": host_s, "setup_s": setup_s, "seed_laps": args.seed_laps, "device_pid_laps_s": pid_s,
                           "exchanges": n_xchg, "exchange_s_total": xchg_s, "allgather_bytes_per_rank": xchg_bytes,
                           "laps_handed_out_rank0": took_total, "share": args.share, "ship_after": args.ship_after,
                           "instances_with_flags_rank0": int((flags_or != 0).sum()), "flag_bits_rank0": int(np.bitwise_or.reduce(flags_or)),

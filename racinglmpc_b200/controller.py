@@ -60,6 +60,11 @@ class BatchedController:
         self.own_laps = [[] for _ in range(self.B)]         # lap numbers of the laps the instance drove itself
         self._sel_dirty = True
         self._used_dirty = False
+        # device-side copies of the lap bookkeeping are rebuilt only for instances whose laps changed (None = all)
+        self._sel_rows, self._used_rows = None, None
+        nit = max(self.numSS_it, 1)
+        self._sel = np.zeros((self.B, nit), np.int32); self._isp = np.zeros((self.B, nit), np.int32)
+        self._prev = -np.ones(self.B, np.int32); self._used = np.zeros((self.B, self.trToUse), np.int32)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -83,7 +88,7 @@ class BatchedController:
         slot = self._model_slot_for(inst, x.shape[0])
         if slot >= 0:
             nat.check(self._lib.lmpc_model_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u)))
-        self._used_dirty = True          # usedIt is pushed once, before the next kernel that reads it
+        self._touch(inst, used=True)     # usedIt is pushed once, before the next kernel that reads it
 
     def _model_slot_for(self, inst, T):
         """Ordering rule of PredictiveModel.py:35-46 for a new lap of T rows; returns the device slot or -1 when the lap
@@ -105,16 +110,29 @@ class BatchedController:
             return self.model_book[inst].take(lapno)
         return -1
 
+    def _touch(self, inst, sel=False, used=False):
+        """Mark one instance's selection / usedIt rows as stale (rebuilt at the next _flush)."""
+        if sel:
+            self._sel_dirty = True
+            if self._sel_rows is not None:
+                self._sel_rows.add(int(inst))
+        if used:
+            self._used_dirty = True
+            if self._used_rows is not None:
+                self._used_rows.add(int(inst))
+
     def _push_used(self, inst=None):
         self._used_dirty = False
-        used = np.zeros((self.B, self.trToUse), np.int32)
-        for b in range(self.B):
+        rows = range(self.B) if self._used_rows is None else self._used_rows
+        used = self._used
+        for b in rows:
             laps = self.model_laps[b]
             for c in range(self.trToUse):
                 if c < len(laps) and laps[c][1] in self.model_book[b].slot_of:
                     used[b, c] = self.model_book[b].slot_of[laps[c][1]]
                 elif laps:
                     used[b, c] = self.model_book[b].slot_of.get(laps[min(c, len(laps) - 1)][1], 0)
+        self._used_rows = set()
         nat.check(self._lib.lmpc_model_set_used(self._h, nat.ptr(used)))
 
     # ------------------------------------------------------------------ LMPC.addTrajectory / addPoint
@@ -129,7 +147,7 @@ class BatchedController:
         nat.check(self._lib.lmpc_ss_put_lap(self._h, inst, slot, x.shape[0], nat.ptr(x), nat.ptr(u), nat.ptr(q)))
         first = (lapno == 0)
         self.it[inst] += 1
-        self._sel_dirty = True
+        self._touch(inst, sel=True)
         return first, slot
 
     def _ss_slot_for(self, inst, lap_time):
@@ -156,9 +174,9 @@ class BatchedController:
 
     def _push_selection(self):
         nit = max(self.numSS_it, 1)
-        sel = np.zeros((self.B, nit), np.int32); isp = np.zeros((self.B, nit), np.int32)
-        prev = -np.ones(self.B, np.int32)
-        for b in range(self.B):
+        sel, isp, prev = self._sel, self._isp, self._prev
+        rows = range(self.B) if self._sel_rows is None else self._sel_rows
+        for b in rows:
             if not self.LapTime[b]:
                 continue
             order = np.argsort(np.array(self.LapTime[b]), kind="stable")[:nit]     # PC.py:395,402
@@ -166,6 +184,7 @@ class BatchedController:
                 sel[b, c] = self.ss_book[b].slot_of[int(jj)]
                 isp[b, c] = 0 if int(jj) < self.it[b] - 1 else 1                    # PC.py:506
             prev[b] = self.ss_book[b].slot_of.get(self.it[b] - 1, -1)
+        self._sel_rows = set()
         nat.check(self._lib.lmpc_ss_set_selection(self._h, nat.ptr(sel), nat.ptr(isp), nat.ptr(prev)))
         self._sel_dirty = False
 
@@ -315,8 +334,8 @@ class BatchedController:
                 elif (sl, ms) != (ss0 + c, m0 + c):
                     raise RuntimeError("seeding needs consecutive free slots (fresh controller)")
         nat.check(self._lib.lmpc_rollout_seed_from_record(self._h, int(copies), int(max(ss0, 0)), int(m0)))
-        self._sel_dirty = True
-        self._used_dirty = True
+        self._sel_dirty = self._used_dirty = True
+        self._sel_rows = self._used_rows = None          # every instance changed
 
     def rollout_done(self):
         d = np.zeros(self.B, np.int32); n = np.zeros(self.B, np.int32)
@@ -350,10 +369,8 @@ class BatchedController:
             if self.lmpc:
                 self.it[b] += 1
         nat.check(self._lib.lmpc_rollout_commit_laps(self._h, nat.ptr(fin), nat.ptr(ss_slots), nat.ptr(m_slots)))
-        if len(finished):
-            self._sel_dirty = True
-            if to_model:
-                self._used_dirty = True
+        for b in finished:
+            self._touch(b, sel=self.lmpc, used=to_model)
         return finished
 
     def rollout_export_laps(self, Tpad, rows_dev, lens_dev):
@@ -411,8 +428,8 @@ class BatchedController:
         if len(took):
             nat.check(self._lib.lmpc_ss_import_laps_dev(self._h, nat.ptr(ss_slots), nat.ptr(m_slots) if to_model else None,
                                                         nat.ptr(use), n_src, int(Tpad), nat.ptr(rows_dev), nat.ptr(lens_dev)))
-            self._sel_dirty = True
-            self._used_dirty = self._used_dirty or to_model
+            for b in took:
+                self._touch(b, sel=True, used=to_model)
         return took
 
     def device_buffer(self, name):
