@@ -1,6 +1,7 @@
 """CPU tier: the CUDA solver core (racinglmpc_b200/csrc/ftocp_pdip.cuh) compiled as a 1-lane host
 emulation, against the reference-pinned golden solutions and the KKT checker.  This checks the
 kernel's arithmetic without a GPU; the warp-parallel execution itself is covered by the -m gpu tests."""
+import os
 import numpy as np
 import pytest
 import hostcore as hc
@@ -65,3 +66,23 @@ def test_horizon_sweep_workload(N):
         n = 6 * (N + 1)
         assert np.max(np.abs(sol["x"].ravel() - z[:n])) < 1e-6
         assert np.max(np.abs(sol["u"].ravel() - z[n:n + 2 * N])) < 1e-6
+
+
+def test_recentring_step_unsticks_boundary_riding_instances(track):
+    """Closed-loop LMPC QPs dumped from a device rollout (tools/scratch/dbg_rollout.py) on which the solver used to ride the
+    central-path neighbourhood boundary with tiny steps until max_iter (6 instances) or for 30+ iterations (2): with the
+    recentring pass (RECENTRE_AFTER) each is solved to 1e-9 in at most 20 iterations, and the NumPy model of the kernel
+    (oracle/pdip_model.py) agrees on the solution."""
+    from oracle import pdip_model as pm
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "stalled_lmpc_qps.npz"))
+    _, _, _, _, Qts, lp = ftocp.lmpc_params(track, 12)
+    c = hc.make_const(lp, Qts)
+    for i in range(8):
+        abc, x0, uold, SS, Qf = (d["q%d_%s" % (i, k)] for k in ("abc", "x0", "uold", "SS", "Qf"))
+        sol = hc.solve(c, 12, abc, x0, uold, SS, Qf)
+        assert sol["status"] == 1 and sol["iters"] <= 20, (i, sol["status"], sol["iters"])
+        assert max(sol["r_prim"], sol["r_dual"]) <= 1.000001e-9 and sol["gap"] <= 1.000001e-11
+        A = abc[:, 0:36].reshape(12, 6, 6); B = abc[:, 36:48].reshape(12, 6, 2); C = abc[:, 48:54]
+        ref = pm.solve(pm.from_params(lp, A, B, C, x0, uold, SS, Qf, Qts), eps=1e-9, eps_gap=1e-11, max_iter=40)
+        assert ref["status"] == 1
+        assert np.max(np.abs(sol["x"] - ref["x"])) < 1e-6 and np.max(np.abs(sol["u"] - ref["u"])) < 1e-6
