@@ -45,6 +45,17 @@ def _worker(rank, world, port, q):
         ok = ok and np.array_equal(best, np.argsort(Ts, kind="stable")[:4])
         m = sharding.max_over_ranks(10.0 + rank, torch.device("cpu"))
         ok = ok and (m == 10.0 + world - 1)
+        # the pooled exchange of benchmarks/rollout_mc.py: 9-column packed laps (x | u | Qfun) + lap times; every rank derives the
+        # same hand-out (the k globally fastest laps an instance does not own), ties to the lower global index
+        rows9 = torch.from_numpy(np.concatenate([rows, np.zeros(rows.shape[:2] + (1,))], axis=2))
+        times = torch.tensor([5, 3, 3] if rank == 0 else [3, 9, 2], dtype=torch.int32)
+        r9_all, _ = sharding.allgather_laps(rows9, torch.from_numpy(lens))
+        t_all = sharding.allgather_vec(times)
+        ok = ok and tuple(r9_all.shape) == (B, Tmax, 9) and t_all.tolist() == [5, 3, 3, 3, 9, 2]
+        best = [int(i) for i in sharding.pooled_fastest(t_all, 3)]
+        ok = ok and best == [5, 1, 2]                           # lap times 2, 3, 3 -> global instances 5, 1, 2 (tie: lower index)
+        mine = [[g for g in best if g != lo + b][:2] for b in range(hi - lo)]
+        ok = ok and (mine == ([[5, 1], [5, 2], [5, 1]] if rank == 0 else [[5, 1], [5, 1], [1, 2]]))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
