@@ -86,3 +86,74 @@ def test_recentring_step_unsticks_boundary_riding_instances(track):
         ref = pm.solve(pm.from_params(lp, A, B, C, x0, uold, SS, Qf, Qts), eps=1e-9, eps_gap=1e-11, max_iter=40)
         assert ref["status"] == 1
         assert np.max(np.abs(sol["x"] - ref["x"])) < 1e-6 and np.max(np.abs(sol["u"] - ref["u"])) < 1e-6
+
+
+def test_properties_on_perturbed_problems(gold):
+    """Solver-independent properties on randomly perturbed LTV-MPC problems (hypothesis): the returned point satisfies the KKT
+    conditions of the QP the oracle assembles with the reference's code path (1e-6), hard input bounds hold, lane slacks are
+    non-negative and equal max(0, violation) where they matter, and a solve is a pure function of its inputs."""
+    from hypothesis import given, settings, strategies as st
+    N = 12
+    _, ltv = ftocp.mpc_params(6, 2, N, 0.8)
+    ltv.timeVarying = True
+    c = hc.make_const(ltv)
+    k = "ltv_t20_"
+    A0, B0, C0 = gold[k + "A"], gold[k + "B"], gold[k + "C"]
+    F, bb = ftocp.build_ineq(ltv)
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(dx=st.lists(st.floats(-1, 1), min_size=6, max_size=6), du=st.lists(st.floats(-1, 1), min_size=2, max_size=2),
+           scale=st.floats(0.9, 1.1), ey=st.floats(-2.5, 2.5))
+    def run(dx, du, scale, ey):
+        x0 = gold[k + "x0"] + np.array(dx) * np.array([0.2, 0.05, 0.2, 0.05, 0.0, 0.1])
+        x0[5] = ey                                           # up to 0.5 outside the 2.0 lane half-width: soft constraint active
+        uold = np.clip(gold[k + "old"].ravel() + 0.2 * np.array(du), [-0.45, -9.0], [0.45, 9.0])
+        A, B, C = A0 * scale, B0, C0
+        sol = hc.solve(c, N, hc.pack_abc(A, B, C, N), x0, uold)
+        assert sol["status"] == 1 and sol["iters"] <= 30
+        again = hc.solve(c, N, hc.pack_abc(A, B, C, N), x0, uold)
+        assert np.array_equal(sol["x"], again["x"]) and np.array_equal(sol["u"], again["u"])
+        assert np.all(np.abs(sol["u"][:, 0]) <= 0.5 + 1e-9) and np.all(np.abs(sol["u"][:, 1]) <= 10.0 + 1e-9)
+        assert np.all(sol["s"] >= -1e-12)
+        viol = np.maximum(np.abs(sol["x"][:N, 5]) - 2.0, 0.0)
+        assert np.max(np.abs(sol["s"].reshape(N, 2).sum(axis=1) - viol)) < 1e-6       # slack = lane violation, nothing more
+        H, q = ftocp.build_cost(ltv, uold); G, E, L = ftocp.build_eq(ltv, list(A), list(B), list(C))
+        P, q, Am, l, u = ftocp.osqp_form(H, q, F, bb, G, E @ x0 + L)
+        z = np.concatenate([sol["x"].ravel(), sol["u"].ravel(), sol["s"].ravel()])
+        y = kkt.dual_from_primal(P, q, Am, l, u, z, tol=1e-6)
+        r = kkt.residuals(P, q, Am, l, u, z, y)
+        assert r["r_prim"] < 1e-6 and r["r_dual"] < 1e-6, r
+    run()
+
+
+def test_lmpc_properties_on_perturbed_problems(gold, track):
+    """LMPC-type QPs (simplex terminal block) around a golden step: lambda lies on the simplex, the terminal slack is what the
+    terminal equality says, and the point satisfies the KKT conditions of the oracle-assembled QP (reference code path)."""
+    from hypothesis import given, settings, strategies as st
+    N = 12
+    _, _, _, _, Qts, lp = ftocp.lmpc_params(track, N)
+    lp.timeVarying = True
+    c = hc.make_const(lp, Qts)
+    k = "lmpc_5_90_"
+    A, B, C, SS, Qf = gold[k + "A"], gold[k + "B"], gold[k + "C"], gold[k + "SS_sel"], gold[k + "Qfun_sel"]
+    F, bb = ftocp.build_ineq(lp)
+
+    @settings(max_examples=15, deadline=None, derandomize=True)
+    @given(dx=st.lists(st.floats(-1, 1), min_size=6, max_size=6), dq=st.lists(st.floats(0, 3), min_size=4, max_size=4))
+    def run(dx, dq):
+        x0 = gold[k + "x0"] + np.array(dx) * np.array([0.1, 0.03, 0.1, 0.03, 0.05, 0.05])
+        uold = gold[k + "OldInput"].ravel()
+        Q = Qf + np.repeat(np.array(dq), 12)                    # shift the cost-to-go of each selected lap
+        sol = hc.solve(c, N, hc.pack_abc(A, B, C, N), x0, uold, SS, Q)
+        assert sol["status"] == 1 and sol["iters"] <= 30
+        lam = sol["lam"]
+        assert lam.min() >= -1e-12 and abs(lam.sum() - 1.0) < 1e-8
+        xi = SS @ lam - sol["x"][-1]
+        G, E, L = ftocp.build_eq(lp, list(A), list(B), list(C)); H, q = ftocp.build_cost(lp, uold[None, :])
+        F2, b2, G2, E2, L2, H2, q2 = ftocp.add_safe_set(F, bb, G, E, L, H, q, 6, N, SS, Q, Qts)
+        P, qq, Am, l, u = ftocp.osqp_form(H2, q2, F2, b2, G2, E2 @ x0 + L2)
+        z = np.concatenate([sol["x"].ravel(), sol["u"].ravel(), sol["s"].ravel(), lam, xi])
+        y = kkt.dual_from_primal(P, qq, Am, l, u, z, tol=1e-6)
+        r = kkt.residuals(P, qq, Am, l, u, z, y)
+        assert r["r_prim"] < 1e-6 and r["r_dual"] < 1e-6, r
+    run()
