@@ -140,39 +140,43 @@ def cpu_model():
     return "unknown"
 
 
-def host_cores():
-    """Threads the CPU arm may use: the cores this process may run on, capped by the container's CPU quota.  NOT
-    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently turn the reference arm into
-    a single-core run.  LMPC_BENCH_THREADS overrides."""
-    if os.environ.get("LMPC_BENCH_THREADS"):
-        return max(1, int(os.environ["LMPC_BENCH_THREADS"]))
+def _affinity_and_quota():
     try:
-        n = len(os.sched_getaffinity(0))
+        a = len(os.sched_getaffinity(0))
     except AttributeError:
-        n = os.cpu_count() or 1
+        a = os.cpu_count() or 1
+    q = None
     try:                                                    # cgroup v2, then v1
-        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if q != "max":
-            n = min(n, max(1, int(np.ceil(int(q) / int(p)))))
+        qs, ps = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if qs != "max":
+            q = max(1, int(np.ceil(int(qs) / int(ps))))
     except (OSError, ValueError):
         try:
-            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
-            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
-            if q > 0:
-                n = min(n, max(1, int(np.ceil(q / p))))
+            qv = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            pv = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if qv > 0:
+                q = max(1, int(np.ceil(qv / pv)))
         except (OSError, ValueError):
             pass
-    return n
+    return a, q
 
 
 def best_oracle_threads(prob):
-    """The CPU arm gets its best configuration: all usable logical CPUs or one thread per physical core (half of them) --
-    whichever solves the sample faster (SMT siblings oversubscribe this fp64-bound solver on some hosts, measured 10x)."""
-    c = host_cores()
-    best, best_v = c, -1.0
-    for n in sorted({c, max(1, c // 2)}, reverse=True):
+    """The CPU arm gets its best configuration, found by measuring: the logical CPUs of the affinity mask, half and a quarter of
+    them (one thread per physical core / per two), and the container's CPU quota and half of it when one is set.  Deliberately
+    NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently make the reference arm
+    single-core -- and a fixed guess is wrong either way (measured on gpurun boxes: 128 SMT threads 16 k solves/s, 64 threads
+    150-175 k, a 32-CPU quota box 44 k at 16).  LMPC_BENCH_THREADS pins the count."""
+    if os.environ.get("LMPC_BENCH_THREADS"):
+        return max(1, int(os.environ["LMPC_BENCH_THREADS"]))
+    a, q = _affinity_and_quota()
+    cand = {a, max(1, a // 2), max(1, a // 4)}
+    if q:
+        cand |= {min(a, q), max(1, min(a, q) // 2)}
+    best, best_v = 1, -1.0
+    for n in sorted(cand, reverse=True):
         oracle_time(prob, n)
-        v = oracle_time(prob, n)[0]
+        v = max(oracle_time(prob, n)[0], oracle_time(prob, n)[0])
         if v > best_v:
             best, best_v = n, v
     return best
