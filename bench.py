@@ -351,7 +351,7 @@ def run_gpu(args):
                          "note": "latency-bound fp64 kernel by construction (SURVEY §8d): HBM fraction is tiny; see fp64_gflops",
                          "fp64_gflops": gflops, "algorithmic_bytes_per_solve": ALGO_BYTES_PER_SOLVE},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # the CPU leg is measured at N = 1 only (rank 0 has the host to itself)
             nsample = 1024
             prob = oracle_problem_set(nsample)
             cores = best_oracle_threads(prob)
