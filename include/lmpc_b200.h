@@ -241,6 +241,12 @@ int lmpc_ss_export_laps_dev(lmpc_handle* h, const int* slots_host, int Tpad, dou
 int lmpc_ss_import_laps_dev(lmpc_handle* h, const int* ss_slots_host, const int* model_slots_host, const int* src_host, int n_src,
                             int Tpad, const double* rows_dev, const int* lens_dev);
 
+/* fp64 micro-benchmarks on `device` (no reference counterpart; measurement support for the roofline of the QP kernel, which is
+ * bound by fp64 issue and dependent-chain latency rather than HBM): out8 = { DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s,
+ * latency in SM cycles of: DFMA, DMMA (accumulator chain), DMMA (result -> A operand), LDS (dependent), SHFL of a double,
+ * rsqrt(double) }. */
+int lmpc_probe_fp64(int device, double* out8);
+
 int lmpc_sizeof_params(void);
 int lmpc_sizeof_model_params(void);
 

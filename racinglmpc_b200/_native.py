@@ -98,6 +98,7 @@ def lib():
     L.lmpc_rollout_export_laps_dev.argtypes = [_vp, C.c_int, _vp, _vp]
     L.lmpc_ss_export_laps_dev.argtypes = [_vp, _vp, C.c_int, _vp, _vp]
     L.lmpc_ss_import_laps_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]
+    L.lmpc_probe_fp64.argtypes = [C.c_int, _vp]
     L.lmpc_sizeof_params.restype = C.c_int
     L.lmpc_sizeof_model_params.restype = C.c_int
     assert L.lmpc_sizeof_params() == C.sizeof(Params), "lmpc_params ABI mismatch"
@@ -127,6 +128,14 @@ def make_model_params(seg_table, TrackLength, trToUse, MaxNumPoint=7, h=5.0, lam
 def check(rc):
     if rc != 0:
         raise NativeError("liblmpc_b200 error %d: %s" % (rc, lib().lmpc_last_error().decode()))
+
+
+def probe_fp64(device=0):
+    """Measured fp64 numbers of the device (csrc/probe.cuh): the roofline denominators of the QP kernel."""
+    out = np.zeros(8)
+    check(lib().lmpc_probe_fp64(int(device), out.ctypes.data_as(_vp)))
+    keys = ("dfma_tflops", "dmma_tflops", "lat_dfma", "lat_dmma_acc", "lat_dmma_a", "lat_lds", "lat_shfl64", "lat_rsqrt")
+    return dict(zip(keys, (float(v) for v in out)))
 
 
 def exported_symbols():

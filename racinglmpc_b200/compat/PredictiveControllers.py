@@ -186,48 +186,61 @@ class LMPC(MPC):
         self.SSStoredPredTraj_it = []
         self.zt = np.array([0.0, 0.0, 0.0, 0.0, 10.0, 0.0])
         self.it = 0
+        self._grow = None
 
-    # PC.py:418-445
+    # ------------------------------------------------------------------ lap bookkeeping (host mirrors for main.py / plot.py)
     def addTrajectory(self, x, u, x_glob):
-        self.LapTime.append(x.shape[0])
-        self.SS.append(x)
-        self.SS_glob.append(x_glob)
-        self.uSS.append(u)
-        self.Qfun.append(self.computeCost(x, u))
+        """LMPC.addTrajectory (PC.py:418-445): the lap goes to the device store (which computes its own cost-to-go); the
+        host lists the reference exposes (SS, uSS, SS_glob, Qfun, LapTime, *StoredPredTraj) are mirrors for main.py:120,127
+        and plot.py."""
+        lap = self.it
+        for store, item in ((self.LapTime, x.shape[0]), (self.SS, x), (self.uSS, u), (self.SS_glob, x_glob),
+                            (self.Qfun, self.computeCost(x, u))):
+            store.append(item)
+        self._grow = None                                   # addPoint now extends this lap
         self._engine.add_trajectory(0, x, u)
-        if self.it == 0:
-            self.xLin = self.SS[self.it][1:self.N + 2, :]      # a view, as in the reference (PC.py:432)
-            self.uLin = self.uSS[self.it][1:self.N + 1, :]
-        self.xStoredPredTraj.append(self.xStoredPredTraj_it)
-        self.xStoredPredTraj_it = []
-        self.uStoredPredTraj.append(self.uStoredPredTraj_it)
-        self.uStoredPredTraj_it = []
-        self.SSStoredPredTraj.append(self.SSStoredPredTraj_it)
-        self.SSStoredPredTraj_it = []
-        self.it = self.it + 1
-        self.timeStep = 0
+        if lap == 0:                                        # PC.py:431-433: views of the stored lap, as in the reference
+            self.xLin, self.uLin = x[1:self.N + 2, :], u[1:self.N + 1, :]
+        for hist, cur in (("xStoredPredTraj", "xStoredPredTraj_it"), ("uStoredPredTraj", "uStoredPredTraj_it"),
+                          ("SSStoredPredTraj", "SSStoredPredTraj_it")):
+            getattr(self, hist).append(getattr(self, cur))
+            setattr(self, cur, [])
+        self.it, self.timeStep = lap + 1, 0
         self._state_dirty = True
 
-    # PC.py:447-464 (host mirror of the Q-function for `lmpc.Qfun[it][0]` / plotting; the device computes its own)
     def computeCost(self, x, u):
-        L = self.predictiveModel.map.TrackLength
-        T = x.shape[0]
-        Cost = 10000 * np.ones((T))
-        for i in range(0, T):
-            if (i == 0):
-                Cost[T - 1 - i] = 0
-            elif x[T - 1 - i, 4] < L:
-                Cost[T - 1 - i] = Cost[T - 1 - i + 1] + 1
-            else:
-                Cost[T - 1 - i] = 0
-        return Cost
+        """LMPC.computeCost (PC.py:447-464): steps until the finish line, counted backwards from the end of the lap and reset
+        to 0 on every row at/after the line.  Closed form: Q[j] = r(j) - j with r(j) the first row >= j that is the last row
+        or has s >= TrackLength -- the same rule the device uses (csrc/safeset.cuh lap_cost_block)."""
+        s = np.asarray(x)[:, 4]
+        T = s.shape[0]
+        rows = np.arange(T)
+        stop = ~(s < self.predictiveModel.map.TrackLength)
+        stop[-1] = True
+        nxt = np.minimum.accumulate(np.where(stop, rows, T)[::-1])[::-1]
+        return (nxt - rows).astype(float)
 
-    # PC.py:466-476
     def addPoint(self, x, u):
-        L = self.predictiveModel.map.TrackLength
-        self.SS[self.it - 1] = np.append(self.SS[self.it - 1], np.array([x + np.array([0, 0, 0, 0, L, 0])]), axis=0)
-        self.uSS[self.it - 1] = np.append(self.uSS[self.it - 1], np.array([u]), axis=0)
-        self.Qfun[self.it - 1] = np.append(self.Qfun[self.it - 1], self.Qfun[self.it - 1][-1] - 1)
+        """LMPC.addPoint (PC.py:466-476): the current (x, u), one track length further, extends lap it-1; its cost-to-go keeps
+        counting down past the finish line.  The device store appends in place; the host mirrors grow in amortised O(1)
+        buffers and SS/uSS/Qfun[it-1] are re-pointed at views of them (the reference re-allocates the whole lap every step)."""
+        j = self.it - 1
+        g = self._grow
+        if g is None or g["lap"] != j:
+            n0 = self.SS[j].shape[0]
+            cap = max(2 * n0, n0 + 256)
+            g = self._grow = dict(lap=j, n=n0, x=np.empty((cap, self.n)), u=np.empty((cap, self.d)), q=np.empty(cap))
+            g["x"][:n0], g["u"][:n0], g["q"][:n0] = self.SS[j], self.uSS[j], self.Qfun[j]
+        n0 = g["n"]
+        if n0 == g["q"].shape[0]:
+            for k in ("x", "u", "q"):
+                g[k] = np.concatenate((g[k], np.empty_like(g[k])), axis=0)
+        g["x"][n0] = x
+        g["x"][n0, 4] += self.predictiveModel.map.TrackLength
+        g["u"][n0] = u
+        g["q"][n0] = g["q"][n0 - 1] - 1
+        g["n"] = n0 + 1
+        self.SS[j], self.uSS[j], self.Qfun[j] = g["x"][:n0 + 1], g["u"][:n0 + 1], g["q"][:n0 + 1]
         self._engine.add_point(np.asarray(x, float), np.asarray(u, float))
 
     def _pre_solve(self, x0):

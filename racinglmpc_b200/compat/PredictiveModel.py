@@ -6,6 +6,8 @@ The object itself only stores laps (like the reference's lists); the k-NN regres
 (PredictiveModel.py:48-197) runs on the GPU inside the controller that owns the model
 (racinglmpc_b200/csrc/safeset.cuh, knn_ltv_regress_kernel).
 """
+import bisect
+
 import numpy as np
 
 
@@ -33,18 +35,12 @@ class PredictiveModel():
         self._added = []              # (x, u) in call order; controllers replay it into their device store
 
     def addTrajectory(self, x, u):
-        # same ordering rule as PredictiveModel.py:35-46 (kept so that .xStored/.uStored read the same)
-        if self.lapTime == [] or x.shape[0] >= self.lapTime[-1]:
-            self.xStored.append(x)
-            self.uStored.append(u)
-            self.lapTime.append(x.shape[0])
-        else:
-            for i in range(0, len(self.xStored)):
-                if x.shape[0] < self.lapTime[i]:
-                    self.xStored.insert(i, x)
-                    self.uStored.insert(i, u)
-                    self.lapTime.insert(i, x.shape[0])
-                    break
+        """PredictiveModel.addTrajectory (PredictiveModel.py:35-46): laps stay ordered by length, a new lap goes behind the
+        stored laps that are not longer than it -- so usedIt = [0..trToUse-1] always names the fastest laps."""
+        T = x.shape[0]
+        pos = bisect.bisect_right(self.lapTime, T)
+        for store, item in ((self.xStored, x), (self.uStored, u), (self.lapTime, T)):
+            store.insert(pos, item)
         self._added.append((x, u))
 
     def seg_table(self):
@@ -52,5 +48,25 @@ class PredictiveModel():
         return np.ascontiguousarray(np.asarray(self.map.PointAndTangent)[:, 3:6], dtype=float)
 
     def regressionAndLinearization(self, x, u):
-        raise NotImplementedError("racinglmpc_b200: the regression runs inside the GPU controller step "
-                                  "(MPC.solve / LMPC.solve); it is not available as a host call")
+        """PredictiveModel.regressionAndLinearization (PredictiveModel.py:48-139) for ONE point as a host call: runs the device
+        regression kernel (csrc/safeset.cuh knn_ltv_regress_kernel) on a private one-instance engine holding the stored
+        laps and returns (A 6x6, B 6x2, C 6).  Controllers do not use this -- their regression runs inside solve()."""
+        from racinglmpc_b200.controller import BatchedController
+        from racinglmpc_b200 import reference_params as rp
+        eng = getattr(self, "_probe_engine", None)
+        if eng is None:
+            eng = self._probe_engine = BatchedController(
+                rp.mpc_params(6), 1, self.seg_table(), self.map.TrackLength, trToUse=len(self.usedIt),
+                model_kwargs=dict(MaxNumPoint=self.MaxNumPoint, h=float(self.h), lamb=float(self.lamb), dt=float(self.dt),
+                                  scaling=tuple(np.diag(self.scaling))))
+            self._probe_seen = 0
+        while self._probe_seen < len(self._added):
+            eng.model_add_trajectory(0, *self._added[self._probe_seen])
+            self._probe_seen += 1
+        N = eng.N
+        eng.set_state(xLin=np.tile(np.asarray(x, float), (N + 1, 1)), uLin=np.tile(np.asarray(u, float), (N, 1)))
+        abc, flags = eng.identify()
+        if flags[0] & 1:
+            raise ArithmeticError("singular local regression (the reference's cvxopt call raises here too)")
+        rec = abc[0, 0]
+        return rec[0:36].reshape(6, 6).copy(), rec[36:48].reshape(6, 2).copy(), rec[48:54].copy()

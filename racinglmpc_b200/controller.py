@@ -179,6 +179,9 @@ class BatchedController:
         for b in rows:
             if not self.LapTime[b]:
                 continue
+            if len(self.LapTime[b]) < nit:
+                # the reference indexes sortedLapTime[0:numSS_it] lap by lap and raises IndexError here (PC.py:402-403)
+                raise IndexError("instance %d has %d stored laps, fewer than numSS_it = %d" % (b, len(self.LapTime[b]), nit))
             order = np.argsort(np.array(self.LapTime[b]), kind="stable")[:nit]     # PC.py:395,402
             for c, jj in enumerate(order):
                 sel[b, c] = self.ss_book[b].slot_of[int(jj)]

@@ -18,6 +18,7 @@
 #include "../../include/lmpc_b200.h"
 #include "ftocp_pdip.cuh"
 #include "safeset.cuh"
+#include "probe.cuh"
 
 using namespace lmpc;
 
@@ -192,7 +193,7 @@ struct lmpc_handle {
     bool has_store;
     ModelConst mc;
     LapPool ss, mdl;
-    int *d_used, *d_sel, *d_isprev, *d_prevslot, *d_timeStep, *d_hasPred, *d_flags, *d_minidx, *d_xchg, *d_health;
+    int *d_used, *d_sel, *d_isprev, *d_prevslot, *d_timeStep, *d_hasPred, *d_flags, *d_minidx, *d_xchg, *d_health, *d_dropped;
     double *d_xLin, *d_uLin, *d_ztState, *d_ztFixed, *d_OldInput, *d_xPredPrev, *d_tmpx, *d_tmpu;
     // device-resident closed loop (lmpc_rollout_create)
     bool has_rollout;
@@ -252,27 +253,89 @@ static int build_const(const lmpc_params& p, FtocpConst& c) {
 }
 
 template <int N, int M>
+static int configure_t(cudaStream_t) {
+    CK(cudaFuncSetAttribute(ftocp_kernel<N, M, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KernelSmem<N, M, 2, 4>)));
+    return LMPC_OK;
+}
+
+template <int N, int M>
 static int launch_t(lmpc_handle* h, const FtocpArgs& a, cudaStream_t st) {
     using KS = KernelSmem<N, M, 2, 4>;
-    auto kern = ftocp_kernel<N, M, 2, 4>;
-    static thread_local int configured_dev = -1;
-    if (configured_dev != h->device) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KS)));
-        configured_dev = h->device;
-    }
-    kern<<<a.batch, 32, sizeof(KS), st>>>(h->c, a);
+    ftocp_kernel<N, M, 2, 4><<<a.batch, 32, sizeof(KS), st>>>(h->c, a);
     CK(cudaGetLastError());
     h->launches += 1;
     return LMPC_OK;
 }
 
+// The supported (horizon, safe-set size) grid: one instantiation of the solver per pair.
+#define LMPC_FOR_EACH_CASE(X) \
+    X(6, 0) X(12, 0) X(14, 0) X(24, 0) X(48, 0) X(6, 48) X(12, 48) X(14, 48) X(24, 48) X(48, 48)
+
 static int launch(lmpc_handle* h, const FtocpArgs& a, bool lmpc_mode, cudaStream_t st) {
     const int N = h->N, M = lmpc_mode ? h->M : 0;
 #define LCASE(n, m) if (N == n && M == m) return launch_t<n, m>(h, a, st);
-    LCASE(6, 0) LCASE(12, 0) LCASE(14, 0) LCASE(24, 0) LCASE(48, 0)
-    LCASE(6, 48) LCASE(12, 48) LCASE(14, 48) LCASE(24, 48) LCASE(48, 48)
+    LMPC_FOR_EACH_CASE(LCASE)
 #undef LCASE
     return fail(LMPC_E_INVALID, "unsupported (N, numSS_Points): built for N in {6,12,14,24,48}, numSS_Points in {0,48}");
+}
+
+// Opt the kernels this handle can launch into their shared-memory size on the handle's device (the attribute is per device and
+// per function: done once per handle at creation, on its device, so handles on different devices never depend on each other).
+static int configure(int N, int M) {
+    int hit = 0, rc = LMPC_OK;
+#define CCASE(n, m) if (N == n && (m == 0 || m == M)) { ++hit; if (rc == LMPC_OK) rc = configure_t<n, m>(0); }
+    LMPC_FOR_EACH_CASE(CCASE)
+#undef CCASE
+    if (rc != LMPC_OK) return rc;
+    const bool have_m = (M == 0) || (hit == 2);
+    if (hit == 0 || !have_m)
+        return fail(LMPC_E_INVALID, "unsupported (N, numSS_Points): built for N in {6,12,14,24,48}, numSS_Points in {0,48}");
+    return LMPC_OK;
+}
+
+template <typename T>
+static void free_null(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static void free_store(lmpc_handle* h) {
+    free_null(h->ss.x); free_null(h->ss.u); free_null(h->ss.q); free_null(h->ss.len);
+    free_null(h->mdl.x); free_null(h->mdl.u); free_null(h->mdl.len);
+    free_null(h->d_used); free_null(h->d_sel); free_null(h->d_isprev); free_null(h->d_prevslot); free_null(h->d_timeStep);
+    free_null(h->d_hasPred); free_null(h->d_flags); free_null(h->d_minidx); free_null(h->d_xLin); free_null(h->d_uLin);
+    free_null(h->d_ztState); free_null(h->d_ztFixed); free_null(h->d_OldInput); free_null(h->d_xPredPrev); free_null(h->d_tmpx);
+    free_null(h->d_tmpu); free_null(h->d_xchg); free_null(h->d_dropped);
+    h->has_store = false;
+}
+
+static void free_rollout(lmpc_handle* h) {
+    for (int i = 0; i < 2; ++i) { free_null(h->d_rx[i]); free_null(h->d_rg[i]); }
+    free_null(h->d_clx); free_null(h->d_clu); free_null(h->d_z); free_null(h->d_zpid); free_null(h->d_abc_lti);
+    free_null(h->d_cllen); free_null(h->d_done); free_null(h->d_health);
+    h->has_rollout = false;
+}
+
+static void free_hb1(lmpc_handle* h) {
+    lmpc_handle::HostBufs& q = h->hb1;
+    free_null(q.x0); free_null(q.uOld); free_null(q.abc); free_null(q.SS); free_null(q.Qfun); free_null(q.SuccSS); free_null(q.SuccU);
+    free_null(q.xPred); free_null(q.uPred); free_null(q.slack); free_null(q.lambd); free_null(q.slackT); free_null(q.zt); free_null(q.ztu);
+    free_null(q.resid); free_null(q.status); free_null(q.iters);
+    h->has_hb1 = false;
+}
+
+static int create_device_side(lmpc_handle* h) {
+    CK(cudaSetDevice(h->device));
+    int rc = configure(h->N, h->M > 0 ? h->M : 0);
+    if (rc != LMPC_OK) return rc;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
+    const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
+#define DALLOC(ptr, count) CK(cudaMalloc((void**)&h->ptr, sizeof(*h->ptr) * (count)))
+    DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54);
+    DALLOC(d_SS, B * 6 * M); DALLOC(d_Qfun, B * M); DALLOC(d_SuccSS, B * 6 * M); DALLOC(d_SuccU, B * 2 * M);
+    DALLOC(d_xPred, B * (N + 1) * 6); DALLOC(d_uPred, B * N * 2); DALLOC(d_slack, B * N * 2);
+    DALLOC(d_lambd, B * M); DALLOC(d_slackT, B * 6); DALLOC(d_zt, B * 6); DALLOC(d_ztu, B * 2);
+    DALLOC(d_resid, B * 3); DALLOC(d_status, B); DALLOC(d_iters, B);
+#undef DALLOC
+    return LMPC_OK;
 }
 
 extern "C" {
@@ -306,18 +369,13 @@ int lmpc_create(const lmpc_params* p, int batch, int device, lmpc_handle** out) 
     h->N = p->N;
     h->M = p->numSS_Points;
     int rc = build_const(*p, h->c);
-    if (rc != LMPC_OK) { delete h; return rc; }
-    CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
-    const size_t B = batch, N = p->N, M = p->numSS_Points > 0 ? p->numSS_Points : 1;
-#define DALLOC(ptr, count) CK(cudaMalloc((void**)&h->ptr, sizeof(*h->ptr) * (count)))
-    DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54);
-    DALLOC(d_SS, B * 6 * M); DALLOC(d_Qfun, B * M); DALLOC(d_SuccSS, B * 6 * M); DALLOC(d_SuccU, B * 2 * M);
-    DALLOC(d_xPred, B * (N + 1) * 6); DALLOC(d_uPred, B * N * 2); DALLOC(d_slack, B * N * 2);
-    DALLOC(d_lambd, B * M); DALLOC(d_slackT, B * 6); DALLOC(d_zt, B * 6); DALLOC(d_ztu, B * 2);
-    DALLOC(d_resid, B * 3); DALLOC(d_status, B); DALLOC(d_iters, B);
-#undef DALLOC
+    if (rc == LMPC_OK) rc = create_device_side(h);
+    if (rc != LMPC_OK) {             // nothing of a half-built handle survives (zero-initialised: freeing what was never allocated is safe)
+        const std::string msg = g_err;
+        lmpc_destroy(h);
+        g_err = msg;
+        return rc;
+    }
     *out = h;
     return LMPC_OK;
 }
@@ -325,29 +383,19 @@ int lmpc_create(const lmpc_params* p, int batch, int device, lmpc_handle** out) 
 int lmpc_destroy(lmpc_handle* h) {
     if (!h) return LMPC_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    if (h->has_rollout) {
-        void* rp[] = {h->d_rx[0], h->d_rx[1], h->d_rg[0], h->d_rg[1], h->d_clx, h->d_clu, h->d_z, h->d_zpid, h->d_abc_lti, h->d_cllen, h->d_done, h->d_health};
-        for (void* q : rp) cudaFree(q);
-    }
-    if (h->has_store) {
-        void* ptrs[] = {h->ss.x, h->ss.u, h->ss.q, h->ss.len, h->mdl.x, h->mdl.u, h->mdl.len, h->d_used, h->d_sel, h->d_isprev,
-                        h->d_prevslot, h->d_timeStep, h->d_hasPred, h->d_flags, h->d_minidx, h->d_xLin, h->d_uLin, h->d_ztState,
-                        h->d_ztFixed, h->d_OldInput, h->d_xPredPrev, h->d_tmpx, h->d_tmpu, h->d_xchg};
-        for (void* q : ptrs) cudaFree(q);
-    }
-    if (h->has_hb1) {
-        void* q1[] = {h->hb1.x0, h->hb1.uOld, h->hb1.abc, h->hb1.SS, h->hb1.Qfun, h->hb1.SuccSS, h->hb1.SuccU, h->hb1.xPred, h->hb1.uPred,
-                      h->hb1.slack, h->hb1.lambd, h->hb1.slackT, h->hb1.zt, h->hb1.ztu, h->hb1.resid, h->hb1.status, h->hb1.iters};
-        for (void* q : q1) cudaFree(q);
-    }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 8; ++i) if (h->cstream[i]) cudaStreamSynchronize(h->cstream[i]);
+    // every pointer freed here is either a live allocation or still null (handle memory is zero-initialised)
+    free_rollout(h);
+    free_store(h);
+    free_hb1(h);
     double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
                      h->d_slack, h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid};
     for (double* q : dbl) cudaFree(q);
     cudaFree(h->d_status);
     cudaFree(h->d_iters);
-    cudaStreamDestroy(h->stream);
-    for (int i = 0; i < 8; ++i) cudaStreamDestroy(h->cstream[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 8; ++i) if (h->cstream[i]) cudaStreamDestroy(h->cstream[i]);
     delete h;
     return LMPC_OK;
 }
@@ -404,7 +452,8 @@ static int host_bufs(lmpc_handle* h, int slot, lmpc_handle::HostBufs& b) {
     if (!h->has_hb1) {
         const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
         lmpc_handle::HostBufs& q = h->hb1;
-#define DA1(ptr, count) CK(cudaMalloc((void**)&q.ptr, sizeof(*q.ptr) * (count)))
+#define DA1(ptr, count) do { if (cudaMalloc((void**)&q.ptr, sizeof(*q.ptr) * (count)) != cudaSuccess) { free_hb1(h); \
+                              return fail(LMPC_E_CUDA, "cudaMalloc of the second host-path buffer set failed"); } } while (0)
         DA1(x0, B * 6); DA1(uOld, B * 2); DA1(abc, B * N * 54);
         DA1(SS, B * 6 * M); DA1(Qfun, B * M); DA1(SuccSS, B * 6 * M); DA1(SuccU, B * 2 * M);
         DA1(xPred, B * (N + 1) * 6); DA1(uPred, B * N * 2); DA1(slack, B * N * 2);
@@ -418,7 +467,7 @@ static int host_bufs(lmpc_handle* h, int slot, lmpc_handle::HostBufs& b) {
 }
 
 // Enqueue one host-buffer solve on buffer set / stream group `slot` (0 or 1) WITHOUT waiting for it.
-static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
+static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
                               long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel,
                               const double* Succ_SS, const double* Succ_uSS, double* xPred, double* uPred, double* slack,
                               double* lambd, double* slackTerminal, double* zt, double* zt_u, int* status, int* iters,
@@ -501,6 +550,24 @@ static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const 
 }
 
 
+// Enqueue one host-buffer solve; on ANY failure part-way through, the chunks already enqueued are still copying into the
+// caller's arrays, so their streams are drained before the error is reported.
+static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
+                              long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel,
+                              const double* Succ_SS, const double* Succ_uSS, double* xPred, double* uPred, double* slack,
+                              double* lambd, double* slackTerminal, double* zt, double* zt_u, int* status, int* iters,
+                              double* resid) {
+    const int rc = enqueue_host_solve_impl(h, slot, x0, uOld, abc, abc_inst_stride, abc_stage_stride, SS_sel, Qfun_sel, Succ_SS, Succ_uSS,
+                                           xPred, uPred, slack, lambd, slackTerminal, zt, zt_u, status, iters, resid);
+    if (rc != LMPC_OK && h && slot >= 0 && slot <= 1) {
+        const std::string msg = g_err;
+        for (int i = 0; i < 4; ++i) cudaStreamSynchronize(h->cstream[4 * slot + i]);
+        g_err = msg;
+    }
+    return rc;
+}
+
+
 int lmpc_host_wait(lmpc_handle* h, int slot) {
     if (!h || slot < 0 || slot > 1) return fail(LMPC_E_INVALID, "bad handle or slot");
     CK(cudaSetDevice(h->device));
@@ -557,7 +624,14 @@ int lmpc_solve_mpc_host(lmpc_handle* h, const double* x0, const double* uOld, co
 int lmpc_sizeof_params(void) { return (int)sizeof(lmpc_params); }
 int lmpc_sizeof_model_params(void) { return (int)sizeof(lmpc_model_params); }
 
+static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, int model_cap, int Tmax);
 int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, int model_cap, int Tmax) {
+    const int rc = store_create_impl(h, mp, ss_cap, model_cap, Tmax);
+    if (rc != LMPC_OK && h && !h->has_store) { const std::string msg = g_err; free_store(h); g_err = msg; }   // no partial store
+    return rc;
+}
+}  // extern "C" (the helper below has C++ linkage)
+static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, int model_cap, int Tmax) {
     if (!h || !mp || ss_cap < 0 || model_cap <= 0 || Tmax < 16) return fail(LMPC_E_INVALID, "bad store arguments");
     if (h->has_store) return fail(LMPC_E_STATE, "store already created");
     if (mp->trToUse < 1 || mp->trToUse > K1_MAXLAPS || mp->trToUse > model_cap) return fail(LMPC_E_INVALID, "trToUse out of range");
@@ -569,6 +643,8 @@ int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, i
         if (ss_cap < h->p.numSS_it) return fail(LMPC_E_INVALID, "ss_cap < numSS_it");
     }
     CK(cudaSetDevice(h->device));
+    CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ModelConst& m = h->mc;
     memset(&m, 0, sizeof(m));
     m.trToUse = mp->trToUse; m.MaxNumPoint = mp->MaxNumPoint; m.h = mp->h; m.lamb = mp->lamb; m.dt = mp->dt;
@@ -588,8 +664,9 @@ int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, i
     DA(h->d_timeStep, int, B); DA(h->d_hasPred, int, B); DA(h->d_flags, int, B); DA(h->d_minidx, int, B * 8);
     DA(h->d_xLin, double, B * (N + 1) * 6); DA(h->d_uLin, double, B * N * 2); DA(h->d_ztState, double, B * 6);
     DA(h->d_ztFixed, double, B * 6); DA(h->d_OldInput, double, B * 2); DA(h->d_xPredPrev, double, B * (N + 1) * 6);
-    DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2); DA(h->d_xchg, int, B * 3);
+    DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2); DA(h->d_xchg, int, B * 3); DA(h->d_dropped, int, 1);
 #undef DA
+    CK(cudaMemsetAsync(h->d_dropped, 0, sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->ss.len, 0, sizeof(int) * B * h->ss.cap, h->stream));
     CK(cudaMemsetAsync(h->mdl.len, 0, sizeof(int) * B * model_cap, h->stream));
     CK(cudaMemsetAsync(h->d_used, 0, sizeof(int) * B * K1_MAXLAPS, h->stream));
@@ -606,6 +683,7 @@ int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, i
     h->has_store = true;
     return LMPC_OK;
 }
+extern "C" {
 
 static int need_store(lmpc_handle* h) {
     if (!h) return fail(LMPC_E_INVALID, "null handle");
@@ -685,10 +763,16 @@ int lmpc_ss_add_point(lmpc_handle* h, const double* x, const double* u) {
     CK(cudaMemcpyAsync(h->d_tmpx, x, sizeof(double) * h->batch * 6, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_tmpu, u, sizeof(double) * h->batch * 2, cudaMemcpyHostToDevice, h->stream));
     ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, h->d_tmpx, h->d_tmpu, 2,
-                                                                        h->mc.TrackLength, h->d_flags);
+                                                                        h->mc.TrackLength, h->d_flags, h->d_dropped);
     CK(cudaGetLastError());
     h->launches += 1;
+    int dropped = 0;
+    CK(cudaMemcpyAsync(&dropped, h->d_dropped, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (dropped) {      // the reference's lists grow without bound (PC.py:466-476); a full slot must not pass silently
+        CK(cudaMemsetAsync(h->d_dropped, 0, sizeof(int), h->stream));
+        return fail(LMPC_E_STATE, "addPoint: " + std::to_string(dropped) + " safe-set lap(s) reached Tmax rows; create the store with a larger Tmax");
+    }
     return LMPC_OK;
 }
 
@@ -762,12 +846,6 @@ static int launch_k1(lmpc_handle* h) {
     a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
     dim3 grid(h->batch, (h->N + a.wpb - 1) / a.wpb);
     size_t smem = sizeof(double) * ((size_t)5 * K1_TILE + (size_t)a.pts_stride * a.wpb);
-    static thread_local int cfg_dev = -1;
-    if (cfg_dev != h->device) {
-        CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CK(cudaFuncSetAttribute(knn_ltv_regress_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        cfg_dev = h->device;
-    }
     knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, h->stream>>>(h->mc, a);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -912,7 +990,14 @@ void* lmpc_device_buffer(lmpc_handle* h, const char* name) {
 // ================================================================================================
 // device-resident closed loop: Simulator.sim's loop body (SysModel.py:33-48) without host round trips
 // ================================================================================================
+static int rollout_create_impl(lmpc_handle* h, int Tcl);
 int lmpc_rollout_create(lmpc_handle* h, int Tcl) {
+    const int rc = rollout_create_impl(h, Tcl);
+    if (rc != LMPC_OK && h && !h->has_rollout) { const std::string msg = g_err; free_rollout(h); g_err = msg; }
+    return rc;
+}
+}  // extern "C"
+static int rollout_create_impl(lmpc_handle* h, int Tcl) {
     int rc = need_store(h);
     if (rc) return rc;
     if (h->has_rollout) return fail(LMPC_E_STATE, "rollout buffers already created");
@@ -939,6 +1024,7 @@ int lmpc_rollout_create(lmpc_handle* h, int Tcl) {
     h->Tcl = Tcl; h->cur = 0; h->sim_step = 0; h->has_rollout = true;
     return LMPC_OK;
 }
+extern "C" {
 
 static int need_rollout(lmpc_handle* h) {
     int rc = need_store(h);
@@ -1000,7 +1086,7 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
     if (rc) return rc;
     if (mode == 1) {
         ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, xc, h->d_uPred,
-                                                                            (long long)h->N * 2, h->mc.TrackLength, h->d_flags);
+                                                                            (long long)h->N * 2, h->mc.TrackLength, h->d_flags, nullptr);
         CK(cudaGetLastError());
         h->launches += 1;
     }
@@ -1192,6 +1278,55 @@ int lmpc_ss_import_laps_dev(lmpc_handle* h, const int* ss_slots, const int* mode
     CK(cudaGetLastError());
     h->launches += 1;
     CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+// ================================================================================================
+// fp64 micro-benchmarks (probe.cuh): the measured denominators of the QP kernel's roofline
+// ================================================================================================
+int lmpc_probe_fp64(int device, double* out8) {
+    if (!out8) return fail(LMPC_E_INVALID, "null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LMPC_E_NODEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(LMPC_E_INVALID, "bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double *d_out = nullptr, *d_lat = nullptr;
+    CK(cudaMalloc((void**)&d_out, sizeof(double) * (size_t)blocks * threads));
+    CK(cudaMalloc((void**)&d_lat, sizeof(double) * 64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms = 0.f;
+    double best_dfma = 0.0, best_dmma = 0.0;
+    const int it_f = 8192, it_m = 2048;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        probe_dfma_tput<<<blocks, threads>>>(d_out, it_f, 1.0 + rep);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * it_f * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best_dfma) best_dfma = tf;
+        CK(cudaEventRecord(e0));
+        probe_dmma_tput<<<blocks, threads>>>(d_out, it_m, 1.0 + rep);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tm = 2.0 * 256.0 * 4.0 * it_m * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tm > best_dmma) best_dmma = tm;
+    }
+    probe_latency<<<1, 32>>>(d_lat, d_lat + 8, 4096);
+    probe_latency<<<1, 32>>>(d_lat, d_lat + 8, 4096);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    double lat[6];
+    CK(cudaMemcpy(lat, d_lat, sizeof(lat), cudaMemcpyDeviceToHost));
+    out8[0] = best_dfma; out8[1] = best_dmma;
+    for (int i = 0; i < 6; ++i) out8[2 + i] = lat[i];
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out); cudaFree(d_lat);
     return LMPC_OK;
 }
 

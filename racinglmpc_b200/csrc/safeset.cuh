@@ -35,7 +35,10 @@ struct LapPool {
 };
 
 // Track.py:292-310 — wrap by repeated subtraction, first segment with s in [s0, s0+len)
+// (a non-finite or absurdly large s -- an unsolved QP feeding garbage to the simulator -- would spin forever in the
+// reference's loop; here it fails the lookup like a negative s does, so the instance is flagged instead of hanging the stream)
 __device__ __forceinline__ double curvature_lookup(const ModelConst& m, double s, int* ok) {
+    if (!(s <= 64.0 * m.TrackLength)) { *ok = 0; return 0.0; }
     while (s > m.TrackLength) s = s - m.TrackLength;
     for (int i = 0; i < m.nseg; ++i) {
         double s0 = m.seg[i * 3], ln = m.seg[i * 3 + 1];
@@ -544,14 +547,18 @@ __global__ void __launch_bounds__(32 * 8) ss_select_kernel(const K2Args a) {
 // ------------------------------------------------------------------------------------------------
 // LMPC.addPoint (PC.py:466-476): append x + [0,0,0,0,L,0], u to lap it-1; Qfun extends by last - 1.
 __global__ void ss_add_point_kernel(int batch, LapPool pool, const int* prev_slot, const double* x, const double* u,
-                                    long long u_stride, double TrackLength, int* status) {
+                                    long long u_stride, double TrackLength, int* status, int* dropped) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const int slot = prev_slot[b];
     if (slot < 0) return;
     const size_t lap = pool.lap_index(b, slot);
     const int T = pool.len[lap];
-    if (T >= pool.Tmax || T < 1) { atomicOr(&status[b], 16); return; }
+    if (T >= pool.Tmax || T < 1) {       // the lap cannot grow (the reference would keep appending): flag it, count it
+        atomicOr(&status[b], 16);
+        if (dropped) atomicAdd(dropped, 1);
+        return;
+    }
     double* X = pool.x + (lap * pool.Tmax + T) * 6;
     double* U = pool.u + (lap * pool.Tmax + T) * 2;
     double* Q = pool.q + lap * pool.Tmax;
