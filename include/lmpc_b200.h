@@ -79,6 +79,10 @@ int lmpc_destroy(lmpc_handle* h);
 int lmpc_sync(lmpc_handle* h);
 void* lmpc_stream(lmpc_handle* h);            /* cudaStream_t the handle enqueues on */
 long long lmpc_kernel_launches(lmpc_handle* h); /* kernels launched by this handle so far */
+/* Number of QPs (since lmpc_create) that were reported LMPC_ST_SOLVED by the late-acceptance safety net of the interior-point
+ * loop -- residuals and gap <= 1e-6 at iteration >= 20 / at max_iter -- instead of at eps_res / eps_gap (see lmpc_params).
+ * Synchronises the handle's streams; -1 on error.  0 on every recorded BASELINE workload (tests assert it). */
+long long lmpc_late_accepts(lmpc_handle* h);
 
 /* ---- FTOCP solve with the model given by the caller ("fixed A/B/C") ---------------------------------
  * Replaces, per instance: buildCost + buildEqConstr + addTerminalComponents + osqp_solve_qp +

@@ -57,6 +57,8 @@ def lib():
     L.lmpc_stream.restype = _vp
     L.lmpc_kernel_launches.argtypes = [_vp]
     L.lmpc_kernel_launches.restype = C.c_longlong
+    L.lmpc_late_accepts.argtypes = [_vp]
+    L.lmpc_late_accepts.restype = C.c_longlong
     ll = C.c_longlong
     for name in ("lmpc_solve_mpc_host", "lmpc_solve_mpc_dev"):
         getattr(L, name).argtypes = [_vp, _vp, _vp, _vp, ll, ll, _vp, _vp, _vp, _vp, _vp, _vp]

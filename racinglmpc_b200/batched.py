@@ -53,6 +53,11 @@ class BatchedFTOCP:
     def kernel_launches(self):
         return int(self._lib.lmpc_kernel_launches(self._h))
 
+    @property
+    def late_accepts(self):
+        """QPs accepted at the 1e-6 safety-net tolerance instead of eps_res / eps_gap since creation (expected 0)."""
+        return int(self._lib.lmpc_late_accepts(self._h))
+
     def sync(self):
         nat.check(self._lib.lmpc_sync(self._h))
 

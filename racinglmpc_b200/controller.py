@@ -81,6 +81,11 @@ class BatchedController:
     def kernel_launches(self):
         return int(self._lib.lmpc_kernel_launches(self._h))
 
+    @property
+    def late_accepts(self):
+        """QPs accepted at the 1e-6 safety-net tolerance instead of eps_res / eps_gap since creation (expected 0)."""
+        return int(self._lib.lmpc_late_accepts(self._h))
+
     # ------------------------------------------------------------------ PredictiveModel.addTrajectory
     def model_add_trajectory(self, inst, x, u):
         """PredictiveModel.py:35-46: keep laps sorted by length; only the trToUse fastest are ever read."""

@@ -169,6 +169,7 @@ constexpr int RECENTRE_AFTER = 3;   // step reductions before the corrector is r
 
 struct SolveInfo {
     int status, iters;
+    int late;            // 1 = reported solved by the late-acceptance safety net (1e-6 contract), not at eps_res / eps_gap
     double r_prim, r_dual, gap;
 };
 
@@ -747,7 +748,7 @@ struct Pdip {
         wsync();
         init_point(w, g, c, x0);
         const double n_ineq = (double)(2 * R1 + R2 + (LMPC ? M : 0));
-        int it = 0, status = ST_MAX_ITER;
+        int it = 0, status = ST_MAX_ITER, late = 0;
         double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0;
         const double d4_floor = c.d4_min;
 
@@ -816,6 +817,7 @@ struct Pdip {
                 // Once the iterate meets the 1e-6 parity contract, stop after LATE_ACCEPT_IT iterations (and at max_iter).
                 if ((it >= LATE_ACCEPT_IT || it >= c.max_iter) && r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) {
                     status = ST_SOLVED;
+                    late = 1;
                     break;
                 }
                 if (it >= c.max_iter) { status = ST_MAX_ITER; break; }
@@ -832,7 +834,10 @@ struct Pdip {
             r_dual = fmax(rd_loc, ru_max);
             if (w.flag != 0) { status = w.flag; break; }
             if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap) { status = ST_SOLVED; break; }
-            if (it >= c.max_iter) { status = (r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) ? ST_SOLVED : ST_MAX_ITER; break; }
+            if (it >= c.max_iter) {
+                if (r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) { status = ST_SOLVED; late = 1; } else { status = ST_MAX_ITER; }
+                break;
+            }
 
             // ---- predictor -----------------------------------------------------------------------
             forward(w);
@@ -1030,6 +1035,7 @@ struct Pdip {
         r_prim = fmax(r_prim, wmax(rdyn));
         info.status = status;
         info.iters = it;
+        info.late = late;
         info.r_prim = r_prim;
         info.r_dual = r_dual;
         info.gap = mu;

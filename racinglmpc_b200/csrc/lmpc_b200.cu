@@ -72,6 +72,7 @@ struct FtocpArgs {
     int* status;
     int* iters;
     double* resid;        // [B,3]
+    unsigned long long* late;   // counter of instances accepted by the late-acceptance rule (ftocp_pdip.cuh), or null
 };
 
 template <int N, int M, int NCX, int NCU>
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 12 : 16) : 1)) ftocp_k
         a.resid[(long long)b * 3 + 0] = info.r_prim;
         a.resid[(long long)b * 3 + 1] = info.r_dual;
         a.resid[(long long)b * 3 + 2] = info.gap;
+        if (info.late && a.late) atomicAdd(a.late, 1ull);
     }
 }
 
@@ -183,6 +185,7 @@ struct lmpc_handle {
     double *d_x0, *d_uOld, *d_abc, *d_SS, *d_Qfun, *d_SuccSS, *d_SuccU;
     double *d_xPred, *d_uPred, *d_slack, *d_lambd, *d_slackT, *d_zt, *d_ztu, *d_resid;
     int *d_status, *d_iters;
+    unsigned long long* d_late;
     // second buffer set of the asynchronous host entry points (slot 1; allocated on first use)
     struct HostBufs {
         double *x0, *uOld, *abc, *SS, *Qfun, *SuccSS, *SuccU, *xPred, *uPred, *slack, *lambd, *slackT, *zt, *ztu, *resid;
@@ -333,8 +336,9 @@ static int create_device_side(lmpc_handle* h) {
     DALLOC(d_SS, B * 6 * M); DALLOC(d_Qfun, B * M); DALLOC(d_SuccSS, B * 6 * M); DALLOC(d_SuccU, B * 2 * M);
     DALLOC(d_xPred, B * (N + 1) * 6); DALLOC(d_uPred, B * N * 2); DALLOC(d_slack, B * N * 2);
     DALLOC(d_lambd, B * M); DALLOC(d_slackT, B * 6); DALLOC(d_zt, B * 6); DALLOC(d_ztu, B * 2);
-    DALLOC(d_resid, B * 3); DALLOC(d_status, B); DALLOC(d_iters, B);
+    DALLOC(d_resid, B * 3); DALLOC(d_status, B); DALLOC(d_iters, B); DALLOC(d_late, 1);
 #undef DALLOC
+    CK(cudaMemset(h->d_late, 0, sizeof(unsigned long long)));
     return LMPC_OK;
 }
 
@@ -394,6 +398,7 @@ int lmpc_destroy(lmpc_handle* h) {
     for (double* q : dbl) cudaFree(q);
     cudaFree(h->d_status);
     cudaFree(h->d_iters);
+    cudaFree(h->d_late);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 8; ++i) if (h->cstream[i]) cudaStreamDestroy(h->cstream[i]);
     delete h;
@@ -407,6 +412,16 @@ int lmpc_sync(lmpc_handle* h) {
 }
 
 void* lmpc_stream(lmpc_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+long long lmpc_late_accepts(lmpc_handle* h) {
+    if (!h) return -1;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+    unsigned long long v = 0;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    for (int i = 0; i < 8; ++i) if (cudaStreamSynchronize(h->cstream[i]) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, h->d_late, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long long)v;
+}
 long long lmpc_kernel_launches(lmpc_handle* h) { return h ? h->launches : 0; }
 
 static int check_align(const void* p, const char* what) {
@@ -433,6 +448,7 @@ int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, co
     a.SS = SS_sel; a.Qfun = Qfun_sel; a.SuccSS = Succ_SS; a.SuccU = Succ_uSS;
     a.xPred = xPred; a.uPred = uPred; a.slack = slack; a.lambd = lambd; a.slackT = slackTerminal;
     a.zt = zt; a.ztu = zt_u; a.status = status; a.iters = iters; a.resid = resid;
+    a.late = h->d_late;
     return launch(h, a, lm, h->stream);
 }
 
@@ -529,6 +545,7 @@ static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, c
         a.slackT = (lm && slackTerminal) ? hb.slackT + lo * 6 : nullptr;
         a.zt = (lm && zt) ? hb.zt + lo * 6 : nullptr; a.ztu = (lm && zt_u) ? hb.ztu + lo * 2 : nullptr;
         a.status = hb.status + lo; a.iters = hb.iters + lo; a.resid = hb.resid + lo * 3;
+        a.late = h->d_late;
         if (trace) cudaEventRecord(h->tev[ci][0], s);
         int rc = launch(h, a, lm, s);
         if (rc != LMPC_OK) return rc;
