@@ -33,6 +33,15 @@
 #define LMPC_HD inline
 #endif
 
+// Device formulation of the Riccati sweeps: fp64 tensor-core fragments (mma.sync.m8n8k4.f64, "DMMA") when compiled by nvcc,
+// the scalar shared-memory formulation on the host (tests/support/host_core.cpp) or with -DLMPC_NO_MMA (A/B measurements).
+// The choice changes the layout of Work<>, so it must not depend on __CUDA_ARCH__ (host and device passes of one TU agree).
+#if defined(__CUDACC__) && !defined(LMPC_NO_MMA)
+#define LMPC_MMA 1
+#else
+#define LMPC_MMA 0
+#endif
+
 namespace lmpc {
 
 // ------------------------------------------------------------------------------------------
@@ -72,6 +81,14 @@ inline double wmax(double v) { return v; }
 #define FOR_LANES(e, n) for (int e = LMPC_LANE; e < (n); e += LMPC_NLANE)
 #endif
 #define NSLOT(CNT) (((CNT) + LMPC_NLANE - 1) / LMPC_NLANE)
+// condensed Hessian weight of lane row (k, i) / input-bound row (k, j): per-stage 8-vector (tensor-core path) or flat arrays
+#if LMPC_MMA
+#define LMPC_WDT(w, k, i, row) (w).Wd[k][i]
+#define LMPC_WD2(w, k, j, row) (w).Wd[k][NCX + (j)]
+#else
+#define LMPC_WDT(w, k, i, row) (w).Dt[row]
+#define LMPC_WD2(w, k, j, row) (w).d2[row]
+#endif
 // row = lane + 32*r ; the body runs only for valid rows.  No warp collectives inside.
 #define FOR_SLOTS(r, row, CNT) \
     _Pragma("unroll") for (int r = 0, row = LMPC_LANE; r < NSLOT(CNT); ++r, row += LMPC_NLANE) if (row < (CNT))
@@ -121,19 +138,33 @@ struct Work {
     // --- iterate ---
     alignas(16) double x[(N + 1) * 6];
     alignas(16) double dx[(N + 1) * 6];
-    double u[N * 2], du[N * 2];
+    alignas(16) double u[N * 2];
+    alignas(16) double du[N * 2];
     // (dx also stages nu1 | nu2 for the stage-gradient pre-pass: it is dead between the update and the next forward sweep)
     static_assert(N * (NCX + NCU) <= (N + 1) * 6, "staging area too small");
     // --- per-row quantities shared between lanes ---
-    double Dt[N * NCX], ex[N * NCX];  // condensed lane-constraint Hessian weights / rhs
-    double d2[N * NCU], eu[N * NCU];  // input-bound Hessian weights / rhs
+    double ex[N * NCX];               // right-hand sides of the condensed lane constraints
+    double eu[N * NCU];               // right-hand sides of the input bounds
     double d4i[MM];                   // 1 / max(nu4/lam, d4_min)
-    // --- Riccati factor, per stage ---
+    alignas(16) double ru[N][2];      // input-stationarity residual
+#if LMPC_MMA
+    // ---- tensor-core formulation of the sweeps: cost-to-go Hessian / gradient live in register fragments; per stage only the
+    //      barrier weights, the stage gradients, the feedback gain, the inverse input Hessian and the feed-forward term are kept
+    static_assert(NCX + NCU <= 8, "barrier weights of one stage must fit one 8-vector");
+    alignas(16) double Wd[N][8];    // (Dt[0..NCX) | d2[0..NCU) | 0): condensed Hessian weights of the stage's inequality rows
+    alignas(16) double gv[N][16];   // row 0: stage gradient incl. the eliminated rows' right-hand side; row 1: -(stage gradient)
+    alignas(16) double Kst[N][16];  // K = -Suu^-1 [Sux | -diag(dR2)]  (2 x 8, row major): u_k = K (x_k, u_{k-1}) + f
+    alignas(16) double Sinv[N][4];  // Suu^-1 = (s00, s01, s11, -)
+    alignas(16) double fst[N][2];   // f = -Suu^-1 g0 for the current right-hand side
+    alignas(16) double tN[8];       // Qf2 x_N + qxN + yT  (= -costate at the end of the horizon)
+    alignas(16) double cst[6];      // (1,0 | 0,1 | 0,0): identity / zero fragments read like stage data
+#else
+    double Dt[N * NCX];               // condensed lane-constraint Hessian weights
+    double d2[N * NCU];               // input-bound Hessian weights
+    alignas(16) double gst[N][8];   // stage gradient: (2Q x + qx + Fx'nu1 | 2R u + rate + Fu'nu2)
     alignas(16) double Zt[N][16];   // Z~ = L^-1 [ (B'Pxx+Pxv')A | -diag(dR2) ]  (2 x 8, row major)
     double Li[N][3];                // 1/L00, L10, 1/L11   (L = chol of the 2x2 input Hessian)
     double z0[N][2];                // L^-1 g0 for the current right-hand side
-    double ru[N][2];                // input-stationarity residual
-    alignas(16) double gst[N][8];   // stage gradient: (2Q x + qx + Fx'nu1 | 2R u + rate + Fu'nu2)
     // --- sweep scratch (augmented state (x, v = previous input), 8 x 8) ---
     static constexpr int PS = 10;   // padded row stride of Paug / Gt (80 B: the 8 rows hit distinct 16 B bank groups)
     alignas(16) double Paug[8 * PS];  // cost-to-go Hessian of stage k+1
@@ -142,6 +173,7 @@ struct Work {
     alignas(16) double pb[2][8];    // cost-to-go gradient (px | pv), double buffered
     alignas(16) double pi[2][8];    // costate (6 used), double buffered
     double hv[8];                   // h~ = r~ + A~' p
+#endif
     // --- terminal block ---
     double Wm[TM], Wi[TM];
     double sbar[6], yT[6];
@@ -219,7 +251,9 @@ struct Pdip {
     static constexpr int R1 = N * NCX, R2 = N * NCU, R4 = (M > 0 ? M : 1);
     static constexpr bool LMPC = (M > 0);
     static constexpr int TMW = (M > 0 ? 36 : 1);
+#if !LMPC_MMA
     static constexpr int PS = W::PS;
+#endif
 
     // ---------------------------------------------------------------- initial point ------
     static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0) {
@@ -232,6 +266,12 @@ struct Pdip {
         }
         FOR_LANES(e, N * 2) w.u[e] = tau * w.uOld[e & 1];
         FOR_LANES(e, 6) w.x[e] = x0[e];
+#if LMPC_MMA
+        FOR_LANES(e, 6) w.cst[e] = (e == 0 || e == 3) ? 1.0 : 0.0;
+        FOR_LANES(e, N * 8) w.Wd[e >> 3][e & 7] = 0.0;
+        wsync();
+        rollout(w, x0, tau * w.uOld[0], tau * w.uOld[1]);     // dynamics hold from the start
+#else
         FOR_LANES(k, N) {               // transpose A and B in place: ABC[k][j*6+c] = [A B](c, j)
             double* A = &w.ABC[k][0];
 #pragma unroll
@@ -255,6 +295,7 @@ struct Pdip {
             }
             wsync();
         }
+#endif
         // Dual-feasible, centred start (oracle/pdip_model.py, mu0 = "auto"): the slack-stationarity row
         // nu1 + nu3 = 2 qs s + ql holds exactly with w1 nu1 = s nu3 = mu_row; every other constraint
         // family starts at the mean of those products.
@@ -423,6 +464,7 @@ struct Pdip {
     }
 
     // ---------------------------------------------------------------- backward sweeps ----
+#if !LMPC_MMA
     // Start of a backward sweep: terminal cost-to-go into (Paug | pb[N&1]) and pi_N.
     template <bool FACTOR>
     static LMPC_HD void backward_start(W& w, const FtocpConst& c, const double* c1) {
@@ -452,6 +494,22 @@ struct Pdip {
         wsync();
     }
 
+#endif
+
+    // r~_k: right-hand side contribution of the eliminated inequality rows (state part j < 6, input part r < 2)
+    static LMPC_HD double rhs_x(const W& w, const FtocpConst& c, int k, int j) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + j] * w.ex[k * NCX + i];
+        return v;
+    }
+    static LMPC_HD double rhs_u(const W& w, const FtocpConst& c, int k, int r) {
+        double v = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.eu[k * NCU + jj];
+        return v;
+    }
+
     // Stage gradients for the costate / input-residual recursion (embarrassingly parallel over stages).
     static LMPC_HD void stage_gradients(W& w, const FtocpConst& c) {
         FOR_LANES(e, N * 8) {
@@ -472,26 +530,19 @@ struct Pdip {
 #pragma unroll
                 for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.dx[N * NCX + k * NCU + jj];
             }
+#if LMPC_MMA
+            // row 0: full stage gradient for the predictor right-hand side (adds the eliminated rows' contribution), row 1: -gst
+            w.gv[k][j] = v + ((j < 6) ? rhs_x(w, c, k, j) : rhs_u(w, c, k, j - 6));
+            w.gv[k][8 + j] = -v;
+#else
             w.gst[k][j] = v;
+#endif
         }
     }
 
-    // r~_k: right-hand side contribution of the eliminated inequality rows (state part j < 6, input part r < 2)
-    static LMPC_HD double rhs_x(const W& w, const FtocpConst& c, int k, int j) {
-        double v = 0.0;
-#pragma unroll
-        for (int i = 0; i < NCX; ++i) v += c.Fx[i * 6 + j] * w.ex[k * NCX + i];
-        return v;
-    }
-    static LMPC_HD double rhs_u(const W& w, const FtocpConst& c, int k, int r) {
-        double v = 0.0;
-#pragma unroll
-        for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.eu[k * NCU + jj];
-        return v;
-    }
-
-    // work item e < 36 of phase b/e: entry (i, j), i <= j, of the 8 x 8 stage matrix and its constant data
     static constexpr int KF = (NCX > NCU ? NCX : NCU);
+#if !LMPC_MMA
+    // work item e < 36 of phase b/e: entry (i, j), i <= j, of the 8 x 8 stage matrix and its constant data
     struct SEnt {
         int i, j, cls;       // class 0 = state-state, 1 = input-state, 2 = input-input
         double kq, kf[KF];
@@ -685,6 +736,320 @@ struct Pdip {
         }
     }
 
+#else   // ======================================================================== LMPC_MMA: tensor-core sweeps
+    // The sweeps of one interior-point iteration on fp64 tensor-core fragments (mma.sync.m8n8k4.f64, SASS DMMA).
+    //
+    // Fragment convention ("D layout" of an 8 x 8 matrix X): lane l = 4 r + q (r = l >> 2, q = l & 3) holds
+    //   X.a = X[r][2q],  X.b = X[r][2q+1]                       -- the accumulator layout of m8n8k4.
+    // With the summation index split into even / odd columns, two MMAs give a full 8 x 8 x 8 product WITHOUT any register
+    // shuffle between chained products:
+    //   prod(X, YT) = X Y    where YT is the D layout of Y' :   mma(X.a, YT.a) + mma(X.b, YT.b)
+    // (A operand X[r][2q] = X.a; B operand Y[2q][r] = Y'[r][2q] = YT.a; same for the odd half.)  The result is again in D
+    // layout, so products chain; a symmetric matrix serves as both X and YT.  Row vectors ride in rows 0 / 1 of a fragment.
+    //
+    // Augmented state w = (x, v) with v_k = u_{k-1}; A~ = [A B; 0 I] maps (x_k, u_k) to w_{k+1}.  Per stage, with the cost-to-go
+    // Hessian P of stage k+1:   S = A~' P A~ + H_k,   H_k = blkdiag(2Q, 2R + rate) + Fa' diag(Wd_k) Fa,  Fa = [Fx 0; 0 Fu],
+    //   Suu = L L',  Z = L^-1 [Sux | -dR2],  K = -L^-T Z,  M = [I 0; K],  P_k = [Sxx 0; 0 0] - Z'Z,
+    //   gradient  c_k = M'(A~' c + g_k),   f_k = -Suu^-1 (A~' c + g_k)_u,        g_k = stage gradient + eliminated-row terms,
+    //   where c = (cost-to-go gradient) - (costate, 0): the costate recursion pi_k = A' pi - gst_x drops out of the solve and is
+    //   only carried (row 1) in the factorising sweep to report the input-stationarity residual ru = gst_u - B' pi.
+    // forward:  (x_k, u_k) = M w_k + (0, f_k),  w_{k+1} = A~ (x_k, u_k).
+    struct Frag { double a, b; };
+
+    static LMPC_HD void dmma(double& d0, double& d1, double a, double b, double c0, double c1) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                     : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+#endif
+    }
+    static LMPC_HD Frag prod(const Frag& X, const Frag& YT) {
+        Frag e, o;
+        dmma(e.a, e.b, X.a, YT.a, 0.0, 0.0);
+        dmma(o.a, o.b, X.b, YT.b, 0.0, 0.0);
+        return Frag{e.a + o.a, e.b + o.b};
+    }
+    static LMPC_HD Frag prod_add(const Frag& X, const Frag& YT, const Frag& C) {
+        Frag e, o;
+        dmma(e.a, e.b, X.a, YT.a, C.a, C.b);
+        dmma(o.a, o.b, X.b, YT.b, 0.0, 0.0);
+        return Frag{e.a + o.a, e.b + o.b};
+    }
+    static LMPC_HD double bcast(double v, int src) {
+#if defined(__CUDA_ARCH__)
+        return __shfl_sync(0xffffffffu, v, src);
+#else
+        return v;
+#endif
+    }
+    static LMPC_HD Frag ld2(const double* p) {
+        const double2 v = *reinterpret_cast<const double2*>(p);
+        return Frag{v.x, v.y};
+    }
+    static LMPC_HD void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+    // Lane-constant addressing of the stage-data fragments.  A lane whose fragment entry is a structural constant (identity /
+    // zero rows of A~ and M) reads it from w.cst with stride 0, so the sweeps contain no lane-dependent branches.
+    struct LaneMap {
+        int r, q;
+        int at_a, at_b, at_step;   // D layout of A~' : (A~[2q][r], A~[2q+1][r]), doubles from &ABC[0][0]; per-stage step
+        int af, af_step;           // D layout of A~  : (A~[r][2q], A~[r][2q+1]) as one 16-byte load
+        int mf, mf_step;           // D layout of M   : rows 6,7 = K (from Kst), identity elsewhere
+        int mt_a, mt_b, mt_step;   // D layout of M'  : (M[2q][r], M[2q+1][r]); q == 3 -> (K0[r], K1[r])
+    };
+    static LMPC_HD LaneMap lane_map(const W& w) {
+        LaneMap m;
+        const int lane = LMPC_LANE;
+        m.r = lane >> 2;
+        m.q = lane & 3;
+        const int r = m.r, q = m.q;
+        const int abc0 = 0;
+        const int cst0 = (int)(&w.cst[0] - &w.ABC[0][0]);
+        const int kst0 = (int)(&w.Kst[0][0] - &w.ABC[0][0]);
+        // A~ = [A B; 0 I], A row major (a*6+b) at 0, B (a*2+j) at 36
+        if (q < 3) {
+            m.at_a = abc0 + ((r < 6) ? (2 * q) * 6 + r : 36 + (2 * q) * 2 + (r - 6));
+            m.at_b = abc0 + ((r < 6) ? (2 * q + 1) * 6 + r : 36 + (2 * q + 1) * 2 + (r - 6));
+            m.at_step = 54;
+        } else {                       // rows 6,7 of A~: (delta(r==6), delta(r==7))
+            m.at_a = cst0 + ((r == 6) ? 0 : 1);
+            m.at_b = cst0 + ((r == 7) ? 0 : 1);
+            m.at_step = 0;
+        }
+        if (r < 6) { m.af = abc0 + ((q < 3) ? r * 6 + 2 * q : 36 + 2 * r); m.af_step = 54; }
+        else { m.af = cst0 + ((q == 3) ? ((r == 6) ? 0 : 2) : 4); m.af_step = 0; }
+        if (r >= 6) { m.mf = kst0 + (r - 6) * 8 + 2 * q; m.mf_step = 16; }
+        else { m.mf = cst0 + ((r == 2 * q) ? 0 : ((r == 2 * q + 1) ? 2 : 4)); m.mf_step = 0; }
+        if (q == 3) { m.mt_a = kst0 + r; m.mt_b = kst0 + 8 + r; m.mt_step = 16; }
+        else { m.mt_a = cst0 + ((r == 2 * q) ? 0 : 1); m.mt_b = cst0 + ((r == 2 * q + 1) ? 0 : 1); m.mt_step = 0; }
+        return m;
+    }
+
+    // Right-hand side rows of the eliminated inequality constraints for a NEW right-hand side (corrector): row 0 of gv becomes
+    // stage gradient + (Fx' ex | Fu' eu); row 1 (= -stage gradient, written by stage_gradients) is kept.
+    static LMPC_HD void stage_rhs(W& w, const FtocpConst& c) {
+        FOR_LANES(e, N * 8) {
+            const int k = e >> 3, j = e & 7;
+            w.gv[k][j] = ((j < 6) ? rhs_x(w, c, k, j) : rhs_u(w, c, k, j - 6)) - w.gv[k][8 + j];
+        }
+    }
+
+    // tN = Qf2 x_N + qxN + yT (minus the costate at the end of the horizon), once per iteration
+    static LMPC_HD void terminal_costate(W& w, const FtocpConst& c) {
+        FOR_LANES(a, 8) {
+            double t = 0.0;
+            if (a < 6) {
+                t = c.qxN[a] + (LMPC ? w.yT[a] : 0.0);
+#pragma unroll
+                for (int b = 0; b < 6; ++b) t += c.Qf2[a * 6 + b] * w.x[N * 6 + b];
+            }
+            w.tN[a] = t;
+        }
+    }
+    // Row vectors at the end of the horizon: row 0 = Wi c1 + tN (gradient minus costate), row 1 = -tN (costate; FACTOR only)
+    template <bool FACTOR>
+    static LMPC_HD Frag terminal_vec(const W& w, const double* c1, int r, int q) {
+        Frag V{0.0, 0.0};
+        if (r <= (FACTOR ? 1 : 0)) {
+            const Frag t = ld2(&w.tN[2 * q]);
+            if (r == 1) { V.a = -t.a; V.b = -t.b; }
+            else {
+                V = t;
+                if (LMPC && q < 3) {
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) {
+                        V.a += w.Wi[((2 * q) * 6 + b) % TMW] * c1[b];
+                        V.b += w.Wi[((2 * q + 1) * 6 + b) % TMW] * c1[b];
+                    }
+                }
+            }
+        }
+        return V;
+    }
+
+    // Factorising backward sweep; carries the gradient recursion of the predictor right-hand side (row 0) and the costate
+    // recursion (row 1, only to report the input-stationarity residual).  Returns max |ru|.
+    static LMPC_HD double backward_factor(W& w, const FtocpConst& c, const double* c1) {
+        const LaneMap lm = lane_map(w);
+        const int lane = LMPC_LANE, r = lm.r, q = lm.q;
+        const double* base = &w.ABC[0][0];
+        // constant part of the stage Hessian in D layout: blkdiag(2Q, 2R + 2 dR2)  (the last stage has 1 dR2: `rate`)
+        Frag Hc{0.0, 0.0}, rate{0.0, 0.0};
+        if (r < 6 && q < 3) Hc = Frag{c.Q2[r * 6 + 2 * q], c.Q2[r * 6 + 2 * q + 1]};
+        if (r >= 6 && q == 3) {
+            Hc = Frag{c.R2[(r - 6) * 2], c.R2[(r - 6) * 2 + 1]};
+            rate = Frag{r == 6 ? c.dR2[0] : 0.0, r == 7 ? c.dR2[1] : 0.0};
+            Hc.a += 2.0 * rate.a;
+            Hc.b += 2.0 * rate.b;
+        }
+        // D layout of Fa' (Fa = [Fx 0; 0 Fu], rows beyond NCX + NCU are zero)
+        Frag FaT{0.0, 0.0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = 2 * q + h;
+            double v = 0.0;
+            if (row < NCX) v = (r < 6) ? c.Fx[row * 6 + r] : 0.0;
+            else if (row < NCX + NCU) v = (r >= 6) ? c.Fu[(row - NCX) * 2 + (r - 6)] : 0.0;
+            if (h == 0) FaT.a = v; else FaT.b = v;
+        }
+        const double y0c = (r == 6) ? -c.dR2[0] : 0.0, y1c = (r == 7) ? -c.dR2[1] : 0.0;
+        const bool keep = (r < 6 && q < 3);                 // entries of Sxx
+        const Frag Id = Frag{(q < 3 && r == 2 * q) ? 1.0 : 0.0, (q < 3 && r == 2 * q + 1) ? 1.0 : 0.0};   // M' for q < 3
+
+        // terminal cost-to-go
+        Frag Pf{0.0, 0.0};
+        if (keep) {
+            Pf.a = c.Qf2[r * 6 + 2 * q] + (LMPC ? w.Wi[(r * 6 + 2 * q) % TMW] : 0.0);
+            Pf.b = c.Qf2[r * 6 + 2 * q + 1] + (LMPC ? w.Wi[(r * 6 + 2 * q + 1) % TMW] : 0.0);
+        }
+        Frag Vf = terminal_vec<true>(w, c1, r, q);
+        bool bad = false;
+        const double* pa = base + lm.at_a + (N - 1) * lm.at_step;
+        const double* pb_ = base + lm.at_b + (N - 1) * lm.at_step;
+        Frag At{*pa, *pb_}, Gn{0.0, 0.0};
+        if (lane < 8) Gn = ld2(&w.gv[N - 1][2 * lane]);
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {
+            const Frag AtF = At, g = Gn;
+            const Frag wd = ld2(&w.Wd[k][2 * q]);
+            if (k > 0) {                                   // prefetch the next stage's operands off the dependent chain
+                pa -= lm.at_step; pb_ -= lm.at_step;
+                At = Frag{*pa, *pb_};
+                if (lane < 8) Gn = ld2(&w.gv[k - 1][2 * lane]);
+            }
+            // ---- stage Hessian: constant part + Fa' diag(Wd_k) Fa as one product (independent of the Riccati chain)
+            Frag Hk = Hc;
+            if (k == N - 1) { Hk.a -= rate.a; Hk.b -= rate.b; }
+            const Frag Hf = prod_add(Frag{FaT.a * wd.a, FaT.b * wd.b}, FaT, Hk);
+            // ---- S = A~' P A~ + H
+            const Frag Gp = prod(AtF, Pf);                 // A~' P   (P symmetric: its D layout is also its transposed layout)
+            const Frag S = prod_add(Gp, AtF, Hf);
+            // ---- row vectors: A~' c + g (row 0), A~' pi - gst (row 1)
+            const Frag Tv = prod(Vf, AtF);
+            Frag Hv{Tv.a + g.a, Tv.b + g.b};               // rows other than 0, 1: 0 + 0
+            if (lane == 7) { st2(&w.ru[k][0], -Hv.a, -Hv.b); Hv = Frag{0.0, 0.0}; }   // ru = gst_u - B' pi; costate has no input part
+            // ---- 2x2 Cholesky of Suu (every lane the same values)
+            double s66 = bcast(S.a, 27);
+            const double s76 = bcast(S.a, 31);
+            const double s77 = bcast(S.b, 31);
+            if (!(s66 > 0.0)) { bad = true; s66 = 1.0; }
+            double det = s66 * s77 - s76 * s76;
+            if (!(det > 0.0)) { bad = true; det = 1.0; }
+            const double i00 = rsqrt_f64(s66);
+            const double l10 = s76 * i00;
+            const double i11 = rsqrt_f64(det) * (s66 * i00);      // 1 / sqrt(s77 - l10^2), independent of the first rsqrt
+            // ---- Z = L^-1 Y and K = -L^-T Z, column r (Y = [Sux | -dR2]; Sux(:, r) = S[r][6..7] sits in lane 4r+3)
+            double y0 = bcast(S.a, lane | 3), y1 = bcast(S.b, lane | 3);
+            if (r >= 6) { y0 = y0c; y1 = y1c; }
+            const double z0r = y0 * i00;
+            const double z1r = (y1 - l10 * z0r) * i11;
+            const double k1r = -z1r * i11;
+            const double k0r = (-z0r - l10 * k1r) * i00;
+            if (q == 0) { w.Kst[k][r] = k0r; w.Kst[k][8 + r] = k1r; }
+            // ---- inverse input Hessian, feed-forward term f = -Suu^-1 h_u (h_u sits in lane 3)
+            const double t = l10 * i00 * i11;
+            const double s11 = i11 * i11, s01 = -t * i11, s00 = i00 * i00 + t * t;
+            if (lane == 3) {
+                st2(&w.Sinv[k][0], s00, s01);
+                w.Sinv[k][2] = s11;
+                st2(&w.fst[k][0], -(s00 * Hv.a + s01 * Hv.b), -(s01 * Hv.a + s11 * Hv.b));
+            }
+            // ---- cost-to-go Hessian of stage k: [Sxx 0; 0 0] - Z'Z  (rank-2 update as one MMA, k = 0,1 used)
+            const double zsel = (q == 0) ? z0r : ((q == 1) ? z1r : 0.0);
+            dmma(Pf.a, Pf.b, -zsel, zsel, keep ? S.a : 0.0, keep ? S.b : 0.0);
+            // ---- c_k = M' h (row 0); the costate passes through the identity part (row 1)
+            const Frag MT = (q < 3) ? Id : Frag{k0r, k1r};
+            Vf = prod(Hv, MT);
+        }
+        if (bad && lane == 0) w.flag = ST_NUMERICAL;
+        wsync();
+        double ru_max = 0.0;
+        FOR_LANES(e, N * 2) ru_max = fmax(ru_max, fabs(w.ru[e >> 1][e & 1]));
+        return wmax(ru_max);
+    }
+
+    // Gradient-only backward sweep for a new right-hand side (corrector / recentring): c_k = M'(A~'c + g_k), f_k.
+    static LMPC_HD void backward_rhs(W& w, const FtocpConst& c, const double* c1) {
+        const LaneMap lm = lane_map(w);
+        const int lane = LMPC_LANE, r = lm.r, q = lm.q;
+        const double* base = &w.ABC[0][0];
+        Frag Vf = terminal_vec<false>(w, c1, r, q);
+        const double* pa = base + lm.at_a + (N - 1) * lm.at_step;
+        const double* pb_ = base + lm.at_b + (N - 1) * lm.at_step;
+        const double* ma = base + lm.mt_a + (N - 1) * lm.mt_step;
+        const double* mb = base + lm.mt_b + (N - 1) * lm.mt_step;
+        Frag At{*pa, *pb_}, Mt{*ma, *mb}, Gn{0.0, 0.0};
+        if (lane < 4) Gn = ld2(&w.gv[N - 1][2 * lane]);
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {
+            const Frag AtF = At, MT = Mt, g = Gn;
+            if (k > 0) {                                   // prefetch the next stage's operands off the dependent chain
+                pa -= lm.at_step; pb_ -= lm.at_step; ma -= lm.mt_step; mb -= lm.mt_step;
+                At = Frag{*pa, *pb_};
+                Mt = Frag{*ma, *mb};
+                if (lane < 4) Gn = ld2(&w.gv[k - 1][2 * lane]);
+            }
+            const Frag Tv = prod(Vf, AtF);
+            const Frag Hv{Tv.a + g.a, Tv.b + g.b};         // rows other than 0: 0 + 0
+            if (lane == 3) {
+                const Frag s0 = ld2(&w.Sinv[k][0]);
+                const double s11 = w.Sinv[k][2];
+                st2(&w.fst[k][0], -(s0.a * Hv.a + s0.b * Hv.b), -(s0.b * Hv.a + s11 * Hv.b));
+            }
+            Vf = prod(Hv, MT);
+        }
+        wsync();
+    }
+
+    // Forward sweep: (dx_k, du_k) = M w_k + (0, f_k), w_{k+1} = A~ (dx_k, du_k), from w_0 = 0.
+    static LMPC_HD void forward(W& w) {
+        const LaneMap lm = lane_map(w);
+        const int lane = LMPC_LANE;
+        const double* base = &w.ABC[0][0];
+        const double* pf = base + lm.af;
+        const double* pm = base + lm.mf;
+        Frag Wf{0.0, 0.0};
+        Frag Af = ld2(pf), Mf = ld2(pm), Cf{0.0, 0.0};
+        if (lane == 3) Cf = ld2(&w.fst[0][0]);
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            const Frag AF = Af, MF = Mf, CF = Cf;
+            if (k + 1 < N) {                               // prefetch the next stage's operands off the dependent chain
+                pf += lm.af_step; pm += lm.mf_step;
+                Af = ld2(pf);
+                Mf = ld2(pm);
+                if (lane == 3) Cf = ld2(&w.fst[k + 1][0]);
+            }
+            const Frag Uf = prod_add(Wf, MF, CF);          // row 0: (dx_k | du_k)
+            if (lane < 3) st2(&w.dx[k * 6 + 2 * lane], Uf.a, Uf.b);
+            if (lane == 3) st2(&w.du[k * 2], Uf.a, Uf.b);
+            Wf = prod(Uf, AF);                             // row 0: (dx_{k+1} | du_k)
+        }
+        if (lane < 3) st2(&w.dx[N * 6 + 2 * lane], Wf.a, Wf.b);
+        wsync();
+    }
+
+    // Model roll-out of the starting point with a constant input: (x_{k+1} | u) = A~ (x_k | u) + (C_k | 0)
+    static LMPC_HD void rollout(W& w, const double* x0, double u0, double u1) {
+        const LaneMap lm = lane_map(w);
+        const int lane = LMPC_LANE;
+        const double* pf = &w.ABC[0][0] + lm.af;
+        Frag Wf{0.0, 0.0};
+        if (lane < 3) Wf = Frag{x0[2 * lane], x0[2 * lane + 1]};
+        if (lane == 3) Wf = Frag{u0, u1};
+        if (lane < 3) st2(&w.x[2 * lane], Wf.a, Wf.b);
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            const Frag AF = ld2(pf);
+            pf += lm.af_step;
+            Frag CF{0.0, 0.0};
+            if (lane < 3) CF = ld2(&w.ABC[k][48 + 2 * lane]);
+            Wf = prod_add(Wf, AF, CF);
+            if (lane < 3) st2(&w.x[(k + 1) * 6 + 2 * lane], Wf.a, Wf.b);
+        }
+        wsync();
+    }
+#endif  // LMPC_MMA
+
     // terminal recovery after a forward sweep: dlam (registers); returns dy1.
     // The 6x6 covariance-form solve loses ~cond(W)*eps in dyT, which the division by a small d4 amplifies in
     // the dlam of active safe-set points.  One step of iterative refinement with the residual of
@@ -770,7 +1135,7 @@ struct Pdip {
                 const double ihs = 1.0 / (c.qs2 + d1 + d3);
                 g.d1[r] = d1;
                 g.ihs[r] = ihs;
-                w.Dt[row] = d1 * (c.qs2 + d3) * ihs;
+                LMPC_WDT(w, k, i, row) = d1 * (c.qs2 + d3) * ihs;
                 // predictor: rc1 = w1 nu1, rc3 = s nu3  ->  e1 = -nu1, rs + rc3/s = rs + nu3
                 w.ex[row] = (-g.nu1[r] * (c.qs2 + d3) + d1 * (rs + g.nu3[r])) * ihs;
                 w.dx[row] = g.nu1[r];
@@ -782,7 +1147,7 @@ struct Pdip {
                 comp += w2 * g.nu2[r];
                 const double iw2 = 1.0 / w2;
                 g.iw2[r] = iw2;
-                w.d2[row] = g.nu2[r] * iw2;
+                LMPC_WD2(w, k, j, row) = g.nu2[r] * iw2;
                 w.eu[row] = -g.nu2[r];           // predictor: -rc2/w2
                 w.dx[N * NCX + row] = g.nu2[r];
             }
@@ -828,8 +1193,14 @@ struct Pdip {
                 terminal_rhs(w, g, -rone, c1, beta);
             }
             stage_gradients(w, c);
+#if LMPC_MMA
+            terminal_costate(w, c);
+            wsync();
+            const double ru_max = backward_factor(w, c, c1);
+#else
             backward_start<true>(w, c, c1);
             const double ru_max = backward_factor(w, c);
+#endif
             ru_prev = ru_max;
             r_dual = fmax(rd_loc, ru_max);
             if (w.flag != 0) { status = w.flag; break; }
@@ -926,8 +1297,14 @@ struct Pdip {
                     terminal_rhs(w, g, -rone, c1, beta);
                 }
                 wsync();
+#if LMPC_MMA
+                stage_rhs(w, c);
+                wsync();
+                backward_rhs(w, c, c1);
+#else
                 backward_start<false>(w, c, c1);
                 backward_rhs(w, c);
+#endif
                 forward(w);
                 if (LMPC) dy1 = terminal_recover(w, g, c, c1, beta, delta, -rone);
 
@@ -1027,9 +1404,15 @@ struct Pdip {
         FOR_LANES(e, N * 6) {
             int k = e / 6, a = e % 6;
             const double* T = &w.ABC[k][0];
-            double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
+#if LMPC_MMA
+            double v = T[48 + a] + T[36 + a * 2] * w.u[k * 2] + T[37 + a * 2] * w.u[k * 2 + 1];      // stage record as loaded
+#pragma unroll
+            for (int b = 0; b < 6; ++b) v += T[a * 6 + b] * w.x[k * 6 + b];
+#else
+            double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];              // transposed in place
 #pragma unroll
             for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];
+#endif
             rdyn = fmax(rdyn, fabs(w.x[(k + 1) * 6 + a] - v));
         }
         r_prim = fmax(r_prim, wmax(rdyn));

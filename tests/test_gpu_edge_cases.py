@@ -182,7 +182,10 @@ def test_add_point_on_a_full_lap_is_flagged(track):
         c.add_trajectory(0, *_random_lap(rng, 63))
     c.add_point(np.zeros(6), np.zeros(2))              # row 64 of 64: fits
     assert c.get_lap(0, 3)[0].shape[0] == 64
-    c.add_point(np.zeros(6), np.zeros(2))              # no room: LMPC.addPoint would np.append; the fixed pool flags bit 16
+    # no room: LMPC.addPoint would np.append (PC.py:466-476); the fixed pool must not drop the point silently: the host
+    # entry reports it (the device-resident rollout accumulates flag bit 16 in its health record instead)
+    with pytest.raises(nat.NativeError, match="Tmax"):
+        c.add_point(np.zeros(6), np.zeros(2))
     assert c.get_lap(0, 3)[0].shape[0] == 64
     assert c.step_results()["flags"][0] & 16
     c.close()
