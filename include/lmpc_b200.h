@@ -52,8 +52,11 @@ typedef struct lmpc_params {
     /* interior-point settings (no reference counterpart; OSQP's eps are 1e-3 + polish, PC.py:275) */
     double eps_res, eps_gap;      /* <= 0 selects the defaults 1e-9 / 1e-11 (unscaled inf-norms); an instance still
                                      running at iteration 20 is reported solved once all three are <= 1e-6 (safety
-                                     net; not reached on any recorded workload) */
+                                     net; counted by lmpc_late_accepts, 0 on every recorded workload) */
     int max_iter;                 /* <= 0 selects the default 40               */
+    double eps_step;              /* <= 0 selects the default 1e-7: besides the residuals, the last primal step
+                                     |alpha (dx, du)|_inf must be below it -- on QPs without strict complementarity the
+                                     iterate is O(sqrt(gap)) from the optimum while the residuals are already tiny */
 } lmpc_params;
 
 /* Local-regression model parameters: PredictiveModel.__init__ (PredictiveModel.py:12-32) and the
@@ -193,7 +196,8 @@ int lmpc_step_results(lmpc_handle* h, int* status, int* iters, double* resid, in
  * The caller is responsible for staying inside the buffer (sizes follow from batch, N and numSS_Points). */
 int lmpc_read_buffer(lmpc_handle* h, const char* name, size_t offset_bytes, void* dst, size_t bytes);
 /* Device address of an internal buffer by name: "xPred","uPred","lambd","zt","zt_u","abc","SS_sel","Qfun_sel",
- * "Succ_SS","Succ_uSS","status","iters","resid","flags","xLin","uLin". */
+ * "Succ_SS","Succ_uSS","status","iters","resid","flags","xLin","uLin","x0","OldInput","slack","slackT" (lane slacks [B,N*ncx] and
+ * terminal slack [B,6] of the most recent step), "abc_lti". */
 void* lmpc_device_buffer(lmpc_handle* h, const char* name);
 
 /* ===== device-resident closed loop (the caller of the hot path) =======================================

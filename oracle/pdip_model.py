@@ -61,7 +61,7 @@ def from_params(p, A, B, C, x0, uOld, SS=None, Qfun=None, Qts=None):
                    p.Fu, np.squeeze(p.bu), A, B, C, x0, np.asarray(uOld, float).ravel(), SS, Qfun, Qts)
 
 
-def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0=0.3, gamma=0.01, warm=None, snap_mu=None,
+def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_step=1e-7, eps_gap=None, mu0="auto", s0=0.3, gamma=0.01, warm=None, snap_mu=None,
           warm_theta=0.5):
     """Returns dict(x[N+1,n], u[N,d], s[N,ncx], lam[m], xi[n], iters, r_prim, r_dual, gap, status)."""
     N, n, d = qp.N, 6, 2
@@ -150,6 +150,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
 
     status, it = 2, 0
     d4_floor, rdual_prev, al_prev = D4_MIN, 1e300, 0.0
+    step_prev = np.inf       # |alpha (dx, du)|_inf of the step just taken: residuals alone do not bound the distance to the optimum
     for it in range(max_iter + 1):
         # ---- residuals -----------------------------------------------------------
         r1 = np.array([Fx @ x[k] - s[k] + w1[k] - bx for k in range(N)])
@@ -181,7 +182,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
             snap = dict(u=u.copy(), s=s.copy(), w1=w1.copy(), nu1=nu1.copy(), nu2=nu2.copy(), nu3=nu3.copy(), mu=mu, it=it)
             if lmpc:
                 snap.update(lam=lam.copy(), nu4=nu4.copy(), y1=y1)
-        if r_prim <= eps and r_dual <= eps and mu <= (eps if eps_gap is None else eps_gap):
+        if r_prim <= eps and r_dual <= eps and mu <= (eps if eps_gap is None else eps_gap) and step_prev <= eps_step:
             status = 1
             break
         if ADAPTIVE_FLOOR and lmpc and it > 0 and al_prev >= 0.9 and r_dual > 0.25 * rdual_prev:
@@ -393,6 +394,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_gap=None, mu0="auto", s0
                 msg += " lam %.2e  |dlam| %.2e |dyT| %.2e |dxN| %.2e alpha %.3f sigma %.2e minD4 %.1e" % (np.abs(e_l).max(), np.abs(cc["dlam"]).max(), np.abs(cc["dyT"]).max(), np.abs(dx_[N]).max(), al, sigma, (nu4/lam).min())
             print(msg)
         al_prev = al
+        step_prev = al * max(np.abs(cc["dx"]).max(), np.abs(cc["du"]).max())
         x = x + al * cc["dx"]
         u = u + al * cc["du"]
         s = s + al * cc["ds"]

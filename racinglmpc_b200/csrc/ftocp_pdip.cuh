@@ -41,6 +41,14 @@
 #else
 #define LMPC_MMA 0
 #endif
+// unroll factor of the stage loops of the sweeps (2 lets the compiler rename the one-stage-ahead operand registers instead
+// of copying them; more only grows the code, which 16 resident warps at different places keep missing in the instruction cache)
+#ifndef LMPC_SWEEP_UNROLL_N
+#define LMPC_SWEEP_UNROLL_N 2
+#endif
+#define LMPC_PRAGMA_(x) _Pragma(#x)
+#define LMPC_PRAGMA(x) LMPC_PRAGMA_(x)
+#define LMPC_SWEEP_UNROLL LMPC_PRAGMA(unroll LMPC_SWEEP_UNROLL_N)
 
 namespace lmpc {
 
@@ -109,6 +117,7 @@ struct FtocpConst {
     double Fx[MAX_NCX * 6], bx[MAX_NCX], Fu[MAX_NCU * 2], bu[MAX_NCU];  // PC.py:166-198
     double T[36], Tinv[36];         // 2*QterminalSlack and its inverse (PC.py:361)
     double eps_res, eps_gap, d4_min;
+    double eps_step;                // convergence also needs the last primal step |alpha (dx, du)|_inf <= eps_step
     int max_iter;
     int pad_;
 };
@@ -150,8 +159,8 @@ struct Work {
 #if LMPC_MMA
     // ---- tensor-core formulation of the sweeps: cost-to-go Hessian / gradient live in register fragments; per stage only the
     //      barrier weights, the stage gradients, the feedback gain, the inverse input Hessian and the feed-forward term are kept
-    static_assert(NCX + NCU <= 8, "barrier weights of one stage must fit one 8-vector");
-    alignas(16) double Wd[N][8];    // (Dt[0..NCX) | d2[0..NCU) | 0): condensed Hessian weights of the stage's inequality rows
+    static_assert(NCX + NCU <= 6, "barrier weights of one stage must fit six entries of one 8-vector");
+    alignas(16) double Wd[N][8];    // (Dt[0..NCX) | d2[0..NCU) | 0.. | input-rate weights at 6,7): diagonal of the stage's Fa' W Fa term
     alignas(16) double gv[N][16];   // row 0: stage gradient incl. the eliminated rows' right-hand side; row 1: -(stage gradient)
     alignas(16) double Kst[N][16];  // K = -Suu^-1 [Sux | -diag(dR2)]  (2 x 8, row major): u_k = K (x_k, u_{k-1}) + f
     alignas(16) double Sinv[N][4];  // Suu^-1 = (s00, s01, s11, -)
@@ -223,11 +232,27 @@ LMPC_HD double dot6v(const double* a, const double* b) {
     return (a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3]) + (a[4] * b[4] + a[5] * b[5]);
 #endif
 }
+// 1/sqrt(v) and 1/v for positive, normal v (every call site guards its argument).  Device: the hardware approximation
+// (MUFU.RSQ64H / MUFU.RCP64H, about 2^-20) refined to full double accuracy -- one cubic step for rsqrt (error e^3), two Newton
+// steps for the reciprocal (e^4) -- without the library's slow-path branches for subnormal / infinite arguments.
 LMPC_HD double rsqrt_f64(double v) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(v);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    const double e = fma(-v, y * y, 1.0);
+    return fma(fma(0.375, e, 0.5), y * e, y);
 #else
     return 1.0 / sqrt(v);
+#endif
+}
+LMPC_HD double recip(double v) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    y = fma(y, fma(-v, y, 1.0), y);
+    return fma(y, fma(-v, y, 1.0), y);
+#else
+    return 1.0 / v;
 #endif
 }
 // (i, j), i <= j, of the e-th entry of the upper triangle of an 8 x 8 matrix (row-wise)
@@ -242,7 +267,7 @@ LMPC_HD void ratio_update(double v, double dv, double& rn, double& rd) {
     const double nn = -dv;
     if (nn * rd > rn * v) { rn = nn; rd = v; }
 }
-LMPC_HD double ratio_bound(double rn, double rd, double a) { return (rn > 0.0) ? fmin(a, rd / rn) : a; }
+LMPC_HD double ratio_bound(double rn, double rd, double a) { return (rn > 0.0) ? fmin(a, rd * recip(rn)) : a; }
 
 template <int N, int M, int NCX, int NCU>
 struct Pdip {
@@ -268,7 +293,10 @@ struct Pdip {
         FOR_LANES(e, 6) w.x[e] = x0[e];
 #if LMPC_MMA
         FOR_LANES(e, 6) w.cst[e] = (e == 0 || e == 3) ? 1.0 : 0.0;
-        FOR_LANES(e, N * 8) w.Wd[e >> 3][e & 7] = 0.0;
+        FOR_LANES(e, N * 8) {           // rows 6,7: weight of u_k^2 in the input-rate cost (PC.py:233-242), rest written every iteration
+            const int k = e >> 3, j = e & 7;
+            w.Wd[k][j] = (j >= 6) ? ((k < N - 1) ? 2.0 : 1.0) * c.dR2[j - 6] : 0.0;
+        }
         wsync();
         rollout(w, x0, tau * w.uOld[0], tau * w.uOld[1]);     // dynamics hold from the start
 #else
@@ -364,16 +392,17 @@ struct Pdip {
         double acc[6] = {0, 0, 0, 0, 0, 0}, dl = 0.0;
         FOR_SLOTS(r, row, R4) {
             double d4 = fmax(g.nu4[r] * g.ilam[r], d4_floor);
-            double di = 1.0 / d4;
+            double di = recip(d4);
             w.d4i[row] = di;
             dl += di;
 #pragma unroll
             for (int a = 0; a < 6; ++a) acc[a] += w.SS[a * M + row] * di;
         }
         double delta = wsum(dl);
+        const double idelta = recip(delta);
         double sb[6];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) sb[a] = wsum(acc[a]) / delta;
+        for (int a = 0; a < 6; ++a) sb[a] = wsum(acc[a]) * idelta;
 #pragma unroll
         for (int a = 0; a < 6; ++a)
             if (LMPC_LANE == (a % LMPC_NLANE)) w.sbar[a] = sb[a];   // same value on every lane
@@ -796,9 +825,17 @@ struct Pdip {
         int mf, mf_step;           // D layout of M   : rows 6,7 = K (from Kst), identity elsewhere
         int mt_a, mt_b, mt_step;   // D layout of M'  : (M[2q][r], M[2q+1][r]); q == 3 -> (K0[r], K1[r])
     };
-    static LMPC_HD LaneMap lane_map(const W& w) {
+    // The lane id the sweeps derive their roles from.  Made opaque to the optimiser on purpose: otherwise every role mask and
+    // address of a sweep is hoisted out of the interior-point loop and stays live (in registers or spilled) across the row loops.
+    static LMPC_HD int sweep_lane() {
+        int lane = LMPC_LANE;
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+r"(lane));
+#endif
+        return lane;
+    }
+    static LMPC_HD LaneMap lane_map(const W& w, int lane) {
         LaneMap m;
-        const int lane = LMPC_LANE;
         m.r = lane >> 2;
         m.q = lane & 3;
         const int r = m.r, q = m.q;
@@ -868,20 +905,19 @@ struct Pdip {
 
     // Factorising backward sweep; carries the gradient recursion of the predictor right-hand side (row 0) and the costate
     // recursion (row 1, only to report the input-stationarity residual).  Returns max |ru|.
+    // The loop body is branch-free: lane roles are encoded in 0/1 masks and per-lane addresses, stage data is read through
+    // running pointers one stage ahead of its use (the dependent chain is MMA -> MMA -> shuffle -> rsqrt -> MMA).
     static LMPC_HD double backward_factor(W& w, const FtocpConst& c, const double* c1) {
-        const LaneMap lm = lane_map(w);
-        const int lane = LMPC_LANE, r = lm.r, q = lm.q;
+        const int lane = sweep_lane();
+        const LaneMap lm = lane_map(w, lane);
+        const int r = lm.r, q = lm.q;
         const double* base = &w.ABC[0][0];
-        // constant part of the stage Hessian in D layout: blkdiag(2Q, 2R + 2 dR2)  (the last stage has 1 dR2: `rate`)
-        Frag Hc{0.0, 0.0}, rate{0.0, 0.0};
+        // constant part of the stage Hessian in D layout: blkdiag(2Q, 2R)
+        Frag Hc{0.0, 0.0};
         if (r < 6 && q < 3) Hc = Frag{c.Q2[r * 6 + 2 * q], c.Q2[r * 6 + 2 * q + 1]};
-        if (r >= 6 && q == 3) {
-            Hc = Frag{c.R2[(r - 6) * 2], c.R2[(r - 6) * 2 + 1]};
-            rate = Frag{r == 6 ? c.dR2[0] : 0.0, r == 7 ? c.dR2[1] : 0.0};
-            Hc.a += 2.0 * rate.a;
-            Hc.b += 2.0 * rate.b;
-        }
-        // D layout of Fa' (Fa = [Fx 0; 0 Fu], rows beyond NCX + NCU are zero)
+        if (r >= 6 && q == 3) Hc = Frag{c.R2[(r - 6) * 2], c.R2[(r - 6) * 2 + 1]};
+        // D layout of Fa', Fa = [Fx 0; 0 Fu; 0 I2]: rows 6,7 select the inputs, their weights Wd[k][6..7] carry the input-rate
+        // cost (2 dR2, the last stage 1 dR2) so that the variable part of the stage Hessian is ONE product Fa' diag(Wd_k) Fa
         Frag FaT{0.0, 0.0};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -889,76 +925,90 @@ struct Pdip {
             double v = 0.0;
             if (row < NCX) v = (r < 6) ? c.Fx[row * 6 + r] : 0.0;
             else if (row < NCX + NCU) v = (r >= 6) ? c.Fu[(row - NCX) * 2 + (r - 6)] : 0.0;
+            else if (row >= 6) v = (r == row) ? 1.0 : 0.0;
             if (h == 0) FaT.a = v; else FaT.b = v;
         }
+        // lane roles as 0/1 factors (selects on doubles cost two instructions each, a multiply-add one)
+        const double m_x = (r < 6) ? 1.0 : 0.0;                               // column r of Y comes from S (else: the -dR2 constant)
         const double y0c = (r == 6) ? -c.dR2[0] : 0.0, y1c = (r == 7) ? -c.dR2[1] : 0.0;
-        const bool keep = (r < 6 && q < 3);                 // entries of Sxx
+        const double m_keep = (r < 6 && q < 3) ? 1.0 : 0.0;                   // entries of Sxx
+        const double m_q0 = (q == 0) ? 1.0 : 0.0, m_q1 = (q == 1) ? 1.0 : 0.0, m_q3 = (q == 3) ? 1.0 : 0.0;
+        const double m_ru = (lane == 7) ? 0.0 : 1.0;                          // the costate has no input part
         const Frag Id = Frag{(q < 3 && r == 2 * q) ? 1.0 : 0.0, (q < 3 && r == 2 * q + 1) ? 1.0 : 0.0};   // M' for q < 3
 
         // terminal cost-to-go
         Frag Pf{0.0, 0.0};
-        if (keep) {
+        if (r < 6 && q < 3) {
             Pf.a = c.Qf2[r * 6 + 2 * q] + (LMPC ? w.Wi[(r * 6 + 2 * q) % TMW] : 0.0);
             Pf.b = c.Qf2[r * 6 + 2 * q + 1] + (LMPC ? w.Wi[(r * 6 + 2 * q + 1) % TMW] : 0.0);
         }
         Frag Vf = terminal_vec<true>(w, c1, r, q);
         bool bad = false;
+        // running pointers (stage N-1 first); lanes without a role in a load / store point at the zero constants / a dump slot
         const double* pa = base + lm.at_a + (N - 1) * lm.at_step;
         const double* pb_ = base + lm.at_b + (N - 1) * lm.at_step;
-        Frag At{*pa, *pb_}, Gn{0.0, 0.0};
-        if (lane < 8) Gn = ld2(&w.gv[N - 1][2 * lane]);
-#pragma unroll 1
+        const double* pw = &w.Wd[N - 1][2 * q];
+        const double* pg = (lane < 8) ? &w.gv[N - 1][2 * lane] : &w.cst[4];
+        const int g_step = (lane < 8) ? 16 : 0;
+        double* pk = &w.Kst[N - 1][r];
+        double* psi = &w.Sinv[N - 1][0];
+        double* pfs = &w.fst[N - 1][0];
+        double* pru = &w.ru[N - 1][0];
+        Frag At{*pa, *pb_}, Gn = ld2(pg), Wn = ld2(pw);
+LMPC_SWEEP_UNROLL
         for (int k = N - 1; k >= 0; --k) {
-            const Frag AtF = At, g = Gn;
-            const Frag wd = ld2(&w.Wd[k][2 * q]);
-            if (k > 0) {                                   // prefetch the next stage's operands off the dependent chain
-                pa -= lm.at_step; pb_ -= lm.at_step;
+            const Frag AtF = At, g = Gn, wd = Wn;
+            {   // prefetch the next stage's operands (k == 0 re-reads stage 0: no branch, nothing out of bounds)
+                const int st = (k > 0) ? 1 : 0;
+                pa -= st * lm.at_step; pb_ -= st * lm.at_step; pw -= st * 8; pg -= st * g_step;
                 At = Frag{*pa, *pb_};
-                if (lane < 8) Gn = ld2(&w.gv[k - 1][2 * lane]);
+                Gn = ld2(pg);
+                Wn = ld2(pw);
             }
             // ---- stage Hessian: constant part + Fa' diag(Wd_k) Fa as one product (independent of the Riccati chain)
-            Frag Hk = Hc;
-            if (k == N - 1) { Hk.a -= rate.a; Hk.b -= rate.b; }
-            const Frag Hf = prod_add(Frag{FaT.a * wd.a, FaT.b * wd.b}, FaT, Hk);
+            const Frag Hf = prod_add(Frag{FaT.a * wd.a, FaT.b * wd.b}, FaT, Hc);
             // ---- S = A~' P A~ + H
             const Frag Gp = prod(AtF, Pf);                 // A~' P   (P symmetric: its D layout is also its transposed layout)
             const Frag S = prod_add(Gp, AtF, Hf);
-            // ---- row vectors: A~' c + g (row 0), A~' pi - gst (row 1)
+            // ---- row vectors: A~' c + g (row 0), A~' pi - gst (row 1); rows 2..7 stay 0
             const Frag Tv = prod(Vf, AtF);
-            Frag Hv{Tv.a + g.a, Tv.b + g.b};               // rows other than 0, 1: 0 + 0
-            if (lane == 7) { st2(&w.ru[k][0], -Hv.a, -Hv.b); Hv = Frag{0.0, 0.0}; }   // ru = gst_u - B' pi; costate has no input part
+            const Frag Hraw{Tv.a + g.a, Tv.b + g.b};
+            if (lane == 7) st2(pru, -Hraw.a, -Hraw.b);      // ru = gst_u - B' pi
+            const Frag Hv{Hraw.a * m_ru, Hraw.b * m_ru};
             // ---- 2x2 Cholesky of Suu (every lane the same values)
             double s66 = bcast(S.a, 27);
             const double s76 = bcast(S.a, 31);
             const double s77 = bcast(S.b, 31);
+            double y0 = bcast(S.a, lane | 3), y1 = bcast(S.b, lane | 3);     // Sux(:, r) = S[r][6..7] sits in lane 4r+3
             if (!(s66 > 0.0)) { bad = true; s66 = 1.0; }
-            double det = s66 * s77 - s76 * s76;
+            double det = fma(s66, s77, -s76 * s76);
             if (!(det > 0.0)) { bad = true; det = 1.0; }
             const double i00 = rsqrt_f64(s66);
+            const double rdet = rsqrt_f64(det);             // independent of the first rsqrt
             const double l10 = s76 * i00;
-            const double i11 = rsqrt_f64(det) * (s66 * i00);      // 1 / sqrt(s77 - l10^2), independent of the first rsqrt
-            // ---- Z = L^-1 Y and K = -L^-T Z, column r (Y = [Sux | -dR2]; Sux(:, r) = S[r][6..7] sits in lane 4r+3)
-            double y0 = bcast(S.a, lane | 3), y1 = bcast(S.b, lane | 3);
-            if (r >= 6) { y0 = y0c; y1 = y1c; }
+            const double i11 = rdet * (s66 * i00);          // 1 / sqrt(s77 - l10^2)
+            // ---- Z = L^-1 Y and K = -L^-T Z, column r (Y = [Sux | -dR2])
+            y0 = fma(m_x, y0, y0c);
+            y1 = fma(m_x, y1, y1c);
             const double z0r = y0 * i00;
             const double z1r = (y1 - l10 * z0r) * i11;
             const double k1r = -z1r * i11;
             const double k0r = (-z0r - l10 * k1r) * i00;
-            if (q == 0) { w.Kst[k][r] = k0r; w.Kst[k][8 + r] = k1r; }
+            if (q == 0) { pk[0] = k0r; pk[8] = k1r; }
             // ---- inverse input Hessian, feed-forward term f = -Suu^-1 h_u (h_u sits in lane 3)
             const double t = l10 * i00 * i11;
-            const double s11 = i11 * i11, s01 = -t * i11, s00 = i00 * i00 + t * t;
+            const double s11 = i11 * i11, s01 = -t * i11, s00 = fma(i00, i00, t * t);
             if (lane == 3) {
-                st2(&w.Sinv[k][0], s00, s01);
-                w.Sinv[k][2] = s11;
-                st2(&w.fst[k][0], -(s00 * Hv.a + s01 * Hv.b), -(s01 * Hv.a + s11 * Hv.b));
+                st2(psi, s00, s01);
+                psi[2] = s11;
+                st2(pfs, -fma(s00, Hv.a, s01 * Hv.b), -fma(s01, Hv.a, s11 * Hv.b));
             }
             // ---- cost-to-go Hessian of stage k: [Sxx 0; 0 0] - Z'Z  (rank-2 update as one MMA, k = 0,1 used)
-            const double zsel = (q == 0) ? z0r : ((q == 1) ? z1r : 0.0);
-            dmma(Pf.a, Pf.b, -zsel, zsel, keep ? S.a : 0.0, keep ? S.b : 0.0);
+            const double zsel = fma(m_q0, z0r, m_q1 * z1r);
+            dmma(Pf.a, Pf.b, -zsel, zsel, m_keep * S.a, m_keep * S.b);
             // ---- c_k = M' h (row 0); the costate passes through the identity part (row 1)
-            const Frag MT = (q < 3) ? Id : Frag{k0r, k1r};
-            Vf = prod(Hv, MT);
+            Vf = prod(Hv, Frag{fma(m_q3, k0r, Id.a), fma(m_q3, k1r, Id.b)});
+            pk -= 16; psi -= 4; pfs -= 2; pru -= 2;
         }
         if (bad && lane == 0) w.flag = ST_NUMERICAL;
         wsync();
@@ -969,32 +1019,39 @@ struct Pdip {
 
     // Gradient-only backward sweep for a new right-hand side (corrector / recentring): c_k = M'(A~'c + g_k), f_k.
     static LMPC_HD void backward_rhs(W& w, const FtocpConst& c, const double* c1) {
-        const LaneMap lm = lane_map(w);
-        const int lane = LMPC_LANE, r = lm.r, q = lm.q;
+        const int lane = sweep_lane();
+        const LaneMap lm = lane_map(w, lane);
+        const int r = lm.r, q = lm.q;
         const double* base = &w.ABC[0][0];
         Frag Vf = terminal_vec<false>(w, c1, r, q);
         const double* pa = base + lm.at_a + (N - 1) * lm.at_step;
         const double* pb_ = base + lm.at_b + (N - 1) * lm.at_step;
         const double* ma = base + lm.mt_a + (N - 1) * lm.mt_step;
         const double* mb = base + lm.mt_b + (N - 1) * lm.mt_step;
-        Frag At{*pa, *pb_}, Mt{*ma, *mb}, Gn{0.0, 0.0};
-        if (lane < 4) Gn = ld2(&w.gv[N - 1][2 * lane]);
-#pragma unroll 1
+        const double* pg = (lane < 4) ? &w.gv[N - 1][2 * lane] : &w.cst[4];
+        const int g_step = (lane < 4) ? 16 : 0;
+        const double* psi = &w.Sinv[N - 1][0];
+        double* pfs = &w.fst[N - 1][0];
+        Frag At{*pa, *pb_}, Mt{*ma, *mb}, Gn = ld2(pg), Sn = ld2(psi);
+        double S2n = psi[2];
+LMPC_SWEEP_UNROLL
         for (int k = N - 1; k >= 0; --k) {
-            const Frag AtF = At, MT = Mt, g = Gn;
-            if (k > 0) {                                   // prefetch the next stage's operands off the dependent chain
-                pa -= lm.at_step; pb_ -= lm.at_step; ma -= lm.mt_step; mb -= lm.mt_step;
+            const Frag AtF = At, MT = Mt, g = Gn, s0 = Sn;
+            const double s11 = S2n;
+            {   // prefetch the next stage's operands off the dependent chain (k == 0 re-reads stage 0)
+                const int st = (k > 0) ? 1 : 0;
+                pa -= st * lm.at_step; pb_ -= st * lm.at_step; ma -= st * lm.mt_step; mb -= st * lm.mt_step;
+                pg -= st * g_step; psi -= st * 4;
                 At = Frag{*pa, *pb_};
                 Mt = Frag{*ma, *mb};
-                if (lane < 4) Gn = ld2(&w.gv[k - 1][2 * lane]);
+                Gn = ld2(pg);
+                Sn = ld2(psi);
+                S2n = psi[2];
             }
             const Frag Tv = prod(Vf, AtF);
             const Frag Hv{Tv.a + g.a, Tv.b + g.b};         // rows other than 0: 0 + 0
-            if (lane == 3) {
-                const Frag s0 = ld2(&w.Sinv[k][0]);
-                const double s11 = w.Sinv[k][2];
-                st2(&w.fst[k][0], -(s0.a * Hv.a + s0.b * Hv.b), -(s0.b * Hv.a + s11 * Hv.b));
-            }
+            if (lane == 3) st2(pfs, -fma(s0.a, Hv.a, s0.b * Hv.b), -fma(s0.b, Hv.a, s11 * Hv.b));
+            pfs -= 2;
             Vf = prod(Hv, MT);
         }
         wsync();
@@ -1002,26 +1059,31 @@ struct Pdip {
 
     // Forward sweep: (dx_k, du_k) = M w_k + (0, f_k), w_{k+1} = A~ (dx_k, du_k), from w_0 = 0.
     static LMPC_HD void forward(W& w) {
-        const LaneMap lm = lane_map(w);
-        const int lane = LMPC_LANE;
+        const int lane = sweep_lane();
+        const LaneMap lm = lane_map(w, lane);
         const double* base = &w.ABC[0][0];
         const double* pf = base + lm.af;
         const double* pm = base + lm.mf;
+        const double* pc = (lane == 3) ? &w.fst[0][0] : &w.cst[4];
+        const int c_step = (lane == 3) ? 2 : 0;
+        // one store per stage: lanes 0..2 write dx_k, lane 3 writes du_k
+        double* po = (lane < 3) ? &w.dx[2 * lane] : &w.du[0];
+        const int o_step = (lane < 3) ? 6 : 2;
         Frag Wf{0.0, 0.0};
-        Frag Af = ld2(pf), Mf = ld2(pm), Cf{0.0, 0.0};
-        if (lane == 3) Cf = ld2(&w.fst[0][0]);
-#pragma unroll 1
+        Frag Af = ld2(pf), Mf = ld2(pm), Cf = ld2(pc);
+LMPC_SWEEP_UNROLL
         for (int k = 0; k < N; ++k) {
             const Frag AF = Af, MF = Mf, CF = Cf;
-            if (k + 1 < N) {                               // prefetch the next stage's operands off the dependent chain
-                pf += lm.af_step; pm += lm.mf_step;
+            {   // prefetch the next stage's operands off the dependent chain (the last stage re-reads itself)
+                const int st = (k + 1 < N) ? 1 : 0;
+                pf += st * lm.af_step; pm += st * lm.mf_step; pc += st * c_step;
                 Af = ld2(pf);
                 Mf = ld2(pm);
-                if (lane == 3) Cf = ld2(&w.fst[k + 1][0]);
+                Cf = ld2(pc);
             }
             const Frag Uf = prod_add(Wf, MF, CF);          // row 0: (dx_k | du_k)
-            if (lane < 3) st2(&w.dx[k * 6 + 2 * lane], Uf.a, Uf.b);
-            if (lane == 3) st2(&w.du[k * 2], Uf.a, Uf.b);
+            if (lane < 4) st2(po, Uf.a, Uf.b);
+            po += o_step;
             Wf = prod(Uf, AF);                             // row 0: (dx_{k+1} | du_k)
         }
         if (lane < 3) st2(&w.dx[N * 6 + 2 * lane], Wf.a, Wf.b);
@@ -1030,20 +1092,21 @@ struct Pdip {
 
     // Model roll-out of the starting point with a constant input: (x_{k+1} | u) = A~ (x_k | u) + (C_k | 0)
     static LMPC_HD void rollout(W& w, const double* x0, double u0, double u1) {
-        const LaneMap lm = lane_map(w);
-        const int lane = LMPC_LANE;
+        const int lane = sweep_lane();
+        const LaneMap lm = lane_map(w, lane);
         const double* pf = &w.ABC[0][0] + lm.af;
+        const double* pc = (lane < 3) ? &w.ABC[0][48 + 2 * lane] : &w.cst[4];
+        const int c_step = (lane < 3) ? 54 : 0;
         Frag Wf{0.0, 0.0};
-        if (lane < 3) Wf = Frag{x0[2 * lane], x0[2 * lane + 1]};
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+            if (lane == h) Wf = Frag{x0[2 * h], x0[2 * h + 1]};
         if (lane == 3) Wf = Frag{u0, u1};
         if (lane < 3) st2(&w.x[2 * lane], Wf.a, Wf.b);
-#pragma unroll 1
+LMPC_SWEEP_UNROLL
         for (int k = 0; k < N; ++k) {
-            const Frag AF = ld2(pf);
-            pf += lm.af_step;
-            Frag CF{0.0, 0.0};
-            if (lane < 3) CF = ld2(&w.ABC[k][48 + 2 * lane]);
-            Wf = prod_add(Wf, AF, CF);
+            Wf = prod_add(Wf, ld2(pf), ld2(pc));
+            pf += lm.af_step; pc += c_step;
             if (lane < 3) st2(&w.x[(k + 1) * 6 + 2 * lane], Wf.a, Wf.b);
         }
         wsync();
@@ -1067,7 +1130,7 @@ struct Pdip {
             for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * v[b];
             dyT[a] = t;
         }
-        const double dy1t = -beta / delta;
+        const double dy1t = -beta * recip(delta);
         double acc[6] = {0, 0, 0, 0, 0, 0};
         FOR_SLOTS(r, row, R4) {
             double t = g.rho[r] - dy1t;
@@ -1114,7 +1177,7 @@ struct Pdip {
         init_point(w, g, c, x0);
         const double n_ineq = (double)(2 * R1 + R2 + (LMPC ? M : 0));
         int it = 0, status = ST_MAX_ITER, late = 0;
-        double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0;
+        double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0, step_prev = 1e300;
         const double d4_floor = c.d4_min;
 
         for (;; ++it) {
@@ -1128,11 +1191,11 @@ struct Pdip {
                 g.rs[r] = rs;
                 rd_loc = fmax(rd_loc, fabs(rs));
                 comp += w1 * g.nu1[r] + g.s[r] * g.nu3[r];
-                const double iw1 = 1.0 / w1, is = 1.0 / g.s[r];
+                const double iw1 = recip(w1), is = recip(g.s[r]);
                 g.iw1[r] = iw1;
                 g.is_[r] = is;
                 double d1 = g.nu1[r] * iw1, d3 = g.nu3[r] * is;
-                const double ihs = 1.0 / (c.qs2 + d1 + d3);
+                const double ihs = recip(c.qs2 + d1 + d3);
                 g.d1[r] = d1;
                 g.ihs[r] = ihs;
                 LMPC_WDT(w, k, i, row) = d1 * (c.qs2 + d3) * ihs;
@@ -1145,7 +1208,7 @@ struct Pdip {
                 double w2 = c.bu[j] - (c.Fu[j * 2] * w.u[k * 2] + c.Fu[j * 2 + 1] * w.u[k * 2 + 1]);
                 g.w2[r] = w2;
                 comp += w2 * g.nu2[r];
-                const double iw2 = 1.0 / w2;
+                const double iw2 = recip(w2);
                 g.iw2[r] = iw2;
                 LMPC_WD2(w, k, j, row) = g.nu2[r] * iw2;
                 w.eu[row] = -g.nu2[r];           // predictor: -rc2/w2
@@ -1161,14 +1224,14 @@ struct Pdip {
                     g.rl[r] = rl;
                     rd_loc = fmax(rd_loc, fabs(rl));
                     comp += g.lam[r] * g.nu4[r];
-                    g.ilam[r] = 1.0 / g.lam[r];
+                    g.ilam[r] = recip(g.lam[r]);
                     g.rho[r] = -rl - g.nu4[r];   // predictor: rc4/lam = nu4
                 }
             } else {
                 wsync();
             }
             comp = wsum(comp);
-            mu = comp / n_ineq;
+            mu = comp * (1.0 / n_ineq);
             rd_loc = wmax(rd_loc);
             r_prim = fabs(rone);
             if (it > 0) {
@@ -1176,7 +1239,11 @@ struct Pdip {
                 // length, so after a step alpha it is exactly (1 - alpha) times its previous value: convergence can be
                 // decided here, before paying for another factorisation.
                 r_dual = fmax(rd_loc, (1.0 - al_prev) * ru_prev);
-                if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap) { status = ST_SOLVED; break; }
+                // Residuals and gap alone do not bound the distance to the optimum: on a QP without strict complementarity the
+                // iterate trails the solution by O(sqrt(mu)) (one of the 4096 configs[1] QPs sat 7.5e-6 away at mu = 1e-11 with
+                // residuals at rounding level).  The primal step just taken does: the iteration is superlinear, so once a step
+                // moved (x, u) by less than eps_step the remaining distance is smaller still.
+                if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap && step_prev <= c.eps_step) { status = ST_SOLVED; break; }
                 // Stragglers: on a few LMPC instances (LP-degenerate simplex block) the covariance-form recovery of
                 // d(lambda) puts a noise floor of ~1e-7..1e-6 under the dual residual and the tail converges linearly.
                 // Once the iterate meets the 1e-6 parity contract, stop after LATE_ACCEPT_IT iterations (and at max_iter).
@@ -1204,7 +1271,7 @@ struct Pdip {
             ru_prev = ru_max;
             r_dual = fmax(rd_loc, ru_max);
             if (w.flag != 0) { status = w.flag; break; }
-            if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap) { status = ST_SOLVED; break; }
+            if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap && step_prev <= c.eps_step) { status = ST_SOLVED; break; }
             if (it >= c.max_iter) {
                 if (r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) { status = ST_SOLVED; late = 1; } else { status = ST_MAX_ITER; }
                 break;
@@ -1258,7 +1325,7 @@ struct Pdip {
                 FOR_SLOTS(r, row, R4) { comp_aff += g.lam[r] * g.nu4[r] * (1.0 - a_aff) + a_aff * a_aff * g.p4[r]; }
             }
             comp_aff = wsum(comp_aff);
-            double sig = comp_aff / comp;
+            double sig = comp_aff * recip(comp);
             sig = sig * sig * sig;
             const double sm = sig * mu;
 
@@ -1370,7 +1437,7 @@ struct Pdip {
                     }
                     pmin = wmin(pmin);
                     psum = wsum(psum);
-                    if (pmin >= CENTRALITY_GAMMA * psum / n_ineq) { inside = true; break; }
+                    if (pmin >= (CENTRALITY_GAMMA / n_ineq) * psum) { inside = true; break; }
                     if (pass == 0 && tries >= RECENTRE_AFTER) break;
                     al *= 0.8;
                 }
@@ -1394,8 +1461,10 @@ struct Pdip {
                 g.y1 += al * dy1;
             }
             al_prev = al;
-            FOR_LANES(e, (N + 1) * 6) w.x[e] += al * w.dx[e];
-            FOR_LANES(e, N * 2) w.u[e] += al * w.du[e];
+            double dmax = 0.0;
+            FOR_LANES(e, (N + 1) * 6) { const double d = al * w.dx[e]; w.x[e] += d; dmax = fmax(dmax, fabs(d)); }
+            FOR_LANES(e, N * 2) { const double d = al * w.du[e]; w.u[e] += d; dmax = fmax(dmax, fabs(d)); }
+            step_prev = wmax(dmax);
             wsync();
         }
 

@@ -81,8 +81,16 @@ struct KernelSmem {
     alignas(8) uint64_t bar;
 };
 
+// resident CTAs (= warps) per SM the register allocation is held to: horizons up to 14 are bounded by registers and shared
+// memory alike; longer horizons by shared memory only
+#ifndef LMPC_LB_MPC
+#define LMPC_LB_MPC 16
+#endif
+#ifndef LMPC_LB_LMPC
+#define LMPC_LB_LMPC 12
+#endif
 template <int N, int M, int NCX, int NCU>
-__global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? 12 : 16) : 1)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
+__global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? LMPC_LB_LMPC : LMPC_LB_MPC) : 1)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using KS = KernelSmem<N, M, NCX, NCU>;
     KS& ks = *reinterpret_cast<KS*>(smem_raw);
@@ -250,6 +258,7 @@ static int build_const(const lmpc_params& p, FtocpConst& c) {
     }
     c.eps_res = p.eps_res > 0 ? p.eps_res : 1e-9;
     c.eps_gap = p.eps_gap > 0 ? p.eps_gap : 1e-11;
+    c.eps_step = p.eps_step > 0 ? p.eps_step : 1e-7;
     c.d4_min = 1e-6;
     c.max_iter = p.max_iter > 0 ? p.max_iter : 40;
     return LMPC_OK;
@@ -999,7 +1008,7 @@ void* lmpc_device_buffer(lmpc_handle* h, const char* name) {
         {"xPred", h->d_xPred}, {"uPred", h->d_uPred}, {"lambd", h->d_lambd}, {"zt", h->d_zt}, {"zt_u", h->d_ztu},
         {"abc", h->d_abc}, {"SS_sel", h->d_SS}, {"Qfun_sel", h->d_Qfun}, {"Succ_SS", h->d_SuccSS}, {"Succ_uSS", h->d_SuccU},
         {"status", h->d_status}, {"iters", h->d_iters}, {"resid", h->d_resid}, {"flags", h->d_flags}, {"xLin", h->d_xLin},
-        {"uLin", h->d_uLin}, {"x0", h->d_x0}, {"OldInput", h->d_OldInput}, {"abc_lti", h->has_rollout ? h->d_abc_lti : nullptr}};
+        {"uLin", h->d_uLin}, {"x0", h->d_x0}, {"slack", h->d_slack}, {"slackT", h->d_slackT}, {"OldInput", h->d_OldInput}, {"abc_lti", h->has_rollout ? h->d_abc_lti : nullptr}};
     for (auto& e : tab) if (strcmp(e.n, name) == 0) return e.p;
     return nullptr;
 }

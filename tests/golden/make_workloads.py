@@ -10,7 +10,7 @@
 Produced with the ORACLE restatement (oracle/ltv_model.py), which tests/golden/make_golden.py pins
 bit-exactly against the real reference.  bench.py and the tests tile these NSTART model sets to the
 batch size and perturb x0 per instance with np.random.default_rng(1) noise.
-Horizons: N = 12 (bench) and N = 6, 24, 48 (horizon-sweep parity cases, fewer starts).
+Horizons: N = 12 (bench), N = 6, 24, 48 (horizon-sweep parity cases, fewer starts) and N = 14 (the reference's own, main.py:43).
 """
 import os
 import sys
@@ -31,7 +31,7 @@ def main():
     pm = ltv_model.LocalLTVModel(6, 2, trk, 1)
     pm.addTrajectory(xP, uP)
     out = {}
-    for N, nstart in ((12, 256), (6, 32), (24, 32), (48, 32)):
+    for N, nstart in ((12, 256), (6, 32), (24, 32), (48, 32), (14, 32)):
         T = xP.shape[0]
         starts = 1 + (np.arange(nstart) * (T - N - 2)) // nstart
         abc = np.zeros((nstart, N, 54))

@@ -19,11 +19,11 @@ class FtocpConst(C.Structure):
                 ("Fx", C.c_double * (MAX_NCX * 6)), ("bx", C.c_double * MAX_NCX),
                 ("Fu", C.c_double * (MAX_NCU * 2)), ("bu", C.c_double * MAX_NCU),
                 ("T", C.c_double * 36), ("Tinv", C.c_double * 36),
-                ("eps_res", C.c_double), ("eps_gap", C.c_double), ("d4_min", C.c_double),
+                ("eps_res", C.c_double), ("eps_gap", C.c_double), ("d4_min", C.c_double), ("eps_step", C.c_double),
                 ("max_iter", C.c_int), ("pad_", C.c_int)]
 
 
-def make_const(p, Qts=None, eps_res=1e-9, eps_gap=1e-11, d4_min=1e-6, max_iter=40):
+def make_const(p, Qts=None, eps_res=1e-9, eps_gap=1e-11, d4_min=1e-6, max_iter=40, eps_step=1e-7):
     """p: any object with the reference's MPCParams field names."""
     c = FtocpConst()
     Q, R, Qf = np.asarray(p.Q, float), np.asarray(p.R, float), np.asarray(p.Qf, float)
@@ -44,7 +44,7 @@ def make_const(p, Qts=None, eps_res=1e-9, eps_gap=1e-11, d4_min=1e-6, max_iter=4
     T = 2 * np.asarray(Qts, float) if Qts is not None else np.eye(6)
     c.T[:] = T.ravel()
     c.Tinv[:] = np.linalg.inv(T).ravel()
-    c.eps_res, c.eps_gap, c.d4_min, c.max_iter = eps_res, eps_gap, d4_min, max_iter
+    c.eps_res, c.eps_gap, c.d4_min, c.max_iter, c.eps_step = eps_res, eps_gap, d4_min, max_iter, eps_step
     return c
 
 
