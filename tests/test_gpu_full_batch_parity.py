@@ -14,7 +14,8 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# the worker pools fork on purpose (the workload is shared copy-on-write; the children never touch CUDA or threads)
+pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore:This process .* is multi-threaded:DeprecationWarning")]
 
 from racinglmpc_b200 import BatchedFTOCP, pack_abc, workloads, reference_params as rp   # noqa: E402
 from racinglmpc_b200.controller import BatchedController                                 # noqa: E402
@@ -123,9 +124,10 @@ def test_config2_all_4096_instances_vs_oracle(track):
     assert err[ok].max() < 1e-6, (err[ok].max(), int(np.where(ok)[0][err[ok].argmax()]))
     r = _kkt_all(orc["prob"], z, zo)
     assert r[:, 0].max() < 1e-6 and r[:, 1].max() < 1e-6, (r[:, 0].max(), r[:, 1].max(), int(r[:, 1].argmax()))
-    # never worse than the oracle's point (its unconverged points are infeasible by up to 1e-4: allow that much objective slack)
-    gap = r[:, 2] - r[:, 3]
-    assert gap[ok].max() < 1e-6 and gap.max() < 1e-2, (gap[ok].max(), gap.max())
+    # same objective as the oracle's certified optimum (both points are feasible only to their residuals, and the multipliers
+    # are O(1e3): 1e-9 of the objective + 1e-6).  Uncertified oracle points are infeasible by up to 1e-4 and say nothing.
+    gap = np.abs(r[:, 2] - r[:, 3])
+    assert np.all(gap[ok] <= 1e-9 * np.abs(r[ok, 3]) + 1e-6), (gap[ok].max(), np.abs(r[ok, 3]).max())
     print("configs[2]: oracle certified %d / %d; max |dz| on those %.2e; KKT max %.2e / %.2e over all" %
           (ok.sum(), B, err[ok].max(), r[:, 0].max(), r[:, 1].max()))
 
@@ -189,7 +191,7 @@ def test_lmpc_qp_instantiations_vs_oracle(gold, track, N, dup):
         assert np.abs(z[ok, :n] - zo[ok, :n]).max() < 1e-6, np.abs(z[ok, :n] - zo[ok, :n]).max()
     r = _kkt_all(prob, z, zo)
     assert r[:, 0].max() < 1e-6 and r[:, 1].max() < 1e-6, r[:, :2].max(axis=0)
-    assert (r[:, 2] - r[:, 3])[ok].max(initial=-1.0) < 1e-6
+    assert np.all(np.abs(r[:, 2] - r[:, 3])[ok] <= 1e-9 * np.abs(r[ok, 3]) + 1e-6)
     # zt = Succ_SS lam, zt_u = Succ_uSS lam (PC.py:382-384)
     assert np.abs(o["zt"] - np.einsum("bij,bj->bi", SuS, o["lambd"])).max() < 1e-12
     assert np.abs(o["zt_u"] - np.einsum("bij,bj->bi", SuU, o["lambd"])).max() < 1e-12
