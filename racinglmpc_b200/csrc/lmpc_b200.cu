@@ -871,7 +871,7 @@ static int launch_k1(lmpc_handle* h) {
     a.pts_stride = k1_pts_stride(h->mc.trToUse);
     a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
     dim3 grid(h->batch, (h->N + a.wpb - 1) / a.wpb);
-    size_t smem = sizeof(double) * ((size_t)5 * K1_TILE + (size_t)a.pts_stride * a.wpb);
+    size_t smem = sizeof(float) * 5 * K1_TILE + sizeof(double) * (size_t)a.pts_stride * a.wpb;
     knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, h->stream>>>(h->mc, a);
     CK(cudaGetLastError());
     h->launches += 1;

@@ -99,7 +99,9 @@ __device__ __forceinline__ bool solve5(double (&A)[5][5], double (&b)[NR][5]) {
 
 constexpr int K1_MAXPTS = 7;     // MaxNumPoint supported by the register top-k
 constexpr int K1_MAXLAPS = 8;    // trToUse supported
-constexpr int K1_TILE = 256;     // lap rows staged in shared memory per pass
+constexpr int K1_TILE = 512;     // lap rows staged in shared memory per pass (fp32 features)
+constexpr int K1_LOCAL = 3;      // entries of the lane-local candidate list
+constexpr int K1_CAND = 32;      // exact re-scoring buffer per warp
 
 struct K1Args {
     int batch, N, wpb, pts_stride;   // warps per block; doubles of per-warp scratch (see k1_pts_stride)
@@ -109,17 +111,42 @@ struct K1Args {
     const int* used;      // [B][trToUse] slot ids, in usedIt order
     double* abc;          // [B][N][54]
     int* status;          // [B] : 0 ok, else bit flags (1 = singular regression, 2 = curvature lookup failed,
-                          //        4 = a single neighbour in a lap — cases where the reference raises)
+                          //        4 = a single neighbour in a lap — cases where the reference raises,
+                          //        32 = more than K1_CAND rows within rounding distance of the k-th neighbour)
 };
 // per-warp scratch: selected points [7*trToUse][10] (x0 x1 x2 u0 u1 K y0 y1 y2 1) | normal equations 45 (+3 pad)
 //                   | two augmented systems 5x6 + 5x7 (+3 pad)
-//                   | candidate buffer 64 distances + 64 row indices
+//                   | re-scoring buffer: K1_CAND exact distances + K1_CAND row indices | the query point (5 doubles, +1 pad)
 constexpr int K1_PW = 10;        // doubles per selected point
-__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * K1_PW + 48 + 68 + 96; }
+__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * K1_PW + 48 + 68 + K1_CAND + K1_CAND / 2 + 6; }
 
-// grid = (B, ceil(N / wpb)); one warp per horizon step; the CTA stages each lap tile in shared memory once
-// (feature-major, conflict-free) and every warp scans it for its own query point.
-__global__ void __launch_bounds__(32 * 12, 3) knn_ltv_regress_kernel(const __grid_constant__ ModelConst m, const K1Args a) {
+// The reference's distance of one stored row to the query (PM.py:185-186): diff = (Data - x) * scaling, 1-norm summed left to
+// right (numpy semantics for 5 columns), in IEEE fp64 with no contraction: the value np.argsort ranks.
+__device__ __noinline__ double k1_exact_dist(const ModelConst& m, const double* X, const double* U, int t, const double* q) {
+    const double* xr = X + (size_t)t * 6;
+    const double* ur = U + (size_t)t * 2;
+    double d = fabs(__dmul_rn(__dsub_rn(xr[0], q[0]), m.scaling[0]));
+    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(xr[1], q[1]), m.scaling[1])));
+    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(xr[2], q[2]), m.scaling[2])));
+    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(ur[0], q[3]), m.scaling[3])));
+    d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(ur[1], q[4]), m.scaling[4])));
+    return d;
+}
+
+// grid = (B, ceil(N / wpb)); one warp per horizon step (= query point).  Per stored lap:
+//   1. the CTA stages the lap's five regression features as fp32, feature-major, in shared memory (tiles of K1_TILE rows) and
+//      every warp scans the tile for its own query with an fp32 distance -- ten full-rate instructions per row instead of
+//      fourteen half-rate fp64 ones -- keeping the K1_LOCAL best rows of every lane in registers;
+//   2. the warp merges the lane lists: g = k-th smallest fp32 distance; every row with an fp32 distance within the rounding
+//      margin of g is re-scored with the reference's exact fp64 distance (global memory, a few rows) and the exact k nearest
+//      are selected on the key (distance, row) -- bit for bit the rows np.argsort picks (PM.py:189), ties to the lower row;
+//   3. a lane list that may have dropped such a row (its last entry is still within the margin) makes the warp re-collect
+//      from global memory with the now known threshold (rare: more than K1_LOCAL near-ties in one lane).
+// HBM traffic is one pass over the used laps per CTA; the scan is instruction-issue bound.
+#ifndef LMPC_K1_MINBLOCKS
+#define LMPC_K1_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_kernel(const __grid_constant__ ModelConst m, const K1Args a) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     const int b = blockIdx.x;
     const int wib = threadIdx.x >> 5;
@@ -127,18 +154,29 @@ __global__ void __launch_bounds__(32 * 12, 3) knn_ltv_regress_kernel(const __gri
     const int lane = threadIdx.x & 31;
     const int nthr = blockDim.x;
     const bool active = (i < a.N);            // all warps take part in the tile loads
-    double* tile = reinterpret_cast<double*>(k1_smem);                 // [5][K1_TILE] : vx vy wz | delta a
-    double* pts = tile + 5 * K1_TILE + (size_t)wib * a.pts_stride;     // this warp's scratch
+    float4* tile4 = reinterpret_cast<float4*>(k1_smem);                // [K1_TILE] : (vx, vy, wz, delta) of a row, one 16-byte load
+    float* tile1 = reinterpret_cast<float*>(k1_smem) + 4 * K1_TILE;    // [K1_TILE] : a
+    double* wbase = reinterpret_cast<double*>(k1_smem + sizeof(float) * 5 * K1_TILE) + (size_t)wib * a.pts_stride;
+    double* pts = wbase;                                               // this warp's scratch
     const int np_max = K1_MAXPTS * m.trToUse;
     double* ne = pts + (size_t)np_max * K1_PW;                         // 48
     double* sys = ne + 48;                                             // 30 + 35 (+3)
-    double* cbd = sys + 68;                                            // candidate distances [64]
-    int* cbi = reinterpret_cast<int*>(cbd + 64);                       // candidate rows [64]
+    double* cbd = sys + 68;                                            // exact distances of the re-scored rows [K1_CAND]
+    int* cbi = reinterpret_cast<int*>(cbd + K1_CAND);                  // their row indices [K1_CAND]
 
     const int ii = active ? i : 0;
     const double* xl = a.xLin + ((size_t)b * (a.N + 1) + ii) * 6;
     const double* ul = a.uLin + ((size_t)b * a.N + ii) * 2;
-    const double q0 = xl[0], q1 = xl[1], q2 = xl[2], q3 = ul[0], q4 = ul[1];
+    // the fp64 query lives in shared memory (read on the rare exact paths only); the scan keeps its fp32 copy in registers
+    double* qv = reinterpret_cast<double*>(cbi + K1_CAND);
+    if (lane < 5) qv[lane] = (lane < 3) ? xl[lane] : ul[lane - 3];
+    __syncwarp();
+    const float f0 = (float)qv[0], f1 = (float)qv[1], f2 = (float)qv[2], f3 = (float)qv[3], f4 = (float)qv[4];
+    const float s0 = (float)m.scaling[0], s1 = (float)m.scaling[1], s2 = (float)m.scaling[2], s3 = (float)m.scaling[3], s4 = (float)m.scaling[4];
+    const float qsum = s0 * fabsf(f0) + s1 * fabsf(f1) + s2 * fabsf(f2) + s3 * fabsf(f3) + s4 * fabsf(f4);
+    const float hf = (float)m.h;
+    const float h_lo = hf;
+    const int kk = m.MaxNumPoint;
     int flags = 0, npts = 0;
 
     for (int c = 0; c < m.trToUse; ++c) {
@@ -147,127 +185,148 @@ __global__ void __launch_bounds__(32 * 12, 3) knn_ltv_regress_kernel(const __gri
         const double* X = a.pool.x + lap * a.pool.Tmax * 6;
         const double* U = a.pool.u + lap * a.pool.Tmax * 2;
         const int T = a.pool.len[lap];
-        // Warp-wide running top-k (k = MaxNumPoint): lanes 0..k-1 hold the current best (sorted), `tau` is the k-th
-        // best so far.  A row is a candidate only if it beats tau; candidates are compacted into a per-warp buffer
-        // (ballot + popc) and folded into the top-k when 32 or more have accumulated.
-        double topd = 1e300;            // lane r < k: r-th best distance so far
-        int topi = 0x7fffffff;
-        double tau_d = 1e300;           // k-th best (all lanes)
-        int tau_i = 0x7fffffff;
-        int nbuf = 0, cnt = 0;
-        const int kk = m.MaxNumPoint;
-        auto fold = [&]() {
-            // candidates: buffer entries lane, lane+32 (< nbuf <= 64) and the current top-k (lane < kk).
-            // kk rounds of warp arg-min on the key (distance bits, row): distances are non-negative doubles, so their bit
-            // patterns order like unsigned integers and three 32-bit REDUX.MIN (high word, low word, row) find the
-            // winner; only the winning lane updates its local minimum.
-            double c0d = (lane < nbuf) ? cbd[lane] : 1e300;
-            int c0i = (lane < nbuf) ? cbi[lane] : 0x7fffffff;
-            double c1d = (lane + 32 < nbuf) ? cbd[lane + 32] : 1e300;
-            int c1i = (lane + 32 < nbuf) ? cbi[lane + 32] : 0x7fffffff;
-            double c2d = (lane < kk) ? topd : 1e300;
-            int c2i = (lane < kk) ? topi : 0x7fffffff;
-            double nd = 1e300;
-            int ni = 0x7fffffff;
-            double ld = c0d;
-            int li = c0i;
-            if (cand_less(c1d, c1i, ld, li)) { ld = c1d; li = c1i; }
-            if (cand_less(c2d, c2i, ld, li)) { ld = c2d; li = c2i; }
-            for (int r = 0; r < kk; ++r) {
-                const unsigned hi = (unsigned)__double2hiint(ld), lo = (unsigned)__double2loint(ld);
-                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-                const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-                const bool eq = (hi == mh) && (lo == ml);
-                const int wi = (int)__reduce_min_sync(0xffffffffu, eq ? (unsigned)li : 0xffffffffu);
-                const double wd = __hiloint2double((int)mh, (int)ml);
-                if (eq && li == wi) {                       // the winning lane drops the entry and re-ranks its three
-                    if (c0i == wi) { c0d = 1e300; c0i = 0x7fffffff; }
-                    else if (c1i == wi) { c1d = 1e300; c1i = 0x7fffffff; }
-                    else { c2d = 1e300; c2i = 0x7fffffff; }
-                    ld = c0d; li = c0i;
-                    if (cand_less(c1d, c1i, ld, li)) { ld = c1d; li = c1i; }
-                    if (cand_less(c2d, c2i, ld, li)) { ld = c2d; li = c2i; }
-                }
-                if (lane == r) { nd = wd; ni = wi; }
-                if (r == kk - 1) { tau_d = wd; tau_i = wi; }
-            }
-            topd = nd; topi = ni;
-            nbuf = 0;
-            __syncwarp();
-        };
+        // lane-local candidate lists, ascending in the fp32 distance (earlier rows first on ties: rows arrive in order)
+        float ld[K1_LOCAL];
+        int li[K1_LOCAL];
+#pragma unroll
+        for (int j = 0; j < K1_LOCAL; ++j) { ld[j] = 3.0e38f; li[j] = 0x7fffffff; }
+        int cnt = 0;
+        float band = 3.0e38f;                                // smallest |d32 - h| seen: rows near the bandwidth need the exact test
+        float amax = 0.0f;                                   // largest scaled 1-norm of a stored row: sizes the rounding margin
         for (int t0 = 0; t0 < T - 1; t0 += K1_TILE) {
             const int rows = min(K1_TILE, T - 1 - t0);      // rows 0..T-2 are candidates (PM.py:183)
             __syncthreads();                                 // previous tile fully consumed
-            for (int r = threadIdx.x; r < rows; r += nthr) {            // one 48 B + one 16 B row per thread -> feature-major
+            for (int r = threadIdx.x; r < rows; r += nthr) {            // one 48 B + one 16 B row per thread -> feature-major fp32
                 const double2 v01 = *reinterpret_cast<const double2*>(X + (size_t)(t0 + r) * 6);
                 const double v2 = X[(size_t)(t0 + r) * 6 + 2];
                 const double2 uu = *reinterpret_cast<const double2*>(U + (size_t)(t0 + r) * 2);
-                tile[r] = v01.x; tile[K1_TILE + r] = v01.y; tile[2 * K1_TILE + r] = v2;
-                tile[3 * K1_TILE + r] = uu.x; tile[4 * K1_TILE + r] = uu.y;
+                tile4[r] = make_float4((float)v01.x, (float)v01.y, (float)v2, (float)uu.x);
+                tile1[r] = (float)uu.y;
             }
             __syncthreads();
             if (active) {
-                // Rows of the tile are visited in a scrambled order (r = 37 i mod 256, a bijection on the tile): stored laps
-                // are time series, and an in-order scan approaching the query makes almost every row a new candidate
-                // (a fold per batch); scrambled, tau tightens after the first batch and few rows pass.
-                for (int rb = 0; rb < K1_TILE; rb += 32) {
-                    const int r = ((rb + lane) * 37) & (K1_TILE - 1);
-                    bool cand = false;
-                    double d = 1e300;
-                    const int t = t0 + r;
+                for (int rb = 0; rb < rows; rb += 32) {
+                    const int r = rb + lane;
                     if (r < rows) {
-                        // diff = (Data - x) * scaling ; 1-norm summed left to right (numpy semantics for 5 columns)
-                        d = fabs(__dmul_rn(__dsub_rn(tile[r], q0), m.scaling[0]));
-                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[K1_TILE + r], q1), m.scaling[1])));
-                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[2 * K1_TILE + r], q2), m.scaling[2])));
-                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[3 * K1_TILE + r], q3), m.scaling[3])));
-                        d = __dadd_rn(d, fabs(__dmul_rn(__dsub_rn(tile[4 * K1_TILE + r], q4), m.scaling[4])));
-                        if (d < m.h) ++cnt;
-                        cand = cand_less(d, t, tau_d, tau_i);
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, cand);
-                    if (mask) {
-                        if (cand) {
-                            const int pos = nbuf + __popc(mask & ((1u << lane) - 1u));
-                            cbd[pos] = d;
-                            cbi[pos] = t;
+                        const float4 xv = tile4[r];
+                        const float x4 = tile1[r];
+                        float d = s0 * fabsf(xv.x - f0);
+                        d = fmaf(s1, fabsf(xv.y - f1), d);
+                        d = fmaf(s2, fabsf(xv.z - f2), d);
+                        d = fmaf(s3, fabsf(xv.w - f3), d);
+                        d = fmaf(s4, fabsf(x4 - f4), d);
+                        amax = fmaxf(amax, d);               // d + qsum bounds the row's own scaled norm
+                        const int t = t0 + r;
+                        cnt += (d < h_lo) ? 1 : 0;
+                        band = fminf(band, fabsf(d - hf));   // a row this close to the bandwidth is decided in fp64 afterwards
+                        if (d < ld[K1_LOCAL - 1]) {
+                            ld[K1_LOCAL - 1] = d; li[K1_LOCAL - 1] = t;
+#pragma unroll
+                            for (int j = K1_LOCAL - 1; j > 0; --j) {
+                                if (ld[j] < ld[j - 1]) {
+                                    const float td = ld[j]; ld[j] = ld[j - 1]; ld[j - 1] = td;
+                                    const int ti = li[j]; li[j] = li[j - 1]; li[j - 1] = ti;
+                                }
+                            }
                         }
-                        nbuf += __popc(mask);
-                        __syncwarp();
-                        if (nbuf > 32) fold();
                     }
                 }
             }
         }
         if (!active) continue;
-        if (nbuf > 0) fold();
+        if (__any_sync(0xffffffffu, band <= hf * 1e-3f)) {    // rare: some row is within 0.1 % of the bandwidth -> exact recount
+            cnt = 0;
+            for (int t = lane; t < T - 1; t += 32) cnt += (k1_exact_dist(m, X, U, t, qv) < m.h) ? 1 : 0;
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
         // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside
-        const int ksel = cnt >= m.MaxNumPoint ? m.MaxNumPoint : cnt;
+        const int ksel = cnt >= kk ? kk : cnt;
         if (cnt == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
-        {
-            // lane r < ksel owns the r-th neighbour: kernel weight once per lane (PM.py:193), then the 10 values of every
-            // selected row are fetched by ksel*10 lanes in parallel
-            const double rr = topd / m.h;
-            const double kw = (1.0 - rr * rr) * 3.0 / 4.0;
-            const int nval = ksel * K1_PW;
-            for (int e0 = 0; e0 < nval; e0 += 32) {
-                const int e = e0 + lane;
-                int r = e / K1_PW;
-                const int f = e - r * K1_PW;
-                r = r < K1_MAXPTS ? r : K1_MAXPTS - 1;
-                const int wi = __shfl_sync(0xffffffffu, topi, r);
-                const double kr = __shfl_sync(0xffffffffu, kw, r);
-                if (e < nval) {
-                    double v;
-                    if (f < 3) v = X[(size_t)wi * 6 + f];
-                    else if (f < 5) v = U[(size_t)wi * 2 + (f - 3)];
-                    else if (f == 5) v = kr;
-                    else if (f < 9) v = X[(size_t)(wi + 1) * 6 + (f - 6)];
-                    else v = 1.0;
-                    pts[(size_t)npts * K1_PW + e] = v;
+        // ---- merge: g = k-th smallest fp32 distance over all lane lists (non-negative floats order like their bit patterns:
+        //      one REDUX.MIN per round); the lists are not consumed, a head counter per lane walks them
+        int hp = 0;
+        float g = 3.0e38f;
+        for (int rnd = 0; rnd < kk; ++rnd) {
+            float hd = 3.0e38f;
+#pragma unroll
+            for (int j = 0; j < K1_LOCAL; ++j) hd = (hp == j) ? ld[j] : hd;
+            const unsigned mn = __reduce_min_sync(0xffffffffu, __float_as_uint(hd));
+            g = __uint_as_float(mn);
+            const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(hd) == mn);
+            if (lane == (__ffs(who) - 1)) ++hp;
+        }
+        // |d32 - d64| < (|row| + |query|) 4.2e-7 (inputs rounded to fp32, five fused terms); a row of the exact top-k is within
+        // twice that of g.  amax + qsum bounds the scaled norm of every row of the lap.
+        const float thr = g + (amax + 2.0f * qsum) * 1.2e-6f;
+        int nl = 0;
+#pragma unroll
+        for (int j = 0; j < K1_LOCAL; ++j) nl += (ld[j] <= thr && li[j] != 0x7fffffff) ? 1 : 0;   // (unused list slots hold +inf)
+        const bool saturated = __any_sync(0xffffffffu, nl == K1_LOCAL);   // that lane may have dropped a row within the threshold
+        int nc = 0;
+        if (!saturated) {
+            int off = nl;                                  // inclusive scan of the per-lane counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
+            nc = __shfl_sync(0xffffffffu, off, 31);
+            off -= nl;
+#pragma unroll
+            for (int j = 0; j < K1_LOCAL; ++j)
+                if (j < nl && off + j < K1_CAND) cbi[off + j] = li[j];
+        } else {                                           // rare: re-collect from global memory with the known threshold
+            for (int t0 = 0; t0 < T - 1; t0 += 32) {
+                const int t = t0 + lane;
+                bool in = false;
+                if (t < T - 1) {
+                    const double* xr = X + (size_t)t * 6;
+                    const double* ur = U + (size_t)t * 2;
+                    float d = s0 * fabsf((float)xr[0] - f0);
+                    d = fmaf(s1, fabsf((float)xr[1] - f1), d);
+                    d = fmaf(s2, fabsf((float)xr[2] - f2), d);
+                    d = fmaf(s3, fabsf((float)ur[0] - f3), d);
+                    d = fmaf(s4, fabsf((float)ur[1] - f4), d);
+                    in = d <= thr;
                 }
+                const unsigned mask = __ballot_sync(0xffffffffu, in);
+                const int pos = nc + __popc(mask & ((1u << lane) - 1u));
+                if (in && pos < K1_CAND) cbi[pos] = t;
+                nc += __popc(mask);
+            }
+        }
+        if (nc > K1_CAND) { flags |= 32; nc = K1_CAND; }
+        __syncwarp();
+        // ---- exact re-scoring and selection of the k nearest on the key (distance, row): kk rounds of warp arg-min; distances
+        //      are non-negative doubles, so their bit patterns order like unsigned integers and three 32-bit REDUX.MIN (high
+        //      word, low word, row) find the winner
+        // The lane that holds a winning candidate writes that point itself: features, kernel weight (PM.py:193) and the
+        // next-row targets -- no second pass over the selected rows.
+        {
+            double cd = 1e300;
+            int ci = 0x7fffffff;
+            if (lane < nc) { ci = cbi[lane]; cd = k1_exact_dist(m, X, U, ci, qv); }
+            const double mine = cd;
+            const int mrow = ci;
+            int rank = -1;
+            for (int r = 0; r < kk; ++r) {
+                const unsigned hi = (unsigned)__double2hiint(cd), lo = (unsigned)__double2loint(cd);
+                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+                const bool eq = (hi == mh) && (lo == ml);
+                const int wi = (int)__reduce_min_sync(0xffffffffu, eq ? (unsigned)ci : 0xffffffffu);
+                if (eq && ci == wi && ci != 0x7fffffff) { rank = r; cd = 1e300; ci = 0x7fffffff; }
+            }
+            if (rank >= 0 && rank < ksel) {
+                double* P = pts + (size_t)(npts + rank) * K1_PW;
+                const double* xr = X + (size_t)mrow * 6;
+                const double* ur = U + (size_t)mrow * 2;
+                const double rr = mine / m.h;
+                P[0] = xr[0]; P[1] = xr[1]; P[2] = xr[2]; P[3] = ur[0]; P[4] = ur[1];
+                P[5] = (1.0 - rr * rr) * 3.0 / 4.0;
+                P[6] = xr[6]; P[7] = xr[7]; P[8] = xr[8];       // row + 1 (PM.py:163: y = xStored[it][index + 1, yIndex])
+                P[9] = 1.0;
             }
         }
         npts += ksel;
@@ -384,7 +443,8 @@ __global__ void __launch_bounds__(32 * 12, 3) knn_ltv_regress_kernel(const __gri
     const double cur = curvature_lookup(m, s, &okc);
     if (!okc) flags |= 2;
     const double den = 1.0 - cur * ey;
-    const double ce = cos(epsi), se = sin(epsi);
+    double se, ce;
+    sincos(epsi, &se, &ce);
     for (int e = lane; e < 54; e += 32) {
         double v = 0.0;
         if (e < 18) {                       // rows 0..2 of A: regression coefficients on (vx, vy, wz)
