@@ -249,6 +249,37 @@ int lmpc_ss_export_laps_dev(lmpc_handle* h, const int* slots_host, int Tpad, dou
 int lmpc_ss_import_laps_dev(lmpc_handle* h, const int* ss_slots_host, const int* model_slots_host, const int* src_host, int n_src,
                             int Tpad, const double* rows_dev, const int* lens_dev);
 
+/* ---- lap bookkeeping on the device (racinglmpc_b200/csrc/lapbooks.cuh) -------------------------------------
+ * The reference decides once per lap, from Python lists, which stored laps the next lap uses: np.argsort(LapTime)[:numSS_it]
+ * (PC.py:395,402), lap it-1 (PC.py:466-476,506-512) and usedIt = the trToUse shortest laps (PredictiveModel.py:31,35-46).  The
+ * host-driven entry points above take those decisions as index arrays (lmpc_ss_set_selection / lmpc_model_set_used); the
+ * entry points below keep the books on the device instead, so that a Monte-Carlo batch hands laps over without the host.
+ * Slot tables per controller: safe set ss_time[B,ss_cap], ss_lap[B,ss_cap] (lap number, -1 = free), it[B]; regression model
+ * md_time[B,model_cap], md_seq[B,model_cap] (arrival number, -1 = free), md_cnt[B].  lmpc_books_set uploads them (e.g. after
+ * seeding through the host-driven path); lmpc_books_get reads them back with the derived selection (any pointer may be NULL):
+ * sel/is_prev[B,numSS_it], prev_slot[B], used[B,trToUse], lap_hist[B,16] = lengths of the laps driven since, lap_n[B]. */
+int lmpc_books_set(lmpc_handle* h, const int* ss_time, const int* ss_lap, const int* it, const int* md_time, const int* md_seq,
+                   const int* md_cnt);
+int lmpc_books_get(lmpc_handle* h, int* ss_time, int* ss_lap, int* it, int* md_time, int* md_seq, int* md_cnt, int* sel, int* is_prev,
+                   int* prev_slot, int* used, int* lap_hist, int* lap_n);
+/* main.py:113-119 for every controller whose lap just ended (its done flag is set): LMPC.addTrajectory + PredictiveModel.addTrajectory
+ * of the recorded lap with the bookkeeping above, s -= TrackLength, timeStep = 0.  Enqueues one kernel; no host data. */
+int lmpc_rollout_commit_laps_dev(lmpc_handle* h);
+/* main.py:99-110 with device books: the record becomes `copies` laps of both stores (books are reset first). */
+int lmpc_rollout_seed_from_record_dev(lmpc_handle* h, int copies);
+/* Progress of the batch: out4 = { min laps driven, max laps driven, min steps into the current lap among the controllers at the
+ * minimum, controllers with a health flag }.  Synchronises. */
+int lmpc_rollout_stats(lmpc_handle* h, int* out4);
+/* Pooled safe-set exchange with device books.  Only the globally fastest laps are ever selected (PC.py:395), so a
+ * rank ships its `kbest` fastest latest-own laps instead of all of them: rows_dev[kbest,Tpad,9] = (x | u | Qfun) incl. the rows
+ * addPoint appended so far, meta_dev[kbest,4] = (rows, lap time, gid_base + controller, 0).  After the all-gather,
+ * lmpc_pool_import_dev ranks the n_src <= 64 gathered laps by (lap time, global id) and every controller files the `share`
+ * fastest laps it does not own before its own latest lap (addTrajectory of a lap another controller drove, into both stores).
+ * took_host (may be NULL; non-NULL synchronises) receives the number of laps stored. */
+int lmpc_pool_export_dev(lmpc_handle* h, int kbest, int Tpad, long long gid_base, double* rows_dev, int* meta_dev);
+int lmpc_pool_import_dev(lmpc_handle* h, int n_src, int share, int Tpad, long long gid_base, const double* rows_dev, const int* meta_dev,
+                         int* took_host);
+
 /* fp64 micro-benchmarks on `device` (no reference counterpart; measurement support for the roofline of the QP kernel, which is
  * bound by fp64 issue and dependent-chain latency rather than HBM): out8 = { DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s,
  * latency in SM cycles of: DFMA, DMMA (accumulator chain), DMMA (result -> A operand), LDS (dependent), SHFL of a double,

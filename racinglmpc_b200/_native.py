@@ -101,6 +101,13 @@ def lib():
     L.lmpc_ss_export_laps_dev.argtypes = [_vp, _vp, C.c_int, _vp, _vp]
     L.lmpc_ss_import_laps_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]
     L.lmpc_probe_fp64.argtypes = [C.c_int, _vp]
+    L.lmpc_books_set.argtypes = [_vp] * 7
+    L.lmpc_books_get.argtypes = [_vp] * 13
+    L.lmpc_rollout_commit_laps_dev.argtypes = [_vp]
+    L.lmpc_rollout_seed_from_record_dev.argtypes = [_vp, C.c_int]
+    L.lmpc_rollout_stats.argtypes = [_vp, _vp]
+    L.lmpc_pool_export_dev.argtypes = [_vp, C.c_int, C.c_int, C.c_longlong, _vp, _vp]
+    L.lmpc_pool_import_dev.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, _vp, _vp]
     L.lmpc_sizeof_params.restype = C.c_int
     L.lmpc_sizeof_model_params.restype = C.c_int
     assert L.lmpc_sizeof_params() == C.sizeof(Params), "lmpc_params ABI mismatch"

@@ -63,6 +63,7 @@ class BatchedController:
         # device-side copies of the lap bookkeeping are rebuilt only for instances whose laps changed (None = all)
         self._sel_rows, self._used_rows = None, None
         nit = max(self.numSS_it, 1)
+        self.device_books = False
         self._sel = np.zeros((self.B, nit), np.int32); self._isp = np.zeros((self.B, nit), np.int32)
         self._prev = -np.ones(self.B, np.int32); self._used = np.zeros((self.B, self.trToUse), np.int32)
 
@@ -172,6 +173,8 @@ class BatchedController:
 
     def _flush(self):
         """Push pending lap bookkeeping (usedIt, the numSS_it fastest laps) to the device before a kernel reads it."""
+        if self.device_books:
+            return                       # the device keeps the books itself
         if self._used_dirty:
             self._push_used()
         if self.lmpc and self._sel_dirty:
@@ -439,6 +442,65 @@ class BatchedController:
             for b in took:
                 self._touch(b, sel=True, used=to_model)
         return took
+
+    # ------------------------------------------------------------------ lap books on the device (csrc/lapbooks.cuh)
+    def enable_device_books(self):
+        """Hand the once-per-lap bookkeeping (which laps are the fastest / usedIt / lap it-1) over to the device, starting from
+        the current host books.  From here on use the *_dev methods; the host-side lists are no longer updated (``books()``
+        reads the device tables back)."""
+        B, sc, mc = self.B, max(self.ss_cap, 1), self.model_cap
+        ss_time = np.full((B, sc), 0x7fffffff, np.int32); ss_lap = -np.ones((B, sc), np.int32)
+        md_time = np.full((B, mc), 0x7fffffff, np.int32); md_seq = -np.ones((B, mc), np.int32)
+        for b in range(B):
+            for lapno, slot in self.ss_book[b].slot_of.items():
+                ss_time[b, slot], ss_lap[b, slot] = self.LapTime[b][lapno], lapno
+            for T, lapno in self.model_laps[b]:
+                slot = self.model_book[b].slot_of.get(lapno)
+                if slot is not None:
+                    md_time[b, slot], md_seq[b, slot] = T, lapno
+        it = np.asarray(self.it, np.int32); cnt = np.asarray(self.model_count, np.int32)
+        self._flush()
+        nat.check(self._lib.lmpc_books_set(self._h, nat.ptr(ss_time), nat.ptr(ss_lap), nat.ptr(it), nat.ptr(md_time), nat.ptr(md_seq),
+                                           nat.ptr(cnt)))
+        self.device_books = True
+
+    def books(self):
+        """The device lap books and the selection derived from them (host copies)."""
+        B, sc, mc, nit, tr = self.B, max(self.ss_cap, 1), self.model_cap, max(self.numSS_it, 1), self.trToUse
+        o = dict(ss_time=np.zeros((B, sc), np.int32), ss_lap=np.zeros((B, sc), np.int32), it=np.zeros(B, np.int32),
+                 md_time=np.zeros((B, mc), np.int32), md_seq=np.zeros((B, mc), np.int32), md_cnt=np.zeros(B, np.int32),
+                 sel=np.zeros((B, nit), np.int32), is_prev=np.zeros((B, nit), np.int32), prev_slot=np.zeros(B, np.int32),
+                 used=np.zeros((B, tr), np.int32), lap_hist=np.zeros((B, 16), np.int32), lap_n=np.zeros(B, np.int32))
+        nat.check(self._lib.lmpc_books_get(self._h, *[nat.ptr(o[k]) for k in ("ss_time", "ss_lap", "it", "md_time", "md_seq", "md_cnt", "sel",
+                                                                               "is_prev", "prev_slot", "used", "lap_hist", "lap_n")]))
+        return o
+
+    def rollout_seed_from_record_dev(self, copies=4):
+        """main.py:99-110 entirely on the device (books included); see ``rollout_seed_from_record`` for the host-book variant."""
+        nat.check(self._lib.lmpc_rollout_seed_from_record_dev(self._h, int(copies)))
+        self.device_books = True
+        self._sel_dirty = self._used_dirty = False
+
+    def rollout_commit_laps_dev(self):
+        """main.py:113-119 for every controller whose lap just ended; nothing crosses to the host."""
+        nat.check(self._lib.lmpc_rollout_commit_laps_dev(self._h))
+
+    def rollout_stats(self):
+        """(min laps driven, max laps driven, min steps into the current lap among the controllers at the minimum, flagged)."""
+        o = np.zeros(4, np.int32)
+        nat.check(self._lib.lmpc_rollout_stats(self._h, nat.ptr(o)))
+        return tuple(int(v) for v in o)
+
+    def pool_export(self, kbest, Tpad, gid_base, rows_dev, meta_dev):
+        """Send side of the pooled exchange: this rank's ``kbest`` fastest latest-own laps -> rows[kbest,Tpad,9], meta[kbest,4]."""
+        nat.check(self._lib.lmpc_pool_export_dev(self._h, int(kbest), int(Tpad), int(gid_base), nat.ptr(rows_dev), nat.ptr(meta_dev)))
+
+    def pool_import(self, n_src, share, Tpad, gid_base, rows_dev, meta_dev, count=False):
+        """Receive side: every controller files the ``share`` globally fastest gathered laps it does not own."""
+        took = np.zeros(1, np.int32) if count else None
+        nat.check(self._lib.lmpc_pool_import_dev(self._h, int(n_src), int(share), int(Tpad), int(gid_base), nat.ptr(rows_dev),
+                                                 nat.ptr(meta_dev), nat.ptr(took)))
+        return int(took[0]) if count else None
 
     def device_buffer(self, name):
         return int(self._lib.lmpc_device_buffer(self._h, name.encode()) or 0)

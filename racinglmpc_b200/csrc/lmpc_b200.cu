@@ -18,6 +18,7 @@
 #include "../../include/lmpc_b200.h"
 #include "ftocp_pdip.cuh"
 #include "safeset.cuh"
+#include "lapbooks.cuh"
 #include "probe.cuh"
 
 using namespace lmpc;
@@ -212,6 +213,10 @@ struct lmpc_handle {
     unsigned long long sim_step;
     double *d_rx[2], *d_rg[2], *d_clx, *d_clu, *d_z, *d_zpid, *d_abc_lti;
     int *d_cllen, *d_done, cur;
+    // device lap books (lapbooks.cuh): slot tables of both pools, lap history, exchange scratch
+    LapBooks bk;
+    int *d_bkbuf, *d_poolidx, *d_stats;
+    bool has_books;
 };
 
 static bool inv6(const double* A, double* Ai) {
@@ -315,6 +320,8 @@ static void free_store(lmpc_handle* h) {
     free_null(h->d_hasPred); free_null(h->d_flags); free_null(h->d_minidx); free_null(h->d_xLin); free_null(h->d_uLin);
     free_null(h->d_ztState); free_null(h->d_ztFixed); free_null(h->d_OldInput); free_null(h->d_xPredPrev); free_null(h->d_tmpx);
     free_null(h->d_tmpu); free_null(h->d_xchg); free_null(h->d_dropped);
+    free_null(h->d_bkbuf); free_null(h->d_poolidx); free_null(h->d_stats);
+    h->has_books = false;
     h->has_store = false;
 }
 
@@ -682,6 +689,7 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     h->ss.cap = ss_cap > 0 ? ss_cap : 1; h->ss.Tmax = Tmax;
     h->mdl.cap = model_cap; h->mdl.Tmax = Tmax;
 #define DA(ptr, T, count) CK(cudaMalloc((void**)&(ptr), sizeof(T) * (count)))
+#define DA2(ptr, T, count) CK(cudaMalloc((void**)&(ptr), sizeof(T) * (count)))
     DA(h->ss.x, double, B * h->ss.cap * Tmax * 6); DA(h->ss.u, double, B * h->ss.cap * Tmax * 2); DA(h->ss.q, double, B * h->ss.cap * Tmax);
     DA(h->ss.len, int, B * h->ss.cap);
     DA(h->mdl.x, double, B * model_cap * Tmax * 6); DA(h->mdl.u, double, B * model_cap * Tmax * 2); h->mdl.q = nullptr;
@@ -693,6 +701,25 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2); DA(h->d_xchg, int, B * 3); DA(h->d_dropped, int, 1);
 #undef DA
     CK(cudaMemsetAsync(h->d_dropped, 0, sizeof(int), h->stream));
+    {   // device lap books: one int buffer carved into the slot tables
+        const size_t sc = h->ss.cap, mcp = model_cap;
+        const size_t n = B * (2 * sc + 1 + 2 * mcp + 1 + LAP_HIST + 1);
+        DA2(h->d_bkbuf, int, n);
+        int* p = h->d_bkbuf;
+        LapBooks& k = h->bk;
+        k.ss_time = p; p += B * sc; k.ss_lap = p; p += B * sc; k.it = p; p += B;
+        k.md_time = p; p += B * mcp; k.md_seq = p; p += B * mcp; k.md_cnt = p; p += B;
+        k.lap_hist = p; p += B * LAP_HIST; k.lap_n = p; p += B;
+        k.sel = h->d_sel; k.isprev = h->d_isprev; k.prevslot = h->d_prevslot; k.used = h->d_used;
+        k.ss_cap = (int)sc; k.md_cap = (int)mcp; k.numSS_it = h->p.numSS_it > 0 ? h->p.numSS_it : 1; k.trToUse = mp->trToUse;
+        CK(cudaMemsetAsync(h->d_bkbuf, 0xff, sizeof(int) * n, h->stream));          // every slot free (-1)
+        CK(cudaMemsetAsync(k.it, 0, sizeof(int) * B, h->stream));
+        CK(cudaMemsetAsync(k.md_cnt, 0, sizeof(int) * B, h->stream));
+        CK(cudaMemsetAsync(k.lap_n, 0, sizeof(int) * B, h->stream));
+        DA2(h->d_poolidx, int, 256);
+        DA2(h->d_stats, int, 8);
+        h->has_books = true;
+    }
     CK(cudaMemsetAsync(h->ss.len, 0, sizeof(int) * B * h->ss.cap, h->stream));
     CK(cudaMemsetAsync(h->mdl.len, 0, sizeof(int) * B * model_cap, h->stream));
     CK(cudaMemsetAsync(h->d_used, 0, sizeof(int) * B * K1_MAXLAPS, h->stream));
@@ -1353,6 +1380,132 @@ int lmpc_probe_fp64(int device, double* out8) {
     for (int i = 0; i < 6; ++i) out8[2 + i] = lat[i];
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_out); cudaFree(d_lat);
+    return LMPC_OK;
+}
+
+// ================================================================================================
+// device lap books (lapbooks.cuh): the reference's once-per-lap list bookkeeping without the host
+// ================================================================================================
+static int need_books(lmpc_handle* h) {
+    int rc = need_store(h);
+    if (rc) return rc;
+    if (!h->has_books) return fail(LMPC_E_STATE, "lap books not allocated");
+    return LMPC_OK;
+}
+
+int lmpc_books_set(lmpc_handle* h, const int* ss_time, const int* ss_lap, const int* it, const int* md_time, const int* md_seq,
+                   const int* md_cnt) {
+    int rc = need_books(h);
+    if (rc) return rc;
+    if (!ss_time || !ss_lap || !it || !md_time || !md_seq || !md_cnt) return fail(LMPC_E_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch, sc = h->bk.ss_cap, mc = h->bk.md_cap;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->bk.ss_time, ss_time, sizeof(int) * B * sc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->bk.ss_lap, ss_lap, sizeof(int) * B * sc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->bk.it, it, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->bk.md_time, md_time, sizeof(int) * B * mc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->bk.md_seq, md_seq, sizeof(int) * B * mc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->bk.md_cnt, md_cnt, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->bk.lap_n, 0, sizeof(int) * B, s));
+    CK(cudaStreamSynchronize(s));
+    return LMPC_OK;
+}
+
+int lmpc_books_get(lmpc_handle* h, int* ss_time, int* ss_lap, int* it, int* md_time, int* md_seq, int* md_cnt, int* sel, int* is_prev,
+                   int* prev_slot, int* used, int* lap_hist, int* lap_n) {
+    int rc = need_books(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->batch, sc = h->bk.ss_cap, mc = h->bk.md_cap, nit = h->bk.numSS_it, tr = h->bk.trToUse;
+    cudaStream_t s = h->stream;
+#define GET(dst, src, n) if (dst) CK(cudaMemcpyAsync(dst, src, sizeof(int) * (n), cudaMemcpyDeviceToHost, s))
+    GET(ss_time, h->bk.ss_time, B * sc); GET(ss_lap, h->bk.ss_lap, B * sc); GET(it, h->bk.it, B);
+    GET(md_time, h->bk.md_time, B * mc); GET(md_seq, h->bk.md_seq, B * mc); GET(md_cnt, h->bk.md_cnt, B);
+    GET(sel, h->d_sel, B * nit); GET(is_prev, h->d_isprev, B * nit); GET(prev_slot, h->d_prevslot, B); GET(used, h->d_used, B * tr);
+    GET(lap_hist, h->bk.lap_hist, B * LAP_HIST); GET(lap_n, h->bk.lap_n, B);
+#undef GET
+    CK(cudaStreamSynchronize(s));
+    return LMPC_OK;
+}
+
+// Lap hand-over of every controller whose lap just ended, bookkeeping on the device; enqueue only.
+int lmpc_rollout_commit_laps_dev(lmpc_handle* h) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if ((rc = need_books(h)) != LMPC_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    commit_laps_books_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, h->bk, h->d_clx, h->d_clu, h->d_cllen, h->Tcl,
+                                                              h->d_rx[h->cur], h->d_timeStep, h->d_done, h->d_health, h->mc.TrackLength,
+                                                              h->M > 0 ? 1 : 0);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LMPC_OK;
+}
+
+int lmpc_rollout_seed_from_record_dev(lmpc_handle* h, int copies) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if ((rc = need_books(h)) != LMPC_OK) return rc;
+    if (copies < 1 || (h->M > 0 && copies > h->ss.cap) || copies > h->mdl.cap) return fail(LMPC_E_INVALID, "seed copies do not fit the lap pools");
+    CK(cudaSetDevice(h->device));
+    seed_books_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, h->bk, copies, h->d_clx, h->d_clu, h->d_cllen, h->Tcl, h->N,
+                                                       h->d_xLin, h->d_uLin, h->d_ztState, h->d_OldInput, h->d_timeStep, h->d_hasPred,
+                                                       h->d_done, h->mc.TrackLength, h->M > 0 ? 1 : 0);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LMPC_OK;
+}
+
+int lmpc_rollout_stats(lmpc_handle* h, int* out4) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if ((rc = need_books(h)) != LMPC_OK) return rc;
+    if (!out4) return fail(LMPC_E_INVALID, "null output");
+    CK(cudaSetDevice(h->device));
+    rollout_stats_kernel<<<1, 1024, 0, h->stream>>>(h->batch, h->bk, h->d_cllen, h->d_health, h->d_stats);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out4, h->d_stats, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LMPC_OK;
+}
+
+// Send side of the pooled exchange: the kbest fastest latest-own laps of this rank, packed on the device.
+int lmpc_pool_export_dev(lmpc_handle* h, int kbest, int Tpad, long long gid_base, double* rows_dev, int* meta_dev) {
+    int rc = need_books(h);
+    if (rc) return rc;
+    if (kbest < 1 || kbest > POOL_MAXK || Tpad < 1 || !rows_dev || !meta_dev) return fail(LMPC_E_INVALID, "bad export arguments");
+    if (h->M <= 0) return fail(LMPC_E_STATE, "handle has no safe set");
+    CK(cudaSetDevice(h->device));
+    pool_local_best_kernel<<<1, 1024, 0, h->stream>>>(h->batch, h->bk, kbest, h->d_poolidx);
+    pool_export_kernel<<<kbest, 256, 0, h->stream>>>(h->ss, h->bk, h->d_poolidx, Tpad, gid_base, rows_dev, meta_dev);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return LMPC_OK;
+}
+
+// Receive side: rank the gathered laps, every controller files the `share` fastest it does not own.  took_host (may be NULL)
+// receives the number of laps stored; the call then synchronises.
+int lmpc_pool_import_dev(lmpc_handle* h, int n_src, int share, int Tpad, long long gid_base, const double* rows_dev, const int* meta_dev,
+                         int* took_host) {
+    int rc = need_books(h);
+    if (rc) return rc;
+    if (n_src < 1 || n_src > 64 || share < 1 || Tpad < 1 || !rows_dev || !meta_dev) return fail(LMPC_E_INVALID, "bad import arguments");
+    if (h->M <= 0) return fail(LMPC_E_STATE, "handle has no safe set");
+    CK(cudaSetDevice(h->device));
+    int* order = h->d_poolidx + 64;
+    int* took = h->d_poolidx + 200;
+    CK(cudaMemsetAsync(took, 0, sizeof(int), h->stream));
+    pool_rank_kernel<<<1, 64, 0, h->stream>>>(n_src, meta_dev, order);
+    pool_import_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, h->bk, n_src, share, Tpad, rows_dev, meta_dev, order, gid_base,
+                                                        took, h->has_rollout ? h->d_health : nullptr);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    if (took_host) {
+        CK(cudaMemcpyAsync(took_host, took, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     return LMPC_OK;
 }
 

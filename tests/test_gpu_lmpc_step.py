@@ -402,3 +402,92 @@ def test_device_pid_lap_sysid_lti_mpc_and_seeding(gold, track):
     r = c.step_results()
     assert np.all(r["status"] == 1) and np.all(r["flags"] == 0), (r["status"], r["flags"])
     c.close()
+
+
+def test_device_lap_books_and_pooled_exchange_match_the_host_books(gold, track):
+    """the once-per-lap bookkeeping on the device (csrc/lapbooks.cuh: which laps are the numSS_it
+    fastest, lap it-1, usedIt, eviction) and the device-side pooled exchange, against the host-side books that restate the
+    reference's lists (controller.py): two batches driven with the same noise must visit bit-identical states, hand over the
+    same laps and -- after exchanging laps -- keep doing so."""
+    _need_gpu()
+    from racinglmpc_b200 import sharding
+    N, B, Tpad, share = 12, 6, 320, 2
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    xP, uP = gold["pid_x"].copy(), gold["pid_u"].copy()
+
+    def fresh():
+        c = BatchedController(par, B, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points,
+                              numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536, ss_cap=7, model_cap=5)
+        for b in range(B):
+            for _ in range(4):
+                c.model_add_trajectory(b, xP, uP)
+            for _ in range(4):
+                c.add_trajectory(b, xP, uP)
+        c.set_state(xLin=np.tile(xP[1:N + 2], (B, 1, 1)), uLin=np.tile(uP[1:N + 1], (B, 1, 1)), zt=np.tile(np.array([0.0, 0, 0, 0, 10.0, 0]), (B, 1)),
+                    OldInput=np.zeros((B, 2)), timeStep=np.zeros(B, np.int32), has_pred=np.zeros(B, np.int32))
+        c.enable_rollout(Tcl=512)
+        x0 = np.tile(np.array([0.5, 0, 0, 0, 0, 0.0]), (B, 1))
+        c.rollout_set_state(x0, x0)
+        return c
+    ca, cb = fresh(), fresh()
+    cb.enable_device_books()
+    rng = np.random.default_rng(7)
+    zs = rng.standard_normal((700, B, 3)) * np.linspace(0.5, 3.0, B)[None, :, None]      # different noise levels -> different lap lengths
+    laps_a = [[] for _ in range(B)]
+
+    def step(k):
+        ca.rollout_step(z=zs[k]); cb.rollout_step(z=zs[k])
+        done, n = ca.rollout_done()
+        if done.any():
+            for b in np.nonzero(done)[0]:
+                laps_a[b].append(int(n[b]))
+            ca.rollout_finish_laps(done, n)
+        cb.rollout_commit_laps_dev()
+        sa, sb = ca.rollout_state(), cb.rollout_state()
+        assert np.array_equal(sa["x"], sb["x"]) and np.array_equal(sa["cl_len"], sb["cl_len"]), k
+
+    k = 0
+    while min(len(l) for l in laps_a) < 2:
+        step(k); k += 1
+        assert k < 560
+    for _ in range(40):                                     # well into the next lap: lap it-1 has grown by addPoint rows
+        step(k); k += 1
+
+    def check_books():
+        bk = cb.books()
+        for b in range(B):
+            host = sorted((ca.LapTime[b][ln], ln) for ln in ca.ss_book[b].slot_of)
+            devb = sorted((int(t), int(l)) for t, l in zip(bk["ss_time"][b], bk["ss_lap"][b]) if l >= 0)
+            assert host == devb, (b, host, devb)
+            assert int(bk["it"][b]) == ca.it[b]
+            order = [int(bk["ss_lap"][b][s]) for s in bk["sel"][b]]
+            assert order == [int(j) for j in np.argsort(np.array(ca.LapTime[b]), kind="stable")[:numSS_it]], b
+            hostm = sorted((T, ln) for T, ln in ca.model_laps[b] if ln in ca.model_book[b].slot_of)
+            devm = sorted((int(t), int(q)) for t, q in zip(bk["md_time"][b], bk["md_seq"][b]) if q >= 0)
+            assert hostm == devm, (b, hostm, devm)
+            assert [int(bk["md_seq"][b][s]) for s in bk["used"][b]] == [ln for _, ln in ca.model_laps[b][:4]], b
+            assert list(bk["lap_hist"][b][:len(laps_a[b])]) == laps_a[b]
+    check_books()
+
+    # ---- pooled exchange: host books (all laps gathered, Python hand-out) vs device books (fastest few, one kernel)
+    rows = torch.zeros(B, Tpad, 9, dtype=torch.float64, device="cuda"); lens = torch.zeros(B, dtype=torch.int32, device="cuda")
+    own = [ca.it[b] - 1 for b in range(B)]
+    ca.export_laps(own, Tpad, rows, lens)
+    times = np.array([ca.LapTime[b][own[b]] for b in range(B)])
+    best = [int(i) for i in sharding.pooled_fastest(times, share + 1)]
+    for j in range(share):
+        src = np.full(B, -1, np.int32); lt = np.zeros(B, np.int64)
+        for b in range(B):
+            cand = [g for g in best if g != b]
+            src[b], lt[b] = cand[j], times[cand[j]]
+        ca.import_laps(src, lt, Tpad, rows, lens)
+    rows_k = torch.zeros(share + 1, Tpad, 9, dtype=torch.float64, device="cuda"); meta = torch.zeros(share + 1, 4, dtype=torch.int32, device="cuda")
+    cb.pool_export(share + 1, Tpad, 0, rows_k, meta)
+    took = cb.pool_import(share + 1, share, Tpad, 0, rows_k, meta, count=True)
+    m = meta.cpu().numpy()
+    assert [int(g) for g in m[:, 2]] == best and [int(t) for t in m[:, 1]] == [int(times[g]) for g in best]
+    assert took >= 1
+    check_books()
+    for _ in range(60):
+        step(k); k += 1
+    ca.close(); cb.close()
