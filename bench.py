@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json metric: QP solves/sec (N=12, nx=6, nu=2).
 
-Workload = BASELINE.json configs[1]: batch=4096 LTV-MPC QPs, N=12, per-instance fixed (A_k,B_k,C_k)
-(126 variables / 174 constraint rows each in the reference's OSQP form), built by
-racinglmpc_b200/workloads.py from the committed fixture.  One "step" = one pass of the hot
-path (assemble-free QP solve + unpack, one kernel launch) over the whole batch.
+Headline workload = BASELINE.json configs[1]: batch=4096 LTV-MPC QPs, N=12, per-instance fixed (A_k,B_k,C_k)
+(126 variables / 174 constraint rows each in the reference's OSQP form), built by racinglmpc_b200/workloads.py from the
+committed fixture.  One "step" = one pass of the hot path (assemble-free QP solve + unpack, one kernel launch)
+over the whole batch.  The same line carries, under "configs", the other BASELINE configurations measured in the same
+process so that the driver's records cover them:
+  configs[2]  batch=4096 full LMPC steps (k-NN regression K1 -> safe-set selection K2 -> 180-variable QP -> shift), with
+              per-kernel durations and rooflines (K1 against HBM, the QP kernels against the measured fp64 peak);
+  configs[3]  LMPC Monte-Carlo rollouts, 8192 controllers per GPU, device-resident closed loop, pooled safe-set exchange with
+              one NCCL all-gather per lap (benchmarks/rollout_mc.py).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1|2|3]
 
-Under torchrun (N > 1) every rank owns its own 4096-QP batch on its own GPU (weak scaling, no data-path
-collective: instances are independent — SURVEY §8e); timing is CUDA events on the launching stream, max
-over ranks.  `--impl reference` times the CPU oracle (oracle/osqp_port.c: the OSQP algorithm with the
-reference's settings, cold start + polish, PC.py:259-283) on the host cores instead.
+Under torchrun (N > 1) every rank owns its own batch on its own GPU (weak scaling; instances are independent — SURVEY §8e);
+timing is CUDA events on the launching stream, max over ranks.  `--impl reference` times the CPU oracle
+(oracle/osqp_port.c: the OSQP algorithm with the reference's settings, cold start + polish, PC.py:259-283) on the host cores.
 """
 import argparse
 import json
@@ -20,6 +24,10 @@ import subprocess
 import sys
 import threading
 import time
+
+# one OpenMP thread per physical core, pinned: the CPU arm has to be repeatable (set before the oracle library loads)
+os.environ.setdefault("OMP_PROC_BIND", "spread")
+os.environ.setdefault("OMP_PLACES", "cores")
 
 import numpy as np
 
@@ -30,12 +38,18 @@ METRIC = "QP solves/sec (N=12, nx=6, nu=2)"
 UNIT = "solves/s"
 BATCH = 4096
 HORIZON = 12
+WORKLOAD = "configs[1]: batch=4096 LTV-MPC QPs N=12 nx=6 nu=2, per-instance fixed A/B/C (126 vars / 174 rows in OSQP form)"
+CPU_SAMPLE = 1024          # QPs of the workload the CPU arm solves per step (bounded sample, both arms)
 # algorithmic HBM bytes per solve (per-instance A/B/C):
 #   in  x0 6 + OldInput 2 + ABC 648 = 656 f64 ; out xPred 78 + uPred 24 + status/iters/3 resid ~4 = 106 f64
 ALGO_BYTES_PER_SOLVE = (656 + 106) * 8
-# fp64 flops of one interior-point iteration of this QP (counted from ftocp_pdip.cuh, N=12, M=0):
-# Riccati factor 12*(2*(288+216+126+72+36+48)) + 4 vector sweeps 12*2*(2*48+30) + elementwise ~4k
+SS_BYTES_PER_SOLVE = (6 * 48 + 48 + 6 * 48 + 2 * 48) * 8           # selected safe set + successors read by the LMPC QP
+# algorithmic fp64 flops of one interior-point iteration (N = 12): Riccati factorisation 12 stages x
+# (A~'PA~ 2*8*8*8*... counted on the 6x8 / 8x8 blocks actually needed) + three vector sweeps + row updates
 FLOPS_PER_ITER = 12 * 2 * (288 + 216 + 126 + 72 + 36 + 48) + 4 * 12 * 2 * 126 + 4000
+FLOPS_PER_ITER_LMPC = FLOPS_PER_ITER + 2 * 48 * (21 + 6 * 6) + 2000       # + simplex terminal block (W assembly, recoveries)
+# fp64 tensor-core instructions issued per iteration: 12 stages x (11 factor + 4 corrector gradient + 2 x 4 forward)
+DMMA_PER_ITER = 12 * (11 + 4 + 8)
 
 
 def dist_env():
@@ -116,18 +130,14 @@ def oracle_problem_set(nsample, seed=1):
     return patP, patA, Px, np.stack(qs), Ax, np.stack(ls), np.stack(us)
 
 
-def oracle_time(prob, nthreads, repeats=1):
+def oracle_pass(prob, nthreads):
+    """One pass of the CPU arm over the sample: (seconds, solved, mean ADMM iterations)."""
     from oracle import osqp_port
     patP, patA, Px, q, Ax, l, u = prob
-    best = None
-    infos = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        _, infos, _ = osqp_port.solve_batch(patP, patA, Px, q, Ax, l, u, nthreads=nthreads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    solved = sum(1 for i in infos if i["status"] == 1)
-    return q.shape[0] / best, best, solved, float(np.mean([i["iters"] for i in infos]))
+    t0 = time.perf_counter()
+    _, infos, _ = osqp_port.solve_batch(patP, patA, Px, q, Ax, l, u, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return dt, sum(1 for i in infos if i["status"] == 1), float(np.mean([i["iters"] for i in infos]))
 
 
 def cpu_model():
@@ -140,97 +150,137 @@ def cpu_model():
     return "unknown"
 
 
-def _affinity_and_quota():
+_CPU_THREADS = None
+
+
+def cpu_threads():
+    """Cached: the affinity mask must be read BEFORE the OpenMP runtime of the oracle library loads (with OMP_PROC_BIND set it
+    pins the calling thread to one core, after which sched_getaffinity reports a single CPU)."""
+    global _CPU_THREADS
+    if _CPU_THREADS is None:
+        _CPU_THREADS = _cpu_threads()
+    return _CPU_THREADS
+
+
+def _cpu_threads():
+    """Threads of the CPU arm, fixed by the machine instead of searched: one per PHYSICAL core of the affinity mask, capped by the
+    container's CPU quota (SMT siblings slow this solver down: measured 16 k solves/s on 128 hardware threads against 150-175 k on
+    the 64 cores behind them).  LMPC_BENCH_THREADS overrides.  Returns (threads, description)."""
+    if os.environ.get("LMPC_BENCH_THREADS"):
+        n = max(1, int(os.environ["LMPC_BENCH_THREADS"]))
+        return n, "LMPC_BENCH_THREADS=%d" % n
     try:
-        a = len(os.sched_getaffinity(0))
+        cpus = sorted(os.sched_getaffinity(0))
     except AttributeError:
-        a = os.cpu_count() or 1
-    q = None
+        cpus = list(range(os.cpu_count() or 1))
+    cores = set()
+    for c in cpus:
+        try:
+            pkg = open("/sys/devices/system/cpu/cpu%d/topology/physical_package_id" % c).read().strip()
+            cid = open("/sys/devices/system/cpu/cpu%d/topology/core_id" % c).read().strip()
+            cores.add((pkg, cid))
+        except OSError:
+            cores.add(("?", c))
+    phys = max(1, len(cores))
+    quota = None
     try:                                                    # cgroup v2, then v1
         qs, ps = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
         if qs != "max":
-            q = max(1, int(np.ceil(int(qs) / int(ps))))
+            quota = max(1, int(int(qs) // int(ps)))
     except (OSError, ValueError):
         try:
             qv = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
             pv = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
             if qv > 0:
-                q = max(1, int(np.ceil(qv / pv)))
+                quota = max(1, qv // pv)
         except (OSError, ValueError):
             pass
-    return a, q
+    n = min(phys, quota) if quota else phys
+    return n, "%d physical cores of %d logical CPUs%s" % (phys, len(cpus), (", CPU quota %d" % quota) if quota else "")
 
 
-def best_oracle_threads(prob):
-    """The CPU arm gets its best configuration, found by measuring: the logical CPUs of the affinity mask, half and a quarter of
-    them (one thread per physical core / per two), and the container's CPU quota and half of it when one is set.  Deliberately
-    NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently make the reference arm
-    single-core -- and a fixed guess is wrong either way (measured on gpurun boxes: 128 SMT threads 16 k solves/s, 64 threads
-    150-175 k, a 32-CPU quota box 44 k at 16).  LMPC_BENCH_THREADS pins the count."""
-    if os.environ.get("LMPC_BENCH_THREADS"):
-        return max(1, int(os.environ["LMPC_BENCH_THREADS"]))
-    a, q = _affinity_and_quota()
-    cand = {a, max(1, a // 2), max(1, a // 4)}
-    if q:
-        cand |= {min(a, q), max(1, min(a, q) // 2)}
-    best, best_v = 1, -1.0
-    for n in sorted(cand, reverse=True):
-        oracle_time(prob, n)
-        v = max(oracle_time(prob, n)[0], oracle_time(prob, n)[0])
-        if v > best_v:
-            best, best_v = n, v
-    return best
+def cpu_arm(prob, repeats=5):
+    """The CPU arm, identical for `--impl reference` and the GPU arm's cpu_baseline leg: fixed thread count, one untimed pass,
+    `repeats` timed passes, median.  Returns a dict."""
+    n, how = cpu_threads()
+    nsample = prob[3].shape[0]
+    oracle_pass(prob, n)
+    ts, solved, iters = [], 0, 0.0
+    for _ in range(repeats):
+        dt, s, it = oracle_pass(prob, n)
+        ts.append(dt); solved = s; iters = it
+    med = float(np.median(ts))
+    return {"value": nsample / med, "threads": n, "threads_how": how, "per_thread": nsample / med / n, "passes_s": [round(t, 4) for t in ts],
+            "spread": (max(ts) - min(ts)) / med, "solved_fraction": solved / nsample, "mean_admm_iters": iters}
+
+
+def cpu_baseline_block(arm):
+    return {"value": arm["value"], "unit": UNIT, "cores": arm["threads"], "kind": "port",
+            "sample": "first %d of the 4096 QPs per pass, OSQP-algorithm C port with the reference's settings (eps 1e-3, polish, cold start "
+                      "per QP; PC.py:259-283), median of %d passes on %s (pass-to-pass spread %.1f %%), %.0f solves/s per thread; cpu %s"
+                      % (CPU_SAMPLE, len(arm["passes_s"]), arm["threads_how"], 100 * arm["spread"], arm["per_thread"], cpu_model())}
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    from oracle import osqp_port
-    nsample = 1024
-    prob = oracle_problem_set(nsample)
-    cores = best_oracle_threads(prob)
+    prob = oracle_problem_set(CPU_SAMPLE)
+    n, _ = cpu_threads()
     for _ in range(args.warmup):
-        oracle_time(prob, cores)
+        oracle_pass(prob, n)
     t0 = time.perf_counter()
-    solved = 0
     for _ in range(args.steps):
-        _, _, s, it = oracle_time(prob, cores)
-        solved += s
+        oracle_pass(prob, n)
     dt = time.perf_counter() - t0
-    val = nsample * args.steps / dt
-    sample = "each step = first %d of the 4096 QPs (OSQP-algorithm C port, reference settings eps 1e-3 + polish, cold)" % nsample
+    arm = cpu_arm(prob)
+    val = CPU_SAMPLE * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1] batch=4096 LTV-MPC QPs N=12 (bounded sample of %d per step)" % nsample,
-                   "cpu": cpu_model(), "solved_fraction": solved / (nsample * args.steps), "mean_admm_iters": it},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample_per_step": CPU_SAMPLE, "cpu": cpu_model(), "solved_fraction": arm["solved_fraction"],
+                   "mean_admm_iters": arm["mean_admm_iters"], "median_of_5_passes": arm["value"]},
+        "cpu_baseline": dict(cpu_baseline_block(arm), value=val),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 # ----------------------------------------------------------------------------------------------
-# GPU arm
+# GPU legs
 # ----------------------------------------------------------------------------------------------
-def run_gpu(args):
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _traffic(kernel):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def _max_over_ranks(v, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def leg_config1(args, rank, world, local, dev):
+    """configs[1]: device-timed value + end-to-end through the public host API."""
     import torch
     import torch.distributed as dist
     from racinglmpc_b200 import BatchedFTOCP, workloads, reference_params as rp
-
-    rank, world, local = dist_env()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     B, N = BATCH, HORIZON
-
     x0, uold, abc = workloads.ltv_mpc_batch(B, N=N, seed=1 + rank)
     solver = BatchedFTOCP(rp.mpc_params(N), batch=B, device=local)
     stream = torch.cuda.ExternalStream(solver.stream, device=dev)
-
-    # ---- device-resident inputs / outputs (the `value` leg) ----
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d_x0, d_u, d_abc = t(x0), t(uold), t(abc)
     d_xP = torch.zeros(B, N + 1, 6, dtype=torch.float64, device=dev)
@@ -273,24 +323,17 @@ def run_gpu(args):
     barrier()
     launches = solver.kernel_launches - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    status = d_st.cpu().numpy()
-    iters = d_it.cpu().numpy()
-    resid = d_rs.cpu().numpy()
-    ok_frac = float(np.mean(status == 1))
+    total_ms = _max_over_ranks(sum(step_ms), dev, world)
+    status, iters, resid = d_st.cpu().numpy(), d_it.cpu().numpy(), d_rs.cpu().numpy()
     # nvidia-smi polling takes driver locks that stall cudaMemcpyAsync enqueues: the sampler covers the device-timed region
     # only and is stopped before the host-timed leg (measured: 2.6-3.4 M/s with it running, 3.9 M/s without)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end leg: host (pinned) buffers through the public API, copies inside the timed region ----
+    # ---- end-to-end: the public host API, used the way a caller streams batch after batch: two batches in flight (solve_async on
+    # buffer sets 0/1, wait before a set is reused), pinned host buffers; every step's inputs are copied H2D and every step's results
+    # D2H inside the timed region
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     h_x0, h_u, h_abc = pin(x0), pin(uold), pin(abc)
-    # The public host API, used the way a caller streams batch after batch: two batches in flight (solve_async on buffer
-    # sets 0/1, wait before a set is reused), so the H2D copy of step i+1 overlaps the solve of step i.  Every step's inputs
-    # are copied from pinned host memory and every step's results are copied back to pinned host memory inside the timed region.
     outs = [{k: torch.from_numpy(v).pin_memory().numpy() for k, v in solver.alloc_outputs(False).items()} for _ in range(2)]
     for i in range(max(args.warmup, 3) + 20):   # untimed; long enough to bring the clocks back up after the pinning pause
         slot = i & 1
@@ -308,80 +351,22 @@ def run_gpu(args):
     solver.wait(0); solver.wait(1)
     torch.cuda.synchronize()
     out = outs[(args.steps - 1) & 1]
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    h2d = int(h_x0.nbytes + h_u.nbytes + h_abc.nbytes)
-    d2h = int(sum(out[k].nbytes for k in ("xPred", "uPred", "slack", "status", "iters", "resid")))
-
-    if rank == 0:
-        value = B * world * args.steps / (total_ms * 1e-3)
-        ms_per_step = total_ms / args.steps
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        kern_ms = float(np.mean(step_ms))                 # one kernel per step: launch duration == step duration
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["ftocp_kernel<12,0,2,4>"]["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        achieved = B * ALGO_BYTES_PER_SOLVE / (kern_ms * 1e-3) / 1e9
-        gflops = float(np.sum(iters + 1)) * FLOPS_PER_ITER / (kern_ms * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch=4096 LTV-MPC QPs N=12 nx=6 nu=2, per-instance fixed A/B/C (126 vars / 174 rows in OSQP form)",
-                       "batch_per_gpu": B, "horizon": N, "l2": "flushed between timed steps (256 MiB memset on the same stream)",
-                       "e2e_mode": "public host API with two batches in flight (solve_async/wait, double-buffered device inputs), pinned host buffers; every step copies its inputs H2D and its results D2H inside the timed region",
-                       "tolerance": "r_prim,r_dual <= 1e-9, gap <= 1e-11 (unscaled inf-norm)",
-                       "solved_fraction": ok_frac, "ipm_iters_mean": float(iters.mean()), "ipm_iters_max": int(iters.max()),
-                       "max_resid": float(resid.max())},
-            "clocks": clocks,
-            "e2e": {"value": B * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "ftocp_kernel<12,0,2,4>",
-                         "note": "latency-bound fp64 kernel by construction (SURVEY §8d): HBM fraction is tiny; see fp64_gflops",
-                         "fp64_gflops": gflops, "algorithmic_bytes_per_solve": ALGO_BYTES_PER_SOLVE},
-        }
-        if not args.no_cpu_baseline and world == 1:       # the CPU leg is measured at N = 1 only (rank 0 has the host to itself)
-            nsample = 1024
-            prob = oracle_problem_set(nsample)
-            cores = best_oracle_threads(prob)
-            oracle_time(prob, cores)
-            v, dt, solved, it = oracle_time(prob, cores, repeats=3)
-            v1, _, _, _ = oracle_time((prob[0], prob[1], prob[2][:128], prob[3][:128], prob[4][:128], prob[5][:128], prob[6][:128]), 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "first %d of the 4096 QPs, OSQP-algorithm C port with the reference's settings "
-                                              "(eps 1e-3, polish, cold start per QP), best of 3; single-core %.0f solves/s; cpu %s"
-                                              % (nsample, v1, cpu_model())}
-        print(json.dumps(line))
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
+    late = solver.late_accepts
     solver.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return dict(B=B, total_ms=total_ms, step_ms=step_ms, launches=int(launches), status=status, iters=iters, resid=resid, clocks=clocks,
+                e2e_s=e2e_s, h2d=int(h_x0.nbytes + h_u.nbytes + h_abc.nbytes),
+                d2h=int(sum(out[k].nbytes for k in ("xPred", "uPred", "slack", "status", "iters", "resid"))), late=late)
 
 
-# ----------------------------------------------------------------------------------------------
-# configs[2]: full LMPC steps (K1 k-NN regression -> K2 safe-set selection -> QP -> shift), per-instance 5-lap safe sets
-# ----------------------------------------------------------------------------------------------
-def run_lmpc_steps(args):
+def leg_config2(args, rank, world, local, dev, steps=None, with_e2e=True):
+    """configs[2]: full LMPC steps (K1 -> K2 -> QP<12,48> -> shift), per-instance 5-lap stores."""
     import torch
     import torch.distributed as dist
     from racinglmpc_b200 import workloads, reference_params as rp
     from racinglmpc_b200.controller import BatchedController
-    rank, world, local = dist_env()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     B, N = args.batch, HORIZON
+    steps = steps or args.steps
     seg = workloads.track_seg_table()      # Map.PointAndTangent[:,3:6] from the reference-pinned fixture
     data = workloads.lmpc_batch(B, seed=2 + rank)
     numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
@@ -397,17 +382,14 @@ def run_lmpc_steps(args):
     def reset():
         c.set_state(**state)      # every timed step solves the same controller states (untimed host upload)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     for _ in range(max(args.warmup, 3)):
         reset(); c.step_dev(d_x0); c.sync()
     l0 = c.kernel_launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    for i in range(args.steps):
+    for i in range(steps):
         reset()
         with torch.cuda.stream(stream):
             flush.zero_()
@@ -418,54 +400,185 @@ def run_lmpc_steps(args):
     launches = c.kernel_launches - l0
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    tot = float(tot.item())
-    clocks = sampler.stop() if rank == 0 else None      # not during the host-timed leg (see run_gpu)
-    # e2e: host x0 in, results out through the public API
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    h_x0 = pin(data["x0"])
-    out = {k: pin(v) for k, v in c.alloc_step_outputs().items()}
-    reset(); c.step(h_x0, out=out, want_ss=False)
-    t_e2e = 0.0
-    for _ in range(args.steps):
+    tot = _max_over_ranks(sum(step_ms), dev, world)
+    # per-kernel durations (CUDA events between the four launches of one step, L2 flushed, median of a few steps)
+    kms = []
+    for _ in range(5):
         reset()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        c.step(h_x0, out=out, want_ss=False)
-        t_e2e += time.perf_counter() - t0
-    ok = float(np.mean((out["status"] == 1) & (out["flags"] == 0)))
-    if rank == 0:
-        rows_model = sum(l[0].shape[0] for l in data["model_laps"][0])
-        rows_ss = sum(l[0].shape[0] for l in data["ss_laps"][0])
-        algo = rows_model * 64 + rows_ss * 48 + (656 + 106) * 8 + 5760
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        ms = tot / args.steps
-        ach = B * algo / (ms * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": B * world * args.steps / (tot * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "configs[2]: batch=%d full LMPC steps (k-NN LTV regression over a 5-lap store, 4-lap sampled safe set, "
-                                       "180 vars / 229 rows QP), N=12" % B, "batch_per_gpu": B,
-                           "l2": "flushed between timed steps (256 MiB memset on the same stream)", "solved_fraction": ok,
-                           "ipm_iters_mean": float(out["iters"].mean()), "ipm_iters_max": int(out["iters"].max()),
-                           "kernels_per_step": "knn_ltv_regress, ss_select, ftocp_kernel<12,48>, shift_state"},
-                "clocks": clocks,
-                "e2e": {"value": B * world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h_x0.nbytes),
-                        "d2h_bytes_per_step": int(sum(out[k].nbytes for k in ("xPred", "uPred", "lambd", "zt", "zt_u", "status", "iters", "resid", "flags")))},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                             "kernel": "whole step (4 kernels)", "algorithmic_bytes_per_solve": algo}}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = lmpc_cpu_baseline(data)
-        print(json.dumps(line))
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        c.sync()
+        kms.append(c.step_profile(d_x0))
+    kms = np.median(np.array(kms), axis=0)
+    res = c.step_results()
+    ok = float(np.mean((res["status"] == 1) & (res["flags"] == 0)))
+    e2e = None
+    if with_e2e:       # host x0 in, results out through the public API
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        h_x0 = pin(data["x0"])
+        out = {k: pin(v) for k, v in c.alloc_step_outputs().items()}
+        reset(); c.step(h_x0, out=out, want_ss=False)
+        t_e2e = 0.0
+        for _ in range(steps):
+            reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c.step(h_x0, out=out, want_ss=False)
+            t_e2e += time.perf_counter() - t0
+        e2e = {"value": B * world * steps / _max_over_ranks(t_e2e, dev, world), "unit": UNIT, "h2d_bytes_per_step": int(h_x0.nbytes),
+               "d2h_bytes_per_step": int(sum(out[k].nbytes for k in ("xPred", "uPred", "lambd", "zt", "zt_u", "status", "iters", "resid", "flags")))}
+    rows_model = sum(l[0].shape[0] for l in data["model_laps"][0])
+    rows_ss = sum(l[0].shape[0] for l in data["ss_laps"][0])
+    late = c.late_accepts
     c.close()
+    return dict(B=B, steps=steps, total_ms=tot, launches=int(launches), kernel_ms=[float(v) for v in kms], ok=ok, iters=res["iters"],
+                rows_model=rows_model, rows_ss=rows_ss, e2e=e2e, data=data, late=late)
+
+
+def config2_block(r, world, probe, peaks):
+    """JSON block of the configs[2] leg with per-kernel rooflines."""
+    B = r["B"]
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1, k2, qp, sh = r["kernel_ms"]
+    k1_bytes = B * r["rows_model"] * 64.0                      # one pass over the used laps: x (48 B) + u (16 B) per stored row
+    k2_bytes = B * r["rows_ss"] * 48.0                         # one pass over the states of the numSS_it fastest laps
+    flops = float(np.sum(r["iters"] + 1)) * FLOPS_PER_ITER_LMPC
+    qp_tf = flops / (qp * 1e-3) / 1e12
+    ms = r["total_ms"] / r["steps"]
+    algo = r["rows_model"] * 64 + r["rows_ss"] * 48 + ALGO_BYTES_PER_SOLVE + SS_BYTES_PER_SOLVE
+    return {"workload": "configs[2]: batch=%d full LMPC steps (k-NN LTV regression over a 5-lap store, 4-lap sampled safe set, 180 vars / 229 "
+                        "rows QP), N=12" % B,
+            "value": B * world * r["steps"] / (r["total_ms"] * 1e-3), "unit": "controller steps/s", "ms_per_step": ms, "steps": r["steps"],
+            "gpu_launches": r["launches"], "solved_fraction": r["ok"], "ipm_iters_mean": float(r["iters"].mean()),
+            "ipm_iters_max": int(r["iters"].max()), "late_accepts": r["late"], "e2e": r["e2e"],
+            "kernels": {
+                "knn_ltv_regress_kernel": {"ms": k1, "roofline": {"bound": "hbm", "achieved": k1_bytes / (k1 * 1e-3) / 1e9, "peak": hbm_peak,
+                                                                  "unit": "GB/s", "frac": k1_bytes / (k1 * 1e-3) / 1e9 / hbm_peak,
+                                                                  "traffic": _traffic("knn_ltv_regress_kernel"),
+                                                                  "algorithmic_bytes_per_launch": k1_bytes}},
+                "ss_select_kernel": {"ms": k2, "roofline": {"bound": "hbm", "achieved": k2_bytes / (k2 * 1e-3) / 1e9, "peak": hbm_peak,
+                                                            "unit": "GB/s", "frac": k2_bytes / (k2 * 1e-3) / 1e9 / hbm_peak, "traffic": None}},
+                "ftocp_kernel<12,48,2,4>": {"ms": qp, "roofline": {"bound": "tensor", "achieved": qp_tf, "peak": probe["dmma_tflops"],
+                                                                   "unit": "TFLOP/s", "frac": qp_tf / probe["dmma_tflops"],
+                                                                   "traffic": _traffic("ftocp_kernel<12,48,2,4>"),
+                                                                   "peak_source": "measured on this GPU (lmpc_probe_fp64: mma.sync.m8n8k4.f64)"}},
+                "shift_state_kernel": {"ms": sh}},
+            "whole_step_hbm": {"algorithmic_bytes_per_step": algo, "achieved_gbs": B * algo / (ms * 1e-3) / 1e9}}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from racinglmpc_b200 import _native
+
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = _peaks()
+    probe = _native.probe_fp64(local)              # measured fp64 numbers of THIS GPU: the QP kernels' roofline denominators
+
+    r1 = leg_config1(args, rank, world, local, dev)
+    B, iters = r1["B"], r1["iters"]
+    line = None
+    if rank == 0:
+        value = B * world * args.steps / (r1["total_ms"] * 1e-3)
+        kern_ms = float(np.mean(r1["step_ms"]))                 # one kernel per step: launch duration == step duration
+        tflops = float(np.sum(iters + 1)) * FLOPS_PER_ITER / (kern_ms * 1e-3) / 1e12
+        issued = float(np.sum(iters + 1)) * DMMA_PER_ITER * 512 / (kern_ms * 1e-3) / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_ach = B * ALGO_BYTES_PER_SOLVE / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r1["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": HORIZON,
+                       "l2": "flushed between timed steps (256 MiB memset on the same stream)",
+                       "e2e_mode": "public host API with two batches in flight (solve_async/wait, double-buffered device inputs), pinned host "
+                                   "buffers; every step copies its inputs H2D and its results D2H inside the timed region",
+                       "tolerance": "r_prim, r_dual <= 1e-9, gap <= 1e-11 (unscaled inf-norm), last primal step <= 1e-7",
+                       "solved_fraction": float(np.mean(r1["status"] == 1)), "ipm_iters_mean": float(iters.mean()),
+                       "ipm_iters_max": int(iters.max()), "max_resid": float(r1["resid"].max()), "late_accepts": r1["late"]},
+            "clocks": r1["clocks"],
+            "e2e": {"value": B * world * args.steps / r1["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": r1["h2d"], "d2h_bytes_per_step": r1["d2h"]},
+            "gpu_launches": r1["launches"],
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": probe["dmma_tflops"], "unit": "TFLOP/s", "frac": tflops / probe["dmma_tflops"],
+                         "traffic": _traffic("ftocp_kernel<12,0,2,4>"), "kernel": "ftocp_kernel<12,0,2,4>",
+                         "peak_source": "measured on this GPU by lmpc_probe_fp64 (mma.sync.m8n8k4.f64, the instruction the Riccati sweeps issue); "
+                                        "MEASURED_PEAKS.json holds no fp64 number",
+                         "note": "achieved = algorithmic fp64 flops of the interior-point iterations / kernel time; the tensor-core instructions "
+                                 "actually issued (8x8x4 fragments, row vectors padded to 8 rows) are `issued_tflops`",
+                         "issued_tflops": issued, "issued_frac": issued / probe["dmma_tflops"], "fp64_probe": probe,
+                         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                                 "algorithmic_bytes_per_solve": ALGO_BYTES_PER_SOLVE,
+                                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}},
+        }
+    # ---- the other BASELINE configurations, same process, all ranks (weak scaling: every rank its own batch)
+    if not args.headline_only:
+        r2 = leg_config2(args, rank, world, local, dev, steps=max(3, min(args.steps, 10)))
+        from benchmarks import rollout_mc
+        r3 = rollout_mc.run(batch=args.rollout_batch, laps=3, mode="pooled", share=2, local=local)
+        if rank == 0:
+            r3["workload"] = ("configs[3]: LMPC Monte-Carlo rollouts, %d controllers per GPU x %d GPUs, device-resident closed loop (main.py's "
+                              "PID lap -> seeding -> 3 LMPC laps), pooled safe-set exchange: one NCCL all-gather per lap" % (args.rollout_batch, world))
+            line["configs"] = {"configs[2]": config2_block(r2, world, probe, peaks), "configs[3]": r3}
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:       # the CPU leg is measured at N = 1 only (rank 0 has the host to itself)
+            line["cpu_baseline"] = cpu_baseline_block(cpu_arm(oracle_problem_set(CPU_SAMPLE)))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_lmpc_steps(args):
+    """--config 2 as its own line."""
+    import torch
+    import torch.distributed as dist
+    from racinglmpc_b200 import _native
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    r = leg_config2(args, rank, world, local, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        blk = config2_block(r, world, _native.probe_fp64(local), _peaks())
+        ms = blk["ms_per_step"]
+        line = {"metric": METRIC, "value": blk["value"], "unit": UNIT, "n_gpus": world, "steps": r["steps"], "warmup": max(args.warmup, 3),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": blk["workload"], "batch_per_gpu": r["B"], "l2": "flushed between timed steps (256 MiB memset on the same stream)",
+                           "solved_fraction": r["ok"], "ipm_iters_mean": blk["ipm_iters_mean"], "ipm_iters_max": blk["ipm_iters_max"],
+                           "kernels_per_step": "knn_ltv_regress, ss_select, ftocp_kernel<12,48>, shift_state"},
+                "clocks": clocks, "e2e": blk["e2e"], "gpu_launches": r["launches"], "kernels": blk["kernels"],
+                "roofline": dict(blk["kernels"]["ftocp_kernel<12,48,2,4>"]["roofline"], kernel="ftocp_kernel<12,48,2,4>")}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = lmpc_cpu_baseline(r["data"])
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rollouts(args):
+    """--config 3 as its own line."""
+    import torch
+    import torch.distributed as dist
+    from benchmarks import rollout_mc
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    r = rollout_mc.run(batch=args.rollout_batch, laps=3, mode="pooled", share=2, local=local)
+    if rank == 0:
+        print(json.dumps({"metric": "LMPC closed-loop controller steps/sec (configs[3])", "value": r["controller_steps_per_s"], "unit": "steps/s",
+                          "n_gpus": world, "steps": r["closed_loop_steps"], "warmup": 0, "ms_per_step": r["ms_total"] / r["closed_loop_steps"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "configs[3]: LMPC Monte-Carlo rollouts, %d controllers per GPU, pooled safe-set exchange"
+                                                 % args.rollout_batch}, "detail": r}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -507,15 +620,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
-    ap.add_argument("--config", type=int, default=1, choices=[1, 2],
-                    help="index into BASELINE.json configs: 1 = batch=4096 LTV-MPC QPs (default, the headline), "
-                         "2 = batch=4096 full LMPC steps with k-NN regression over a 5-lap safe set")
+    ap.add_argument("--headline-only", action="store_true", help="configs[1] only: skip the configs[2] / configs[3] legs (profiling runs)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="0 (default) = the headline line: configs[1] as `value`, configs[2] and configs[3] under `configs`; "
+                         "1 = configs[1] only; 2 = batch=4096 full LMPC steps as its own line; 3 = Monte-Carlo rollouts as its own line")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--rollout-batch", type=int, default=8192, help="controllers per GPU of the configs[3] leg")
     args = ap.parse_args()
-    if args.config == 2:
-        run_lmpc_steps(args)
-    elif args.impl == "reference":
+    cpu_threads()                 # read the affinity mask before any OpenMP runtime pins this thread
+    if args.config == 1:
+        args.headline_only = True
+    if args.impl == "reference":
         run_reference(args)
+    elif args.config == 2:
+        run_lmpc_steps(args)
+    elif args.config == 3:
+        run_rollouts(args)
     else:
         run_gpu(args)
 

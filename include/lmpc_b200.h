@@ -190,6 +190,9 @@ int lmpc_step_host(lmpc_handle* h, int mode, const double* x0, double* xPred, do
                    double* zt_u, double* SS_sel, int* status, int* iters, double* resid, int* flags);
 /* Same with x0 already on the device; results stay in the handle's device buffers (lmpc_device_buffer). */
 int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev);
+/* lmpc_step_dev with CUDA events between its kernels: ms4 = milliseconds of K1 (k-NN regression), K2 (safe-set selection, 0 for
+ * mode 0), the QP kernel and the state shift.  Measurement support for per-kernel rooflines; synchronises. */
+int lmpc_step_profile(lmpc_handle* h, int mode, const double* x0_dev, float* ms4);
 /* QP status / iterations / residuals [B,3] / step flags of the most recent lmpc_step_dev or lmpc_rollout_step (any NULL). */
 int lmpc_step_results(lmpc_handle* h, int* status, int* iters, double* resid, int* flags);
 /* Inspection: copy `bytes` from the named device buffer (names as lmpc_device_buffer) at `offset_bytes` to host memory.

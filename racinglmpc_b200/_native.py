@@ -82,6 +82,7 @@ def lib():
     L.lmpc_select_host.argtypes = [_vp] + [_vp] * 7
     L.lmpc_step_host.argtypes = [_vp, C.c_int] + [_vp] * 11
     L.lmpc_step_dev.argtypes = [_vp, C.c_int, _vp]
+    L.lmpc_step_profile.argtypes = [_vp, C.c_int, _vp, _vp]
     L.lmpc_step_results.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.lmpc_read_buffer.argtypes = [_vp, C.c_char_p, C.c_size_t, _vp, C.c_size_t]
     L.lmpc_device_buffer.argtypes = [_vp, C.c_char_p]

@@ -275,6 +275,13 @@ class BatchedController:
         self._flush()
         nat.check(self._lib.lmpc_step_dev(self._h, 1 if self.lmpc else 0, nat.ptr(x0_dev)))
 
+    def step_profile(self, x0_dev):
+        """One step with CUDA events between its kernels: milliseconds of (K1, K2, QP, shift)."""
+        self._flush()
+        ms = np.zeros(4, np.float32)
+        nat.check(self._lib.lmpc_step_profile(self._h, 1 if self.lmpc else 0, nat.ptr(x0_dev), nat.ptr(ms)))
+        return [float(v) for v in ms]
+
     def read_buffer(self, name, inst, shape, dtype=np.float64):
         """Inspection: the slice of instance `inst` of a per-instance device buffer ("abc", "SS_sel", "Qfun_sel", ...)."""
         out = np.zeros(shape, dtype)

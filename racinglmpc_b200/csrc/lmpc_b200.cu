@@ -954,20 +954,43 @@ int lmpc_select_host(lmpc_handle* h, const double* x0, double* SS_sel, double* Q
     return LMPC_OK;
 }
 
-int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) {
+static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev);
+int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) { return step_dev_impl(h, mode, x0_dev, nullptr); }
+
+// The same step with CUDA events between its kernels: ms4 = durations of K1 (regression), K2 (selection; 0 for mode 0), the QP
+// kernel and the state shift.  Measurement support (bench.py's per-kernel rooflines); synchronises.
+int lmpc_step_profile(lmpc_handle* h, int mode, const double* x0_dev, float* ms4) {
+    if (!h || !ms4) return fail(LMPC_E_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&ev[i]));
+    int rc = step_dev_impl(h, mode, x0_dev, ev);
+    if (rc == LMPC_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(LMPC_E_CUDA, "stream synchronisation failed");
+    if (rc == LMPC_OK)
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms4[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}
+}  // extern "C"
+
+static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev) {
     int rc = need_store(h);
     if (rc) return rc;
     if (!x0_dev || (mode != 0 && mode != 1)) return fail(LMPC_E_INVALID, "bad mode or null x0");
     if (mode == 1 && h->M <= 0) return fail(LMPC_E_INVALID, "LMPC step on a handle without a safe set");
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
+    if (ev) CK(cudaEventRecord(ev[0], h->stream));
     if ((rc = launch_k1(h)) != LMPC_OK) return rc;                      // PC.py:117
+    if (ev) CK(cudaEventRecord(ev[1], h->stream));
     if (mode == 1 && (rc = launch_k2(h, x0_dev)) != LMPC_OK) return rc;  // PC.py:121
+    if (ev) CK(cudaEventRecord(ev[2], h->stream));
     rc = lmpc_solve_lmpc_dev(h, x0_dev, h->d_OldInput, h->d_abc, (long long)h->N * 54, 54, mode == 1 ? h->d_SS : nullptr,
                              mode == 1 ? h->d_Qfun : nullptr, mode == 1 ? h->d_SuccSS : nullptr, mode == 1 ? h->d_SuccU : nullptr,
                              h->d_xPred, h->d_uPred, h->d_slack, mode == 1 ? h->d_lambd : nullptr, mode == 1 ? h->d_slackT : nullptr,
                              mode == 1 ? h->d_zt : nullptr, mode == 1 ? h->d_ztu : nullptr, h->d_status, h->d_iters, h->d_resid);  // PC.py:124-125
     if (rc) return rc;
+    if (ev) CK(cudaEventRecord(ev[3], h->stream));
     ShiftArgs sa;
     sa.batch = h->batch; sa.N = h->N; sa.lmpc = mode;
     sa.xPred = h->d_xPred; sa.uPred = h->d_uPred; sa.zt_in = h->d_zt; sa.ztu_in = h->d_ztu;
@@ -976,8 +999,10 @@ int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) {
     shift_state_kernel<<<h->batch, 64, 0, h->stream>>>(sa);             // PC.py:129-137
     CK(cudaGetLastError());
     h->launches += 1;
+    if (ev) CK(cudaEventRecord(ev[4], h->stream));
     return LMPC_OK;
 }
+extern "C" {
 
 int lmpc_step_host(lmpc_handle* h, int mode, const double* x0, double* xPred, double* uPred, double* lambd, double* zt,
                    double* zt_u, double* SS_sel, int* status, int* iters, double* resid, int* flags) {
