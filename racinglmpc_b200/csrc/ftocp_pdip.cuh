@@ -778,7 +778,7 @@ struct Pdip {
     //
     // Augmented state w = (x, v) with v_k = u_{k-1}; A~ = [A B; 0 I] maps (x_k, u_k) to w_{k+1}.  Per stage, with the cost-to-go
     // Hessian P of stage k+1:   S = A~' P A~ + H_k,   H_k = blkdiag(2Q, 2R + rate) + Fa' diag(Wd_k) Fa,  Fa = [Fx 0; 0 Fu],
-    //   Suu = L L',  Z = L^-1 [Sux | -dR2],  K = -L^-T Z,  M = [I 0; K],  P_k = [Sxx 0; 0 0] - Z'Z,
+    //   Y = [Sux | -dR2],  W = Suu^-1 Y (2 x 2 adjugate, no square roots),  K = -W,  M = [I 0; K],  P_k = [Sxx 0; 0 0] - Y'W,
     //   gradient  c_k = M'(A~' c + g_k),   f_k = -Suu^-1 (A~' c + g_k)_u,        g_k = stage gradient + eliminated-row terms,
     //   where c = (cost-to-go gradient) - (costate, 0): the costate recursion pi_k = A' pi - gst_x drops out of the solve and is
     //   only carried (row 1) in the factorising sweep to report the input-stationarity residual ru = gst_u - B' pi.
@@ -791,17 +791,32 @@ struct Pdip {
                      : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
 #endif
     }
+    // LMPC_PROD_CHAIN: accumulate the odd half through the C operand of the second MMA (two dependent MMAs, no extra adds)
+    // instead of two independent MMAs and a pair of DADDs (shorter chain, two more fp64 instructions per product).
+#ifndef LMPC_PROD_CHAIN
+#define LMPC_PROD_CHAIN 1
+#endif
     static LMPC_HD Frag prod(const Frag& X, const Frag& YT) {
         Frag e, o;
         dmma(e.a, e.b, X.a, YT.a, 0.0, 0.0);
+#if LMPC_PROD_CHAIN
+        dmma(o.a, o.b, X.b, YT.b, e.a, e.b);
+        return o;
+#else
         dmma(o.a, o.b, X.b, YT.b, 0.0, 0.0);
         return Frag{e.a + o.a, e.b + o.b};
+#endif
     }
     static LMPC_HD Frag prod_add(const Frag& X, const Frag& YT, const Frag& C) {
         Frag e, o;
         dmma(e.a, e.b, X.a, YT.a, C.a, C.b);
+#if LMPC_PROD_CHAIN
+        dmma(o.a, o.b, X.b, YT.b, e.a, e.b);
+        return o;
+#else
         dmma(o.a, o.b, X.b, YT.b, 0.0, 0.0);
         return Frag{e.a + o.a, e.b + o.b};
+#endif
     }
     static LMPC_HD double bcast(double v, int src) {
 #if defined(__CUDA_ARCH__)
@@ -932,7 +947,7 @@ struct Pdip {
         const double m_x = (r < 6) ? 1.0 : 0.0;                               // column r of Y comes from S (else: the -dR2 constant)
         const double y0c = (r == 6) ? -c.dR2[0] : 0.0, y1c = (r == 7) ? -c.dR2[1] : 0.0;
         const double m_keep = (r < 6 && q < 3) ? 1.0 : 0.0;                   // entries of Sxx
-        const double m_q0 = (q == 0) ? 1.0 : 0.0, m_q1 = (q == 1) ? 1.0 : 0.0, m_q3 = (q == 3) ? 1.0 : 0.0;
+        const double m_q01 = (q < 2) ? 1.0 : 0.0, m_q3 = (q == 3) ? 1.0 : 0.0;
         const double m_ru = (lane == 7) ? 0.0 : 1.0;                          // the costate has no input part
         const Frag Id = Frag{(q < 3 && r == 2 * q) ? 1.0 : 0.0, (q < 3 && r == 2 * q + 1) ? 1.0 : 0.0};   // M' for q < 3
 
@@ -975,39 +990,32 @@ LMPC_SWEEP_UNROLL
             const Frag Hraw{Tv.a + g.a, Tv.b + g.b};
             if (lane == 7) st2(pru, -Hraw.a, -Hraw.b);      // ru = gst_u - B' pi
             const Frag Hv{Hraw.a * m_ru, Hraw.b * m_ru};
-            // ---- 2x2 Cholesky of Suu (every lane the same values)
+            // ---- eliminate the inputs: Suu^-1 by the adjugate (2 x 2, every lane the same values; no square roots), W = Suu^-1 Y,
+            //      K = -W,  P_k = [Sxx 0; 0 0] - Y'W  (Y = [Sux | -dR2]; column r of Sux = S[r][6..7] sits in lane 4r+3)
             double s66 = bcast(S.a, 27);
             const double s76 = bcast(S.a, 31);
             const double s77 = bcast(S.b, 31);
-            double y0 = bcast(S.a, lane | 3), y1 = bcast(S.b, lane | 3);     // Sux(:, r) = S[r][6..7] sits in lane 4r+3
+            double y0 = bcast(S.a, lane | 3), y1 = bcast(S.b, lane | 3);
             if (!(s66 > 0.0)) { bad = true; s66 = 1.0; }
             double det = fma(s66, s77, -s76 * s76);
             if (!(det > 0.0)) { bad = true; det = 1.0; }
-            const double i00 = rsqrt_f64(s66);
-            const double rdet = rsqrt_f64(det);             // independent of the first rsqrt
-            const double l10 = s76 * i00;
-            const double i11 = rdet * (s66 * i00);          // 1 / sqrt(s77 - l10^2)
-            // ---- Z = L^-1 Y and K = -L^-T Z, column r (Y = [Sux | -dR2])
+            const double idet = recip(det);
+            const double s00 = s77 * idet, s01 = -s76 * idet, s11 = s66 * idet;
             y0 = fma(m_x, y0, y0c);
             y1 = fma(m_x, y1, y1c);
-            const double z0r = y0 * i00;
-            const double z1r = (y1 - l10 * z0r) * i11;
-            const double k1r = -z1r * i11;
-            const double k0r = (-z0r - l10 * k1r) * i00;
-            if (q == 0) { pk[0] = k0r; pk[8] = k1r; }
-            // ---- inverse input Hessian, feed-forward term f = -Suu^-1 h_u (h_u sits in lane 3)
-            const double t = l10 * i00 * i11;
-            const double s11 = i11 * i11, s01 = -t * i11, s00 = fma(i00, i00, t * t);
+            const double w0r = fma(s00, y0, s01 * y1);
+            const double w1r = fma(s01, y0, s11 * y1);
+            if (q == 0) { pk[0] = -w0r; pk[8] = -w1r; }
+            // ---- feed-forward term f = -Suu^-1 h_u (h_u sits in lane 3)
             if (lane == 3) {
                 st2(psi, s00, s01);
                 psi[2] = s11;
                 st2(pfs, -fma(s00, Hv.a, s01 * Hv.b), -fma(s01, Hv.a, s11 * Hv.b));
             }
-            // ---- cost-to-go Hessian of stage k: [Sxx 0; 0 0] - Z'Z  (rank-2 update as one MMA, k = 0,1 used)
-            const double zsel = fma(m_q0, z0r, m_q1 * z1r);
-            dmma(Pf.a, Pf.b, -zsel, zsel, m_keep * S.a, m_keep * S.b);
+            // ---- cost-to-go Hessian of stage k as one MMA (summation index 0,1 used: rows of Y and W)
+            dmma(Pf.a, Pf.b, -((q & 1) ? y1 : y0), m_q01 * ((q & 1) ? w1r : w0r), m_keep * S.a, m_keep * S.b);
             // ---- c_k = M' h (row 0); the costate passes through the identity part (row 1)
-            Vf = prod(Hv, Frag{fma(m_q3, k0r, Id.a), fma(m_q3, k1r, Id.b)});
+            Vf = prod(Hv, Frag{fma(-m_q3, w0r, Id.a), fma(-m_q3, w1r, Id.b)});
             pk -= 16; psi -= 4; pfs -= 2; pru -= 2;
         }
         if (bad && lane == 0) w.flag = ST_NUMERICAL;
