@@ -90,8 +90,14 @@ struct KernelSmem {
 #ifndef LMPC_LB_LMPC
 #define LMPC_LB_LMPC 12
 #endif
+// what shared memory allows (about 992 B per stage + 3.5 KB for a safe set + 1 KB reserved per CTA), capped by the register target
+constexpr int ftocp_min_blocks(int N, int M) {
+    const int by_smem = 227 * 1024 / (992 * N + (M > 0 ? 74 * M : 0) + 448 + 1024);
+    const int by_regs = M > 0 ? LMPC_LB_LMPC : LMPC_LB_MPC;
+    return by_smem < 1 ? 1 : (by_smem < by_regs ? by_smem : by_regs);
+}
 template <int N, int M, int NCX, int NCU>
-__global__ void __launch_bounds__(32, (N <= 14 ? (M > 0 ? LMPC_LB_LMPC : LMPC_LB_MPC) : 1)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
+__global__ void __launch_bounds__(32, ftocp_min_blocks(N, M)) ftocp_kernel(const __grid_constant__ FtocpConst c, const FtocpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using KS = KernelSmem<N, M, NCX, NCU>;
     KS& ks = *reinterpret_cast<KS*>(smem_raw);
@@ -285,15 +291,20 @@ static int launch_t(lmpc_handle* h, const FtocpArgs& a, cudaStream_t st) {
 }
 
 // The supported (horizon, safe-set size) grid: one instantiation of the solver per pair.
+// Horizons 4..48 with and without the reference's 48-point safe set (initControllerParameters.py:43-44), and other safe-set
+// sizes (numSS_it x even points per lap) at the reference's and BASELINE's horizons.
 #define LMPC_FOR_EACH_CASE(X) \
-    X(6, 0) X(12, 0) X(14, 0) X(24, 0) X(48, 0) X(6, 48) X(12, 48) X(14, 48) X(24, 48) X(48, 48)
+    X(4, 0) X(6, 0) X(8, 0) X(10, 0) X(12, 0) X(14, 0) X(16, 0) X(20, 0) X(24, 0) X(32, 0) X(48, 0) \
+    X(4, 48) X(6, 48) X(8, 48) X(10, 48) X(12, 48) X(14, 48) X(16, 48) X(20, 48) X(24, 48) X(32, 48) X(48, 48) \
+    X(12, 24) X(12, 32) X(12, 64) X(12, 96) X(14, 24) X(14, 32) X(14, 64) X(14, 96)
+#define LMPC_GRID_TEXT "N in {4,6,8,10,12,14,16,20,24,32,48} with numSS_Points in {0,48}; N in {12,14} also with numSS_Points in {24,32,64,96}"
 
 static int launch(lmpc_handle* h, const FtocpArgs& a, bool lmpc_mode, cudaStream_t st) {
     const int N = h->N, M = lmpc_mode ? h->M : 0;
 #define LCASE(n, m) if (N == n && M == m) return launch_t<n, m>(h, a, st);
     LMPC_FOR_EACH_CASE(LCASE)
 #undef LCASE
-    return fail(LMPC_E_INVALID, "unsupported (N, numSS_Points): built for N in {6,12,14,24,48}, numSS_Points in {0,48}");
+    return fail(LMPC_E_INVALID, "unsupported (N, numSS_Points): built for " LMPC_GRID_TEXT);
 }
 
 // Opt the kernels this handle can launch into their shared-memory size on the handle's device (the attribute is per device and
@@ -306,7 +317,7 @@ static int configure(int N, int M) {
     if (rc != LMPC_OK) return rc;
     const bool have_m = (M == 0) || (hit == 2);
     if (hit == 0 || !have_m)
-        return fail(LMPC_E_INVALID, "unsupported (N, numSS_Points): built for N in {6,12,14,24,48}, numSS_Points in {0,48}");
+        return fail(LMPC_E_INVALID, "unsupported (N, numSS_Points): built for " LMPC_GRID_TEXT);
     return LMPC_OK;
 }
 

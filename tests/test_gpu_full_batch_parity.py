@@ -132,40 +132,50 @@ def test_config2_all_4096_instances_vs_oracle(track):
           (ok.sum(), B, err[ok].max(), r[:, 0].max(), r[:, 1].max()))
 
 
-def _lmpc_qp_inputs(gold, N, B, duplicate_laps):
+def _ltv_inputs(B, N):
+    """LTV-MPC inputs at any horizon <= 48: the first N stage models of the N = 48 fixture when N has no fixture of its own."""
+    try:
+        x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
+        start = np.load(workloads._GOLD + "/workload_ltv.npz")["N%d_start" % N]
+    except KeyError:
+        x0, uold, abc = workloads.ltv_mpc_batch(B, N=48)
+        abc = np.ascontiguousarray(abc[:, :N])
+        start = np.load(workloads._GOLD + "/workload_ltv.npz")["N48_start"]
+    return x0, uold, abc, start[np.arange(B) % start.shape[0]]
+
+
+def _lmpc_qp_inputs(gold, N, B, duplicate_laps, M=48):
     """LMPC-type QPs at horizon N: stage models from the LTV workload fixture, safe set = 4 x 12 consecutive rows of the PID
     lap around the end of the prediction (4 identical laps when `duplicate_laps`: the reference's own first LMPC laps,
     main.py:109-110, the LP-degenerate case), cost-to-go counting down."""
-    x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
-    g = np.load(workloads._GOLD + "/workload_ltv.npz")
-    start = g["N%d_start" % N][np.arange(B) % g["N%d_start" % N].shape[0]]
+    x0, uold, abc, start = _ltv_inputs(B, N)
     xP, uP = gold["pid_x"], gold["pid_u"]
-    SS = np.zeros((B, 6, 48)); Qf = np.zeros((B, 48)); SuS = np.zeros((B, 6, 48)); SuU = np.zeros((B, 2, 48))
+    P = M // 4
+    SS = np.zeros((B, 6, M)); Qf = np.zeros((B, M)); SuS = np.zeros((B, 6, M)); SuU = np.zeros((B, 2, M))
     for b in range(B):
-        i0 = int(min(start[b] + N - 6, xP.shape[0] - 16))
+        i0 = int(min(start[b] + N - P // 2, xP.shape[0] - P - 12))
         for j in range(4):
-            rows = np.arange(i0, i0 + 13) + (0 if duplicate_laps else 2 * j)
+            rows = np.arange(i0, i0 + P + 1) + (0 if duplicate_laps else 2 * j)
             blk = xP[rows].copy()
             if not duplicate_laps:
                 blk[:, 0:3] += 1e-3 * (j + 1)
-            SS[b, :, 12 * j:12 * j + 12] = blk[:12].T
-            SuS[b, :, 12 * j:12 * j + 12] = blk[1:].T
-            SuU[b, :, 12 * j:12 * j + 12] = uP[rows[1:]].T
-            Qf[b, 12 * j:12 * j + 12] = 300.0 - rows[:12] * 0.3 + 5.0 * j
+            SS[b, :, P * j:P * j + P] = blk[:P].T
+            SuS[b, :, P * j:P * j + P] = blk[1:].T
+            SuU[b, :, P * j:P * j + P] = uP[rows[1:]].T
+            Qf[b, P * j:P * j + P] = 300.0 - rows[:P] * 0.3 + 5.0 * j
     return x0, uold, abc, SS, Qf, SuS, SuU
 
 
-@pytest.mark.parametrize("N,dup", [(14, False), (14, True), (24, False), (48, False), (6, True)])
-def test_lmpc_qp_instantiations_vs_oracle(gold, track, N, dup):
+@pytest.mark.parametrize("N,dup,M", [(14, False, 48), (14, True, 48), (24, False, 48), (48, False, 48), (6, True, 48), (4, False, 48),
+                                     (16, False, 48), (32, False, 48), (12, False, 24), (12, True, 96), (14, False, 64), (14, False, 32)])
+def test_lmpc_qp_instantiations_vs_oracle(gold, track, N, dup, M):
     """ftocp_kernel<N,48> for the reference's own horizon (main.py:43: N = 14) and the sweep horizons, LMPC-type QPs
     (180 + 9 (N - 12) variables) against the oracle on the reference-assembled matrices."""
     _need_gpu()
     B = 16
-    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
-    try:
-        x0, uold, abc, SS, Qf, SuS, SuU = _lmpc_qp_inputs(gold, N, B, dup)
-    except KeyError:
-        pytest.skip("no LTV workload fixture for N = %d" % N)
+    numSS_it, _, _, _, Qts, par = rp.lmpc_params(N)
+    numSS_Points = M
+    x0, uold, abc, SS, Qf, SuS, SuU = _lmpc_qp_inputs(gold, N, B, dup, M)
     s = BatchedFTOCP(par, batch=B, numSS_Points=numSS_Points, numSS_it=numSS_it, QterminalSlack=Qts)
     o = s.solve(x0, uold, abc, SS, Qf, SuS, SuU)
     counts = dict(zip(*np.unique(o["status"], return_counts=True)))
@@ -198,14 +208,13 @@ def test_lmpc_qp_instantiations_vs_oracle(gold, track, N, dup):
     s.close()
 
 
-def test_mpc_qp_reference_horizon_N14_vs_oracle():
-    """ftocp_kernel<14,0>: the reference's own horizon (main.py:43), LTV-MPC QPs, all instances against the oracle."""
+@pytest.mark.parametrize("N", [14, 4, 8, 10, 16, 20, 32])
+def test_mpc_qp_horizon_grid_vs_oracle(N):
+    """ftocp_kernel<N,0> over the instantiated horizon grid (14 = the reference's own, main.py:43): LTV-MPC QPs, all instances
+    against the oracle."""
     _need_gpu()
-    B, N = 64, 14
-    try:
-        x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
-    except KeyError:
-        pytest.skip("no LTV workload fixture for N = 14")
+    B = 64
+    x0, uold, abc, _ = _ltv_inputs(B, N)
     prob = ob.ltv_problem_set(x0, uold, abc, N)
     zo, infos = ob.tight_batch(prob)
     assert _certified(infos).all()
