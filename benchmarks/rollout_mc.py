@@ -35,7 +35,7 @@ from racinglmpc_b200 import workloads, sharding, reference_params as rp      # n
 from racinglmpc_b200.controller import BatchedController                      # noqa: E402
 
 
-def run(batch=8192, laps=3, mode="pooled", share=2, tpad=288, ship_after=40, poll=8, max_steps=0, seed=1234, local=None):
+def run(batch=8192, laps=3, mode="pooled", share=2, tpad=288, ship_after=40, poll=8, max_steps=0, seed=1234, local=None, warm=False):
     """One Monte-Carlo run on this rank's GPU (torch.distributed may or may not be initialised).  Returns a dict (all ranks)."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -45,7 +45,7 @@ def run(batch=8192, laps=3, mode="pooled", share=2, tpad=288, ship_after=40, pol
     B, N = int(batch), 12
     numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
     c = BatchedController(par, B, workloads.track_seg_table(), rp.TRACK_LENGTH, trToUse=4, numSS_Points=numSS_Points,
-                          numSS_it=numSS_it, QterminalSlack=Qts, device=local, Tmax=1280, ss_cap=7, model_cap=5)
+                          numSS_it=numSS_it, QterminalSlack=Qts, device=local, Tmax=1280, ss_cap=7, model_cap=5, warm_start=warm)
     stream = torch.cuda.ExternalStream(c.stream, device=dev)
     x0 = np.tile(np.array([0.5, 0, 0, 0, 0, 0.0]), (B, 1))
     # ---- main.py:65-66 + 99-110 on the device: every controller drives its OWN PID lap (the full 100 s) and is seeded with it
@@ -70,6 +70,7 @@ def run(batch=8192, laps=3, mode="pooled", share=2, tpad=288, ship_after=40, pol
     torch.cuda.synchronize()
     max_steps = int(max_steps) or 300 * laps
     steps, next_round, n_xchg, xchg_s, took_total = 0, 1, 0, 0.0, 0
+    it_sum, it_n, it_max = 0.0, 0, 0                     # interior-point iterations, sampled at the polls
     l0 = c.kernel_launches
     e0.record(stream)
     while steps < max_steps:
@@ -80,6 +81,8 @@ def run(batch=8192, laps=3, mode="pooled", share=2, tpad=288, ship_after=40, pol
             continue
         # ---- poll: four integers of progress; ranks agree on what happens next (same decision everywhere, no deadlock)
         lap_min, lap_max, since, flagged = c.rollout_stats()
+        its = c.step_results()["iters"]
+        it_sum += float(its.mean()); it_n += 1; it_max = max(it_max, int(its.max()))
         ready = int(mode == "pooled" and next_round < laps and lap_min >= next_round and (lap_min > next_round or since >= ship_after))
         done = int(lap_min >= laps)
         if world > 1:
@@ -117,7 +120,8 @@ def run(batch=8192, laps=3, mode="pooled", share=2, tpad=288, ship_after=40, pol
            "kernel_launches_rank0": int(c.kernel_launches - l0), "lap_stats_rank0": stats, "device_pid_laps_s": pid_s,
            "exchanges": n_xchg, "exchange_s_total": xchg_s, "exchange_ms_each": 1e3 * xchg_s / max(n_xchg, 1),
            "allgather_bytes_per_rank": int(rows.numel() * 8 + meta.numel() * 4), "laps_filed_rank0": took_total,
-           "share": share, "ship_after": ship_after, "poll_every": poll,
+           "share": share, "ship_after": ship_after, "poll_every": poll, "warm_start": bool(warm),
+           "ipm_iters_mean_sampled": it_sum / max(it_n, 1), "ipm_iters_max_sampled": it_max,
            "instances_with_flags_rank0": int((flags_or != 0).sum()), "flag_bits_rank0": int(np.bitwise_or.reduce(flags_or)),
            "unsolved_steps_rank0": int(unsolved.sum()), "late_accepts_rank0": c.late_accepts}
     c.close()
@@ -134,11 +138,12 @@ def main():
     ap.add_argument("--tpad", type=int, default=288, help="rows per exchanged lap (lap + addPoint overrun)")
     ap.add_argument("--ship-after", type=int, default=40, help="pooled mode: steps into the next lap before a lap is shipped")
     ap.add_argument("--poll", type=int, default=8, help="closed-loop steps between progress polls")
+    ap.add_argument("--warm", action="store_true", help="warm-started interior-point solves (lmpc_params.warm_start)")
     args = ap.parse_args()
     world, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    out = run(args.batch, args.laps, args.mode, args.share, args.tpad, args.ship_after, args.poll, args.max_steps, local=local)
+    out = run(args.batch, args.laps, args.mode, args.share, args.tpad, args.ship_after, args.poll, args.max_steps, local=local, warm=args.warm)
     if (dist.get_rank() if dist.is_initialized() else 0) == 0:
         print(json.dumps(out))
     if world > 1:

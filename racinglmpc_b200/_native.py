@@ -20,7 +20,7 @@ class Params(C.Structure):
                 ("Fx", C.c_double * (MAX_NCX * 6)), ("bx", C.c_double * MAX_NCX),
                 ("Fu", C.c_double * (MAX_NCU * 2)), ("bu", C.c_double * MAX_NCU),
                 ("numSS_Points", C.c_int), ("numSS_it", C.c_int), ("QterminalSlack", C.c_double * 36),
-                ("eps_res", C.c_double), ("eps_gap", C.c_double), ("max_iter", C.c_int), ("eps_step", C.c_double)]
+                ("eps_res", C.c_double), ("eps_gap", C.c_double), ("max_iter", C.c_int), ("warm_start", C.c_int), ("eps_step", C.c_double)]
 
 
 class ModelParams(C.Structure):
@@ -167,7 +167,7 @@ def ptr(a):
     return C.c_void_p(int(a))
 
 
-def make_params(p, numSS_Points=0, numSS_it=0, QterminalSlack=None, eps_res=0.0, eps_gap=0.0, max_iter=0, eps_step=0.0):
+def make_params(p, numSS_Points=0, numSS_it=0, QterminalSlack=None, eps_res=0.0, eps_gap=0.0, max_iter=0, eps_step=0.0, warm_start=False):
     """p: object with the reference's MPCParams field names (PredictiveControllers.py:24-51)."""
     if int(p.n) != 6 or int(p.d) != 2:
         raise ValueError("racinglmpc_b200 supports n == 6, d == 2 (the reference's vehicle model)")
@@ -193,4 +193,5 @@ def make_params(p, numSS_Points=0, numSS_it=0, QterminalSlack=None, eps_res=0.0,
     q.numSS_Points, q.numSS_it = int(numSS_Points), int(numSS_it)
     q.QterminalSlack[:] = (np.asarray(QterminalSlack, float).ravel() if QterminalSlack is not None else np.zeros(36))
     q.eps_res, q.eps_gap, q.max_iter, q.eps_step = float(eps_res), float(eps_gap), int(max_iter), float(eps_step)
+    q.warm_start = 1 if warm_start else 0
     return q

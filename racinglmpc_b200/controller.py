@@ -33,7 +33,7 @@ class _LapBook:
 class BatchedController:
     def __init__(self, params, batch, seg_table, TrackLength, trToUse=1, numSS_Points=0, numSS_it=0,
                  QterminalSlack=None, device=0, Tmax=2048, ss_cap=None, model_cap=None,
-                 eps_res=0.0, eps_gap=0.0, max_iter=0, model_kwargs=None):
+                 eps_res=0.0, eps_gap=0.0, max_iter=0, model_kwargs=None, warm_start=False):
         L = nat.lib()
         self._lib = L
         self.B, self.N, self.M = int(batch), int(params.N), int(numSS_Points)
@@ -42,7 +42,7 @@ class BatchedController:
         self.lmpc = self.M > 0
         self.ncx = np.asarray(params.Fx).shape[0]
         self.Tmax = int(Tmax)
-        self._p = nat.make_params(params, numSS_Points, numSS_it, QterminalSlack, eps_res, eps_gap, max_iter)
+        self._p = nat.make_params(params, numSS_Points, numSS_it, QterminalSlack, eps_res, eps_gap, max_iter, warm_start=warm_start)
         h = C.c_void_p()
         nat.check(L.lmpc_create(C.byref(self._p), self.B, int(device), C.byref(h)))
         self._h = h

@@ -280,25 +280,69 @@ struct Pdip {
     static constexpr int PS = W::PS;
 #endif
 
-    // ---------------------------------------------------------------- initial point ------
-    static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0) {
-        // inputs: a strictly feasible multiple of the previous input, held over the horizon
-        double tau = 1.0;
-#pragma unroll
-        for (int j = 0; j < NCU; ++j) {
-            double v = c.Fu[j * 2] * w.uOld[0] + c.Fu[j * 2 + 1] * w.uOld[1];
-            if (v > 0.9 * c.bu[j]) tau = fmin(tau, 0.9 * c.bu[j] / v);
+    // ---------------------------------------------------------------- warm-start record ---
+    // Per-controller snapshot of an interior-point iterate, taken at the first iteration (>= 1) whose complementarity gap is
+    // below WARM_SNAP_MU, for the NEXT solve of the same controller (the reference always starts cold,
+    // PC.py:124,276).  Starting the next QP from the converged solution does not help an interior-point method (it sits on the
+    // boundary); an iterate from the middle of the central path, shifted by one stage, does (oracle/pdip_model.py `warm=`).
+    // Layout (doubles): u [N*2] | s, w1, nu1, nu3 [R1 each] | nu2 [R2] | lam, nu4 [M each] | y1.
+    static constexpr int WS_U = 0, WS_S = N * 2, WS_W1 = WS_S + R1, WS_N1 = WS_W1 + R1, WS_N3 = WS_N1 + R1, WS_N2 = WS_N3 + R1,
+                         WS_LAM = WS_N2 + R2, WS_N4 = WS_LAM + (LMPC ? M : 0), WS_Y1 = WS_N4 + (LMPC ? M : 0), WS_SIZE = WS_Y1 + 2;
+    // The snapshot is the first iterate (the starting point included) whose gap lies in [WARM_MIN_MU, WARM_SNAP_MU]: an iterate
+    // closer to the boundary makes a poor start (measured: snapshots at mu <= 1e-2 cost iterations and can stall).  A record is
+    // re-used for at most WARM_MAX_AGE consecutive solves before a cold start re-anchors it, and it is dropped whenever a solve
+    // started from it does not finish cleanly within WARM_MAX_ITERS iterations -- the next solve of that controller is cold.
+    static constexpr double WARM_SNAP_MU = 0.1, WARM_MIN_MU = 0.01, WARM_THETA = 0.25;
+    static constexpr int WARM_MAX_AGE = 8, WARM_MAX_ITERS = 16;
+
+    static LMPC_HD void warm_snapshot(const W& w, const RG& g, double* wb) {
+        FOR_LANES(e, N * 2) wb[WS_U + e] = w.u[e];
+        FOR_SLOTS(r, row, R1) { wb[WS_S + row] = g.s[r]; wb[WS_W1 + row] = g.w1[r]; wb[WS_N1 + row] = g.nu1[r]; wb[WS_N3 + row] = g.nu3[r]; }
+        FOR_SLOTS(r, row, R2) { wb[WS_N2 + row] = g.nu2[r]; }
+        if (LMPC) {
+            FOR_SLOTS(r, row, R4) { wb[WS_LAM + row] = g.lam[r]; wb[WS_N4 + row] = g.nu4[r]; }
+            if (LMPC_LANE == 0) wb[WS_Y1] = g.y1;
         }
-        FOR_LANES(e, N * 2) w.u[e] = tau * w.uOld[e & 1];
+    }
+
+    // Start from the snapshot of the previous solve shifted by one stage (stage k takes stage k+1, the last stage repeats):
+    // inputs, lane slacks and all multipliers are taken over, the states are rolled out from the new x0 with the new model, and a
+    // derived slack that shrank below WARM_THETA of its old value is restored through its lane slack.
+    static LMPC_HD void warm_point(W& w, RG& g, const FtocpConst& c, const double* x0, const double* wb) {
+        FOR_LANES(e, N * 2) { const int k = e >> 1, ks = (k + 1 < N) ? k + 1 : N - 1; w.u[e] = wb[WS_U + ks * 2 + (e & 1)]; }
         FOR_LANES(e, 6) w.x[e] = x0[e];
+        prepare_model(w, c);
+        wsync();
+        rollout(w, x0);
+        FOR_SLOTS(r, row, R1) {
+            const int k = row / NCX, i = row % NCX;
+            const int rs = (k + 1 < N) ? row + NCX : row;
+            const double fx = dot6(&c.Fx[i * 6], &w.x[k * 6]) - c.bx[i];
+            double s = wb[WS_S + rs];
+            const double floor1 = WARM_THETA * wb[WS_W1 + rs];
+            if (s - fx < floor1) s = fx + floor1;
+            g.s[r] = s;
+            g.nu1[r] = wb[WS_N1 + rs];
+            g.nu3[r] = wb[WS_N3 + rs];
+        }
+        FOR_SLOTS(r, row, R2) {
+            const int k = row / NCU;
+            g.nu2[r] = wb[WS_N2 + ((k + 1 < N) ? row + NCU : row)];
+        }
+        if (LMPC) {
+            FOR_SLOTS(r, row, R4) { g.lam[r] = wb[WS_LAM + row]; g.nu4[r] = wb[WS_N4 + row]; }
+            g.y1 = wb[WS_Y1];
+        }
+    }
+
+    // one-time preparation of the stage data (constants of the tensor-core sweeps / in-place transposition for the scalar sweeps)
+    static LMPC_HD void prepare_model(W& w, const FtocpConst& c) {
 #if LMPC_MMA
         FOR_LANES(e, 6) w.cst[e] = (e == 0 || e == 3) ? 1.0 : 0.0;
         FOR_LANES(e, N * 8) {           // rows 6,7: weight of u_k^2 in the input-rate cost (PC.py:233-242), rest written every iteration
             const int k = e >> 3, j = e & 7;
             w.Wd[k][j] = (j >= 6) ? ((k < N - 1) ? 2.0 : 1.0) * c.dR2[j - 6] : 0.0;
         }
-        wsync();
-        rollout(w, x0, tau * w.uOld[0], tau * w.uOld[1]);     // dynamics hold from the start
 #else
         FOR_LANES(k, N) {               // transpose A and B in place: ABC[k][j*6+c] = [A B](c, j)
             double* A = &w.ABC[k][0];
@@ -312,8 +356,14 @@ struct Pdip {
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) { A[36 + cc] = bt[cc * 2]; A[42 + cc] = bt[cc * 2 + 1]; }
         }
-        wsync();
-        for (int k = 0; k < N; ++k) {   // roll the model out (dynamics hold from the start)
+#endif
+    }
+
+#if !LMPC_MMA
+    // roll the model out with the inputs in w.u (dynamics hold from the start); scalar formulation, transposed stage records
+    static LMPC_HD void rollout(W& w, const double* x0) {
+        (void)x0;
+        for (int k = 0; k < N; ++k) {
             FOR_LANES(a, 6) {
                 const double* T = &w.ABC[k][0];
                 double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];
@@ -323,7 +373,23 @@ struct Pdip {
             }
             wsync();
         }
+    }
 #endif
+
+    // ---------------------------------------------------------------- initial point ------
+    static LMPC_HD void init_point(W& w, RG& g, const FtocpConst& c, const double* x0, bool prepare = true) {
+        // inputs: a strictly feasible multiple of the previous input, held over the horizon
+        double tau = 1.0;
+#pragma unroll
+        for (int j = 0; j < NCU; ++j) {
+            double v = c.Fu[j * 2] * w.uOld[0] + c.Fu[j * 2 + 1] * w.uOld[1];
+            if (v > 0.9 * c.bu[j]) tau = fmin(tau, 0.9 * c.bu[j] / v);
+        }
+        FOR_LANES(e, N * 2) w.u[e] = tau * w.uOld[e & 1];
+        FOR_LANES(e, 6) w.x[e] = x0[e];
+        if (prepare) prepare_model(w, c);   // (a restart inside a solve finds the stage data prepared already)
+        wsync();
+        rollout(w, x0);                 // dynamics hold from the start
         // Dual-feasible, centred start (oracle/pdip_model.py, mu0 = "auto"): the slack-stationarity row
         // nu1 + nu3 = 2 qs s + ql holds exactly with w1 nu1 = s nu3 = mu_row; every other constraint
         // family starts at the mean of those products.
@@ -1098,8 +1164,8 @@ LMPC_SWEEP_UNROLL
         wsync();
     }
 
-    // Model roll-out of the starting point with a constant input: (x_{k+1} | u) = A~ (x_k | u) + (C_k | 0)
-    static LMPC_HD void rollout(W& w, const double* x0, double u0, double u1) {
+    // Model roll-out of a starting point with the inputs in w.u: (x_{k+1} | u_k) = A~ (x_k | u_k) + (C_k | 0)
+    static LMPC_HD void rollout(W& w, const double* x0) {
         const int lane = sweep_lane();
         const LaneMap lm = lane_map(w, lane);
         const double* pf = &w.ABC[0][0] + lm.af;
@@ -1109,10 +1175,10 @@ LMPC_SWEEP_UNROLL
 #pragma unroll
         for (int h = 0; h < 3; ++h)
             if (lane == h) Wf = Frag{x0[2 * h], x0[2 * h + 1]};
-        if (lane == 3) Wf = Frag{u0, u1};
         if (lane < 3) st2(&w.x[2 * lane], Wf.a, Wf.b);
-LMPC_SWEEP_UNROLL
+        LMPC_SWEEP_UNROLL
         for (int k = 0; k < N; ++k) {
+            if (lane == 3) Wf = ld2(&w.u[k * 2]);
             Wf = prod_add(Wf, ld2(pf), ld2(pc));
             pf += lm.af_step; pc += c_step;
             if (lane < 3) st2(&w.x[(k + 1) * 6 + 2 * lane], Wf.a, Wf.b);
@@ -1177,12 +1243,25 @@ LMPC_SWEEP_UNROLL
 
     // ---------------------------------------------------------------- the solver ---------
     // Preconditions: w.ABC, w.SS, w.Qfun, w.uOld loaded and visible to the warp; x0[6].
+    // warm: this controller's warm-start record (WS_SIZE doubles, global memory) or null; warm_valid: in = the record holds a
+    // snapshot of the previous solve, out = it holds one of this solve.
     static LMPC_HD void solve(W& w, const FtocpConst& c, const double* x0, SolveInfo& info,
-                              double* lam_out /* M or null */, double* slack_out /* R1 or null */) {
+                              double* lam_out /* M or null */, double* slack_out /* R1 or null */,
+                              double* warm = nullptr, int* warm_valid = nullptr) {
         RG g;
         if (LMPC_LANE == 0) w.flag = 0;
         wsync();
-        init_point(w, g, c, x0);
+        bool snapped = (warm == nullptr), warm_started = false, warm_restarted = false;
+        int late_it = LATE_ACCEPT_IT;
+        int age = 0;
+        if (warm != nullptr) {
+            age = *warm_valid;                            // 0 = no record, else 1 + number of solves it has been carried through
+            warm_started = (age >= 1 && age <= WARM_MAX_AGE);
+        }
+        if (warm_started) warm_point(w, g, c, x0, warm);
+        else init_point(w, g, c, x0);
+        wsync();
+        if (warm != nullptr && LMPC_LANE == 0) *warm_valid = 0;
         const double n_ineq = (double)(2 * R1 + R2 + (LMPC ? M : 0));
         int it = 0, status = ST_MAX_ITER, late = 0;
         double r_prim = 0.0, r_dual = 0.0, mu = 0.0, ru_prev = 0.0, al_prev = 0.0, step_prev = 1e300;
@@ -1192,6 +1271,16 @@ LMPC_SWEEP_UNROLL
         const double d4_floor = c.d4_min;
 
         for (;; ++it) {
+            if (warm_started && it == WARM_MAX_ITERS) {
+                // a start from the previous solve's iterate that is still not through: give the QP the cold start it would have
+                // had without the record (the same answer at the same tolerances, a few iterations later), drop the record
+                init_point(w, g, c, x0, false);
+                wsync();
+                warm_started = false;
+                warm_restarted = true;
+                late_it = LATE_ACCEPT_IT + WARM_MAX_ITERS;
+                al_prev = 0.0; ru_prev = 0.0; step_prev = 1e300; res_ok = false;
+            }
             // ---- lane-local residuals, barrier diagonals, predictor right-hand sides -------
             double comp = 0.0, rd_loc = 0.0;
             FOR_SLOTS(r, row, R1) {
@@ -1243,9 +1332,16 @@ LMPC_SWEEP_UNROLL
             }
             comp = wsum(comp);
             mu = comp * (1.0 / n_ineq);
+            if (!snapped && mu <= WARM_SNAP_MU) {                // record this iterate for the controller's next solve
+                if (mu >= WARM_MIN_MU) {
+                    warm_snapshot(w, g, warm);
+                    if (LMPC_LANE == 0) *warm_valid = warm_started ? age + 1 : 1;
+                }
+                snapped = true;
+            }
             rd_loc = wmax(rd_loc);
             r_prim = fabs(rone);
-            if (it > 0) {
+            if (it > 0 && step_prev < 1e299) {      // (not right after a (re)start: there is no previous step to extrapolate from)
                 // The input-stationarity residual is linear in the iterate and every variable moved by the same step
                 // length, so after a step alpha it is exactly (1 - alpha) times its previous value: convergence can be
                 // decided here, before paying for another factorisation.
@@ -1259,7 +1355,7 @@ LMPC_SWEEP_UNROLL
                 // Stragglers: on a few LMPC instances (LP-degenerate simplex block) the covariance-form recovery of
                 // d(lambda) puts a noise floor of ~1e-7..1e-6 under the dual residual and the tail converges linearly.
                 // Once the iterate meets the 1e-6 parity contract, stop after LATE_ACCEPT_IT iterations (and at max_iter).
-                if ((it >= LATE_ACCEPT_IT || it >= c.max_iter) && r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) {
+                if ((it >= late_it || it >= c.max_iter) && r_prim <= 1e-6 && r_dual <= 1e-6 && mu <= 1e-6) {
                     status = ST_SOLVED;
                     late = res_ok ? 0 : 1;
                     break;
@@ -1499,6 +1595,7 @@ LMPC_SWEEP_UNROLL
             rdyn = fmax(rdyn, fabs(w.x[(k + 1) * 6 + a] - v));
         }
         r_prim = fmax(r_prim, wmax(rdyn));
+        if (warm != nullptr && (warm_restarted || (warm_started && status != ST_SOLVED)) && LMPC_LANE == 0) *warm_valid = 0;
         info.status = status;
         info.iters = it;
         info.late = late;

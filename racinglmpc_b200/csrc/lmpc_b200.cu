@@ -74,6 +74,9 @@ struct FtocpArgs {
     int* iters;
     double* resid;        // [B,3]
     unsigned long long* late;   // counter of instances accepted by the late-acceptance rule (ftocp_pdip.cuh), or null
+    double* warm;         // [B][warm_stride] warm-start records (ftocp_pdip.cuh), or null = cold start
+    int* warm_valid;      // [B]
+    long long warm_stride;
 };
 
 template <int N, int M, int NCX, int NCU>
@@ -131,7 +134,8 @@ __global__ void __launch_bounds__(32, ftocp_min_blocks(N, M)) ftocp_kernel(const
 
     // ---- solve ----
     SolveInfo info;
-    Pdip<N, M, NCX, NCU>::solve(w, c, x0, info, (M > 0) ? w.d4i : nullptr, a.slack ? a.slack + (long long)b * N * NCX : nullptr);
+    Pdip<N, M, NCX, NCU>::solve(w, c, x0, info, (M > 0) ? w.d4i : nullptr, a.slack ? a.slack + (long long)b * N * NCX : nullptr,
+                                a.warm ? a.warm + (long long)b * a.warm_stride : nullptr, a.warm ? a.warm_valid + b : nullptr);
 
     // ---- unpack (PC.py:364-384) ----
     for (int e = lane; e < (N + 1) * 6; e += 32) a.xPred[(long long)b * (N + 1) * 6 + e] = w.x[e];
@@ -201,6 +205,12 @@ struct lmpc_handle {
     double *d_xPred, *d_uPred, *d_slack, *d_lambd, *d_slackT, *d_zt, *d_ztu, *d_resid;
     int *d_status, *d_iters;
     unsigned long long* d_late;
+    // warm-start records of the controllers of the device-resident step (lmpc_params.warm_start; allocated with the store)
+    double* d_warm;
+    int* d_warm_valid;
+    long long warm_stride;
+    int warm_mode;
+    bool use_warm_next;
     // second buffer set of the asynchronous host entry points (slot 1; allocated on first use)
     struct HostBufs {
         double *x0, *uOld, *abc, *SS, *Qfun, *SuccSS, *SuccU, *xPred, *uPred, *slack, *lambd, *slackT, *zt, *ztu, *resid;
@@ -332,6 +342,7 @@ static void free_store(lmpc_handle* h) {
     free_null(h->d_ztState); free_null(h->d_ztFixed); free_null(h->d_OldInput); free_null(h->d_xPredPrev); free_null(h->d_tmpx);
     free_null(h->d_tmpu); free_null(h->d_xchg); free_null(h->d_dropped);
     free_null(h->d_bkbuf); free_null(h->d_poolidx); free_null(h->d_stats);
+    free_null(h->d_warm); free_null(h->d_warm_valid);
     h->has_books = false;
     h->has_store = false;
 }
@@ -476,6 +487,11 @@ int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, co
     a.xPred = xPred; a.uPred = uPred; a.slack = slack; a.lambd = lambd; a.slackT = slackTerminal;
     a.zt = zt; a.ztu = zt_u; a.status = status; a.iters = iters; a.resid = resid;
     a.late = h->d_late;
+    a.warm = nullptr; a.warm_valid = nullptr; a.warm_stride = 0;
+    if (h->use_warm_next) {          // set by the device-resident step only: these QPs belong to persistent controllers
+        a.warm = h->d_warm; a.warm_valid = h->d_warm_valid; a.warm_stride = h->warm_stride;
+        h->use_warm_next = false;
+    }
     return launch(h, a, lm, h->stream);
 }
 
@@ -573,6 +589,7 @@ static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, c
         a.zt = (lm && zt) ? hb.zt + lo * 6 : nullptr; a.ztu = (lm && zt_u) ? hb.ztu + lo * 2 : nullptr;
         a.status = hb.status + lo; a.iters = hb.iters + lo; a.resid = hb.resid + lo * 3;
         a.late = h->d_late;
+        a.warm = nullptr; a.warm_valid = nullptr; a.warm_stride = 0;
         if (trace) cudaEventRecord(h->tev[ci][0], s);
         int rc = launch(h, a, lm, s);
         if (rc != LMPC_OK) return rc;
@@ -712,6 +729,14 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     DA(h->d_tmpx, double, B * 6); DA(h->d_tmpu, double, B * 2); DA(h->d_xchg, int, B * 3); DA(h->d_dropped, int, 1);
 #undef DA
     CK(cudaMemsetAsync(h->d_dropped, 0, sizeof(int), h->stream));
+    if (h->p.warm_start) {          // per-controller interior-point snapshot for the next solve
+        const size_t Mx = h->M > 0 ? h->M : 0;
+        h->warm_stride = (long long)(N * 2 + 4 * N * h->p.ncx + N * h->p.ncu + 2 * Mx + 2);
+        DA2(h->d_warm, double, B * (size_t)h->warm_stride);
+        DA2(h->d_warm_valid, int, B);
+        CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * B, h->stream));
+        h->warm_mode = -1;
+    }
     {   // device lap books: one int buffer carved into the slot tables
         const size_t sc = h->ss.cap, mcp = model_cap;
         const size_t n = B * (2 * sc + 1 + 2 * mcp + 1 + LAP_HIST + 1);
@@ -883,6 +908,7 @@ int lmpc_state_set(lmpc_handle* h, const double* xLin, const double* uLin, const
     if (timeStep) CK(cudaMemcpyAsync(h->d_timeStep, timeStep, B * sizeof(int), cudaMemcpyHostToDevice, s));
     if (has_pred) CK(cudaMemcpyAsync(h->d_hasPred, has_pred, B * sizeof(int), cudaMemcpyHostToDevice, s));
     if (xPred) CK(cudaMemcpyAsync(h->d_xPredPrev, xPred, B * (N + 1) * 6 * D, cudaMemcpyHostToDevice, s));
+    if (h->d_warm_valid) CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * B, s));     // a new controller state starts cold
     CK(cudaStreamSynchronize(s));
     return LMPC_OK;
 }
@@ -996,6 +1022,13 @@ static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEve
     if (ev) CK(cudaEventRecord(ev[1], h->stream));
     if (mode == 1 && (rc = launch_k2(h, x0_dev)) != LMPC_OK) return rc;  // PC.py:121
     if (ev) CK(cudaEventRecord(ev[2], h->stream));
+    if (h->d_warm) {
+        if (h->warm_mode != mode) {                  // records of the other problem type are not comparable
+            CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * h->batch, h->stream));
+            h->warm_mode = mode;
+        }
+        h->use_warm_next = true;
+    }
     rc = lmpc_solve_lmpc_dev(h, x0_dev, h->d_OldInput, h->d_abc, (long long)h->N * 54, 54, mode == 1 ? h->d_SS : nullptr,
                              mode == 1 ? h->d_Qfun : nullptr, mode == 1 ? h->d_SuccSS : nullptr, mode == 1 ? h->d_SuccU : nullptr,
                              h->d_xPred, h->d_uPred, h->d_slack, mode == 1 ? h->d_lambd : nullptr, mode == 1 ? h->d_slackT : nullptr,
@@ -1247,6 +1280,7 @@ int lmpc_rollout_seed_from_record(lmpc_handle* h, int copies, int ss_slot0, int 
     if (copies < 1 || ss_slot0 < 0 || model_slot0 < 0 || ss_slot0 + copies > h->ss.cap || model_slot0 + copies > h->mdl.cap)
         return fail(LMPC_E_INVALID, "seed copies do not fit the lap pools");
     CK(cudaSetDevice(h->device));
+    if (h->d_warm_valid) CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * h->batch, h->stream));
     seed_from_record_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, copies, ss_slot0, model_slot0, h->d_clx, h->d_clu,
                                                              h->d_cllen, h->Tcl, h->N, h->d_xLin, h->d_uLin, h->d_ztState, h->d_OldInput,
                                                              h->d_timeStep, h->d_hasPred, h->d_done, h->mc.TrackLength);
@@ -1485,6 +1519,7 @@ int lmpc_rollout_seed_from_record_dev(lmpc_handle* h, int copies) {
     if ((rc = need_books(h)) != LMPC_OK) return rc;
     if (copies < 1 || (h->M > 0 && copies > h->ss.cap) || copies > h->mdl.cap) return fail(LMPC_E_INVALID, "seed copies do not fit the lap pools");
     CK(cudaSetDevice(h->device));
+    if (h->d_warm_valid) CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * h->batch, h->stream));
     seed_books_kernel<<<h->batch, 256, 0, h->stream>>>(h->batch, h->ss, h->mdl, h->bk, copies, h->d_clx, h->d_clu, h->d_cllen, h->Tcl, h->N,
                                                        h->d_xLin, h->d_uLin, h->d_ztState, h->d_OldInput, h->d_timeStep, h->d_hasPred,
                                                        h->d_done, h->mc.TrackLength, h->M > 0 ? 1 : 0);

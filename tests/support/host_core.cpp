@@ -10,7 +10,7 @@ using namespace lmpc;
 
 template <int N, int M>
 static int run(const FtocpConst* c, const double* abc, const double* ss, const double* qfun, const double* x0,
-               const double* uold, double* xpred, double* upred, double* lam, double* slack, double* info_out) {
+               const double* uold, double* xpred, double* upred, double* lam, double* slack, double* info_out, double* warm, int* warm_valid) {
     using P = Pdip<N, M, 2, 4>;
     typename P::W* w = new typename P::W();
     std::memcpy(w->ABC, abc, sizeof(double) * N * 54);
@@ -21,7 +21,7 @@ static int run(const FtocpConst* c, const double* abc, const double* ss, const d
     w->uOld[0] = uold[0];
     w->uOld[1] = uold[1];
     SolveInfo info;
-    P::solve(*w, *c, x0, info, lam, slack);
+    P::solve(*w, *c, x0, info, lam, slack, warm, warm ? warm_valid : nullptr);
     std::memcpy(xpred, w->x, sizeof(double) * (N + 1) * 6);
     std::memcpy(upred, w->u, sizeof(double) * N * 2);
     info_out[0] = info.status; info_out[1] = info.iters; info_out[2] = info.r_prim; info_out[3] = info.r_dual; info_out[4] = info.gap;
@@ -31,8 +31,8 @@ static int run(const FtocpConst* c, const double* abc, const double* ss, const d
 
 extern "C" int host_core_solve(int N, int M, const FtocpConst* c, const double* abc, const double* ss, const double* qfun,
                                const double* x0, const double* uold, double* xpred, double* upred, double* lam,
-                               double* slack, double* info_out) {
-#define CASE(n, m) if (N == n && M == m) return run<n, m>(c, abc, ss, qfun, x0, uold, xpred, upred, lam, slack, info_out);
+                               double* slack, double* info_out, double* warm, int* warm_valid) {
+#define CASE(n, m) if (N == n && M == m) return run<n, m>(c, abc, ss, qfun, x0, uold, xpred, upred, lam, slack, info_out, warm, warm_valid);
     CASE(6, 0) CASE(12, 0) CASE(14, 0) CASE(24, 0) CASE(48, 0)
     CASE(6, 48) CASE(12, 48) CASE(14, 48) CASE(24, 48) CASE(48, 48)
 #undef CASE

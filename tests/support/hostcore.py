@@ -75,7 +75,8 @@ def lib():
     return _LIB
 
 
-def solve(const, N, abc, x0, uOld, SS=None, Qfun=None):
+def solve(const, N, abc, x0, uOld, SS=None, Qfun=None, warm=None):
+    """warm: None, or a dict {"buf": float64[>= 512], "valid": int32[1]} carried from solve to solve (the controller's warm-start record)."""
     M = 0 if SS is None else SS.shape[1]
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     abc = np.ascontiguousarray(abc, float)
@@ -84,7 +85,9 @@ def solve(const, N, abc, x0, uOld, SS=None, Qfun=None):
     x0 = np.ascontiguousarray(x0, float); uOld = np.ascontiguousarray(np.asarray(uOld, float).ravel())
     xp, up = np.zeros((N + 1, 6)), np.zeros((N, 2))
     lam, slack, info = np.zeros(max(M, 1)), np.zeros(N * 2), np.zeros(5)
-    rc = lib().host_core_solve(N, M, C.byref(const), dp(abc), dp(ss), dp(qf), dp(x0), dp(uOld), dp(xp), dp(up), dp(lam), dp(slack), dp(info))
+    wb = None if warm is None else dp(warm["buf"])
+    wv = None if warm is None else warm["valid"].ctypes.data_as(C.POINTER(C.c_int))
+    rc = lib().host_core_solve(N, M, C.byref(const), dp(abc), dp(ss), dp(qf), dp(x0), dp(uOld), dp(xp), dp(up), dp(lam), dp(slack), dp(info), wb, wv)
     assert rc != -1, "unsupported (N, M)"
     return dict(x=xp, u=up, lam=lam[:M], s=slack.reshape(N, 2), status=int(info[0]), iters=int(info[1]),
                 r_prim=info[2], r_dual=info[3], gap=info[4])

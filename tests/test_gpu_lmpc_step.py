@@ -491,3 +491,46 @@ def test_device_lap_books_and_pooled_exchange_match_the_host_books(gold, track):
     for _ in range(60):
         step(k); k += 1
     ca.close(); cb.close()
+
+
+def test_warm_started_closed_loop_matches_cold_start(gold, track):
+    """controllers that start every solve from the shifted mid-path iterate of their previous solve
+    (lmpc_params.warm_start) must drive the same closed loop as cold-started ones -- the optimum of each QP is the same, only the
+    iteration count changes -- and need fewer interior-point iterations."""
+    _need_gpu()
+    N, B = 12, 8
+    numSS_it, numSS_Points, _, _, Qts, par = rp.lmpc_params(N)
+    xP, uP = gold["pid_x"].copy(), gold["pid_u"].copy()
+
+    def fresh(warm):
+        c = BatchedController(par, B, track.seg_table(), track.TrackLength, trToUse=4, numSS_Points=numSS_Points,
+                              numSS_it=numSS_it, QterminalSlack=Qts, Tmax=1536, ss_cap=7, model_cap=5, warm_start=warm)
+        for b in range(B):
+            for _ in range(4):
+                c.model_add_trajectory(b, xP, uP)
+            for _ in range(4):
+                c.add_trajectory(b, xP, uP)
+        c.set_state(xLin=np.tile(xP[1:N + 2], (B, 1, 1)), uLin=np.tile(uP[1:N + 1], (B, 1, 1)), zt=np.tile(np.array([0.0, 0, 0, 0, 10.0, 0]), (B, 1)),
+                    OldInput=np.zeros((B, 2)), timeStep=np.zeros(B, np.int32), has_pred=np.zeros(B, np.int32))
+        c.enable_rollout(Tcl=512)
+        c.enable_device_books()
+        x0 = np.tile(np.array([0.5, 0, 0, 0, 0, 0.0]), (B, 1))
+        c.rollout_set_state(x0, x0)
+        return c
+    cc, cw = fresh(False), fresh(True)
+    zs = np.random.default_rng(5).standard_normal((300, B, 3))
+    it_c, it_w, worst = [], [], 0.0
+    for k in range(300):
+        for c, acc in ((cc, it_c), (cw, it_w)):
+            c.rollout_step(z=zs[k])
+            r = c.step_results()
+            assert np.all(r["status"] == 1) and np.all(r["flags"] == 0), (k, r["status"], r["flags"])
+            acc.append(r["iters"].mean())
+            c.rollout_commit_laps_dev()
+        worst = max(worst, np.abs(cc.rollout_state()["x"] - cw.rollout_state()["x"]).max())
+    assert worst < 1e-5, worst                                # same optimum every step; the closed loop amplifies 1e-9 a little
+    assert list(cc.books()["lap_hist"][:, 0]) == list(cw.books()["lap_hist"][:, 0])
+    mc, mw = float(np.mean(it_c[1:])), float(np.mean(it_w[1:]))
+    print("interior-point iterations per solve: cold %.2f, warm %.2f" % (mc, mw))
+    assert mw < mc - 0.3, (mc, mw)
+    cc.close(); cw.close()
