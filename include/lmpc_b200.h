@@ -287,6 +287,20 @@ int lmpc_pool_export_dev(lmpc_handle* h, int kbest, int Tpad, long long gid_base
 int lmpc_pool_import_dev(lmpc_handle* h, int n_src, int share, int Tpad, long long gid_base, const double* rows_dev, const int* meta_dev,
                          int* took_host);
 
+/* ---- presentation support (the inputs of the reference's plot.py for device-resident batches) --------------
+ * lmpc_track_global_position: Map.getGlobalPosition (Track.py:135-189) for n points; table6[nseg,6] = Map.PointAndTangent
+ *   (x_end, y_end, psi_end, s_start, length, curvature), host arrays, xy[n,2] out, ok[n] (may be NULL) = 0 where the reference
+ *   would raise (no segment holds s).
+ * lmpc_rollout_trace_create: from now on every lmpc_rollout_step records, for the n chosen controllers, what
+ *   LMPC.unpackSolution keeps per step for plotting (PC.py:377-379) -- the prediction xPred[N+1,6], the selected safe-set points
+ *   SS_sel[6,M] -- plus the closed-loop state x[6], the global state x_glob[6] (SysModel.py), the applied input u[2] and the
+ *   number of laps the controller had driven (to split the trace into laps), at most cap_steps rows each.
+ * lmpc_rollout_trace_get: rows of trace `tr` (index into the chosen controllers); any array pointer may be NULL. */
+int lmpc_track_global_position(int device, const double* table6, int nseg, double TrackLength, int n, const double* s, const double* ey,
+                               double* xy, int* ok);
+int lmpc_rollout_trace_create(lmpc_handle* h, int n, const int* inst, int cap_steps);
+int lmpc_rollout_trace_get(lmpc_handle* h, int tr, int* steps, double* x, double* xglob, double* u, double* xPred, double* SS_sel, int* lap);
+
 /* fp64 micro-benchmarks on `device` (no reference counterpart; measurement support for the roofline of the QP kernel, which is
  * bound by fp64 issue and dependent-chain latency rather than HBM): out8 = { DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s,
  * latency in SM cycles of: DFMA, DMMA (accumulator chain), DMMA (result -> A operand), LDS (dependent), SHFL of a double,

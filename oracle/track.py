@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 Follows src/fnc/simulator/Track.py:
   * segment table construction   Track.py:31-133  (L-shaped track, halfWidth fixed 0.4)
   * ``curvature(s)``             Track.py:292-310
+  * ``global_position(s, ey)``   Track.py:135-189  (curvilinear -> inertial frame; presentation only)
 Only columns 3:6 of the table (cumulative s, length, signed curvature) and
 ``TrackLength`` are consumed by the hot path (PredictiveModel.py:95-96).
 """
@@ -80,3 +81,27 @@ class TrackTable:
         if idx.shape[0] != 1:
             raise ValueError("curvature: s=%r matches %d segments" % (s, idx.shape[0]))
         return tab[int(idx[0]), 5]
+
+    # Track.py:135-189
+    def global_position(self, s, ey):
+        while s > self.TrackLength:
+            s = s - self.TrackLength
+        pt = self.PointAndTangent
+        hit = np.where((s >= pt[:, 3]) & (s < pt[:, 3] + pt[:, 4]))[0]
+        i = int(hit[0])                     # the reference takes int() of a single hit and raises otherwise
+        if pt[i, 5] == 0.0:                 # straight segment: interpolate between its end points
+            xf, yf, psi = pt[i, 0], pt[i, 1], pt[i, 2]
+            xs, ys = pt[i - 1, 0], pt[i - 1, 1]
+            rel = (s - pt[i, 3]) / pt[i, 4]
+            return ((1 - rel) * xs + rel * xf + ey * np.cos(psi + np.pi / 2),
+                    (1 - rel) * ys + rel * yf + ey * np.sin(psi + np.pi / 2))
+        r = 1 / pt[i, 5]
+        ang = pt[i - 1, 2]
+        d = 1 if r >= 0 else -1
+        cx = pt[i - 1, 0] + np.abs(r) * np.cos(ang + d * np.pi / 2)
+        cy = pt[i - 1, 1] + np.abs(r) * np.sin(ang + d * np.pi / 2)
+        span = (s - pt[i, 3]) / (np.pi * np.abs(r)) * np.pi
+        an = _wrap(d * np.pi / 2 + ang)
+        angle = -(np.pi - np.abs(an)) * _sgn(an)
+        return (cx + (np.abs(r) - d * ey) * np.cos(angle + d * span), cy + (np.abs(r) - d * ey) * np.sin(angle + d * span))
+

@@ -102,6 +102,9 @@ def lib():
     L.lmpc_ss_export_laps_dev.argtypes = [_vp, _vp, C.c_int, _vp, _vp]
     L.lmpc_ss_import_laps_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]
     L.lmpc_probe_fp64.argtypes = [C.c_int, _vp]
+    L.lmpc_track_global_position.argtypes = [C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp, _vp, _vp, _vp]
+    L.lmpc_rollout_trace_create.argtypes = [_vp, C.c_int, _vp, C.c_int]
+    L.lmpc_rollout_trace_get.argtypes = [_vp, C.c_int, _vp] + [_vp] * 6
     L.lmpc_books_set.argtypes = [_vp] * 7
     L.lmpc_books_get.argtypes = [_vp] * 13
     L.lmpc_rollout_commit_laps_dev.argtypes = [_vp]

@@ -359,4 +359,79 @@ __global__ void __launch_bounds__(1024) rollout_stats_kernel(int batch, LapBooks
     if (threadIdx.x == 0) { out[0] = s_min; out[1] = s_max; out[2] = s_since; out[3] = s_flag; }
 }
 
+// ---- presentation support (what plot.py reads) ----------------------------------------------------------
+// Map.getGlobalPosition (Track.py:135-189): curvilinear (s, ey) -> inertial (X, Y) on the segment table
+// [x_end, y_end, psi_end, s_start, length, curvature] (Map.PointAndTangent), row i-1 wrapping to the last row like Python's
+// negative index.  ok[i] = 0 where no segment contains s (the reference raises there).
+__global__ void track_global_position_kernel(const double* table, int nseg, double TrackLength, int n, const double* s_in,
+                                             const double* ey_in, double* xy, int* ok) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double PI = 3.141592653589793;
+    double s = s_in[idx];
+    const double ey = ey_in[idx];
+    int found = -1;
+    if (s <= 64.0 * TrackLength) {
+        while (s > TrackLength) s = s - TrackLength;
+        for (int i = 0; i < nseg; ++i) {
+            const double s0 = table[i * 6 + 3], ln = table[i * 6 + 4];
+            if (s >= s0 && s < s0 + ln) { found = i; break; }
+        }
+    }
+    if (found < 0) { xy[idx * 2] = 0.0; xy[idx * 2 + 1] = 0.0; if (ok) ok[idx] = 0; return; }
+    const int i = found, im = (i == 0) ? nseg - 1 : i - 1;
+    const double* ti = table + i * 6;
+    const double* tm = table + im * 6;
+    double x, y;
+    if (ti[5] == 0.0) {
+        const double rel = (s - ti[3]) / ti[4];
+        x = (1 - rel) * tm[0] + rel * ti[0] + ey * cos(ti[2] + PI / 2);
+        y = (1 - rel) * tm[1] + rel * ti[1] + ey * sin(ti[2] + PI / 2);
+    } else {
+        const double r = 1 / ti[5], ang = tm[2];
+        const double d = (r >= 0) ? 1.0 : -1.0;
+        const double cx = tm[0] + fabs(r) * cos(ang + d * PI / 2);
+        const double cy = tm[1] + fabs(r) * sin(ang + d * PI / 2);
+        const double span = (s - ti[3]) / (PI * fabs(r)) * PI;
+        double an = d * PI / 2 + ang;
+        if (an < -PI) an = 2 * PI + an; else if (an > PI) an = an - 2 * PI;      // wrap (Track.py:367-375)
+        const double angle = -(PI - fabs(an)) * ((an >= 0) ? 1.0 : -1.0);
+        x = cx + (fabs(r) - d * ey) * cos(angle + d * span);
+        y = cy + (fabs(r) - d * ey) * sin(angle + d * span);
+    }
+    xy[idx * 2] = x; xy[idx * 2 + 1] = y;
+    if (ok) ok[idx] = 1;
+}
+
+// Trace of chosen controllers during a device-resident rollout: what LMPC.unpackSolution stores per step for plot.py
+// (xStoredPredTraj, SSStoredPredTraj: PC.py:377-379) plus the closed-loop point and the lap it belongs to.
+struct TraceBufs {
+    int n, cap, N, M;
+    const int* inst;      // [n] traced controllers
+    int* steps;           // [n] rows written
+    double* x;            // [n][cap][6]   curvilinear state at the step
+    double* g;            // [n][cap][6]   global state (SysModel.py x_glob: vx vy wz psi X Y)
+    double* u;            // [n][cap][2]   applied input
+    double* xPred;        // [n][cap][N+1][6]
+    double* ss;           // [n][cap][6][M] selected safe-set points (SS_PointSelectedTot)
+    int* lap;             // [n][cap]      laps the controller had driven before this step
+};
+__global__ void trace_step_kernel(TraceBufs t, const double* x, const double* xg, const double* uPred, long long u_stride,
+                                  const double* xPred, const double* SS_sel, const int* lap_n) {
+    const int tr = blockIdx.x;
+    if (tr >= t.n) return;
+    const int b = t.inst[tr];
+    const int row = t.steps[tr];
+    if (row >= t.cap) return;
+    const size_t o = (size_t)tr * t.cap + row;
+    for (int e = threadIdx.x; e < 6; e += blockDim.x) { t.x[o * 6 + e] = x[(size_t)b * 6 + e]; t.g[o * 6 + e] = xg[(size_t)b * 6 + e]; }
+    for (int e = threadIdx.x; e < 2; e += blockDim.x) t.u[o * 2 + e] = uPred[(size_t)b * u_stride + e];
+    const int np = (t.N + 1) * 6;
+    for (int e = threadIdx.x; e < np; e += blockDim.x) t.xPred[o * np + e] = xPred[(size_t)b * np + e];
+    if (t.M > 0)
+        for (int e = threadIdx.x; e < 6 * t.M; e += blockDim.x) t.ss[o * 6 * t.M + e] = SS_sel[(size_t)b * 6 * t.M + e];
+    __syncthreads();
+    if (threadIdx.x == 0) { t.lap[o] = lap_n ? lap_n[b] : 0; t.steps[tr] = row + 1; }
+}
+
 }  // namespace lmpc

@@ -233,6 +233,10 @@ struct lmpc_handle {
     LapBooks bk;
     int *d_bkbuf, *d_poolidx, *d_stats;
     bool has_books;
+    // rollout trace of chosen controllers (presentation support, lmpc_rollout_trace_*)
+    TraceBufs tr;
+    int* d_trinst;
+    bool has_trace;
 };
 
 static bool inv6(const double* A, double* Ai) {
@@ -351,6 +355,9 @@ static void free_rollout(lmpc_handle* h) {
     for (int i = 0; i < 2; ++i) { free_null(h->d_rx[i]); free_null(h->d_rg[i]); }
     free_null(h->d_clx); free_null(h->d_clu); free_null(h->d_z); free_null(h->d_zpid); free_null(h->d_abc_lti);
     free_null(h->d_cllen); free_null(h->d_done); free_null(h->d_health);
+    free_null(h->d_trinst); free_null(h->tr.steps); free_null(h->tr.x); free_null(h->tr.g); free_null(h->tr.u); free_null(h->tr.xPred);
+    free_null(h->tr.ss); free_null(h->tr.lap);
+    h->has_trace = false;
     h->has_rollout = false;
 }
 
@@ -1212,6 +1219,12 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
         CK(cudaGetLastError());
         h->launches += 1;
     }
+    if (h->has_trace) {
+        trace_step_kernel<<<h->tr.n, 128, 0, h->stream>>>(h->tr, xc, h->d_rg[h->cur], h->d_uPred, (long long)h->N * 2, h->d_xPred,
+                                                        mode == 1 ? h->d_SS : nullptr, h->has_books ? h->bk.lap_n : nullptr);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
     if (z_host) CK(cudaMemcpyAsync(h->d_z, z_host, sizeof(double) * h->batch * 3, cudaMemcpyHostToDevice, h->stream));
     SimArgs sa;
     sa.batch = h->batch; sa.x = xc; sa.xg = h->d_rg[h->cur]; sa.u = h->d_uPred; sa.u_stride = (long long)h->N * 2;
@@ -1577,6 +1590,82 @@ int lmpc_pool_import_dev(lmpc_handle* h, int n_src, int share, int Tpad, long lo
         CK(cudaMemcpyAsync(took_host, took, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    return LMPC_OK;
+}
+
+// ================================================================================================
+// presentation support: what plot.py reads, for device-resident batches
+// ================================================================================================
+int lmpc_track_global_position(int device, const double* table6, int nseg, double TrackLength, int n, const double* s, const double* ey,
+                               double* xy, int* ok) {
+    if (!table6 || nseg < 1 || nseg > 64 || n < 1 || !s || !ey || !xy) return fail(LMPC_E_INVALID, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LMPC_E_NODEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(LMPC_E_INVALID, "bad device index");
+    CK(cudaSetDevice(device));
+    double *d_t = nullptr, *d_s = nullptr, *d_e = nullptr, *d_xy = nullptr;
+    int* d_ok = nullptr;
+    int rc = LMPC_OK;
+    do {
+#define TRY(call) if ((call) != cudaSuccess) { rc = fail(LMPC_E_CUDA, #call " failed"); break; }
+        TRY(cudaMalloc((void**)&d_t, sizeof(double) * nseg * 6)); TRY(cudaMalloc((void**)&d_s, sizeof(double) * n));
+        TRY(cudaMalloc((void**)&d_e, sizeof(double) * n)); TRY(cudaMalloc((void**)&d_xy, sizeof(double) * n * 2));
+        TRY(cudaMalloc((void**)&d_ok, sizeof(int) * n));
+        TRY(cudaMemcpy(d_t, table6, sizeof(double) * nseg * 6, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(d_s, s, sizeof(double) * n, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(d_e, ey, sizeof(double) * n, cudaMemcpyHostToDevice));
+        track_global_position_kernel<<<(n + 127) / 128, 128>>>(d_t, nseg, TrackLength, n, d_s, d_e, d_xy, d_ok);
+        TRY(cudaGetLastError());
+        TRY(cudaMemcpy(xy, d_xy, sizeof(double) * n * 2, cudaMemcpyDeviceToHost));
+        if (ok) TRY(cudaMemcpy(ok, d_ok, sizeof(int) * n, cudaMemcpyDeviceToHost));
+#undef TRY
+    } while (0);
+    cudaFree(d_t); cudaFree(d_s); cudaFree(d_e); cudaFree(d_xy); cudaFree(d_ok);
+    return rc;
+}
+
+int lmpc_rollout_trace_create(lmpc_handle* h, int n, const int* inst, int cap_steps) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (h->has_trace) return fail(LMPC_E_STATE, "trace buffers already created");
+    if (n < 1 || n > 1024 || !inst || cap_steps < 1) return fail(LMPC_E_INVALID, "bad trace arguments");
+    for (int i = 0; i < n; ++i) if (inst[i] < 0 || inst[i] >= h->batch) return fail(LMPC_E_INVALID, "traced controller out of range");
+    CK(cudaSetDevice(h->device));
+    TraceBufs& t = h->tr;
+    t.n = n; t.cap = cap_steps; t.N = h->N; t.M = h->M > 0 ? h->M : 0;
+    const size_t rows = (size_t)n * cap_steps, np = (size_t)(h->N + 1) * 6;
+    CK(cudaMalloc((void**)&h->d_trinst, sizeof(int) * n));
+    CK(cudaMalloc((void**)&t.steps, sizeof(int) * n));
+    CK(cudaMalloc((void**)&t.x, sizeof(double) * rows * 6)); CK(cudaMalloc((void**)&t.g, sizeof(double) * rows * 6));
+    CK(cudaMalloc((void**)&t.u, sizeof(double) * rows * 2)); CK(cudaMalloc((void**)&t.xPred, sizeof(double) * rows * np));
+    CK(cudaMalloc((void**)&t.ss, sizeof(double) * rows * 6 * (t.M > 0 ? t.M : 1)));
+    CK(cudaMalloc((void**)&t.lap, sizeof(int) * rows));
+    CK(cudaMemcpyAsync(h->d_trinst, inst, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(t.steps, 0, sizeof(int) * n, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    t.inst = h->d_trinst;
+    h->has_trace = true;
+    return LMPC_OK;
+}
+
+int lmpc_rollout_trace_get(lmpc_handle* h, int tr, int* steps, double* x, double* xglob, double* u, double* xPred, double* SS_sel, int* lap) {
+    int rc = need_rollout(h);
+    if (rc) return rc;
+    if (!h->has_trace || tr < 0 || tr >= h->tr.n || !steps) return fail(LMPC_E_INVALID, "no such trace");
+    CK(cudaSetDevice(h->device));
+    const TraceBufs& t = h->tr;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(steps, t.steps + tr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const size_t n = (size_t)*steps, o = (size_t)tr * t.cap, np = (size_t)(t.N + 1) * 6;
+    if (n == 0) return LMPC_OK;
+    if (x) CK(cudaMemcpyAsync(x, t.x + o * 6, sizeof(double) * n * 6, cudaMemcpyDeviceToHost, s));
+    if (xglob) CK(cudaMemcpyAsync(xglob, t.g + o * 6, sizeof(double) * n * 6, cudaMemcpyDeviceToHost, s));
+    if (u) CK(cudaMemcpyAsync(u, t.u + o * 2, sizeof(double) * n * 2, cudaMemcpyDeviceToHost, s));
+    if (xPred) CK(cudaMemcpyAsync(xPred, t.xPred + o * np, sizeof(double) * n * np, cudaMemcpyDeviceToHost, s));
+    if (SS_sel && t.M > 0) CK(cudaMemcpyAsync(SS_sel, t.ss + o * 6 * t.M, sizeof(double) * n * 6 * t.M, cudaMemcpyDeviceToHost, s));
+    if (lap) CK(cudaMemcpyAsync(lap, t.lap + o, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return LMPC_OK;
 }
 

@@ -105,3 +105,13 @@ def test_lmpc_step_replay(gold, track, key):
     assert np.max(np.abs(c.xPred - gold[k + "xPred"])) < 1e-9
     assert np.max(np.abs(c.uPred - gold[k + "uPred"])) < 1e-9
     assert np.max(np.abs(c.zt - gold[k + "zt_out"])) < 1e-7
+
+
+def test_track_global_position_against_reference_values(track):
+    """oracle/track.py::global_position (Track.py:135-189) against values computed by the real reference
+    (tests/golden/make_track_global.py): bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "track_global.npz"))
+    assert np.array_equal(g["table"], track.PointAndTangent)
+    xy = np.array([track.global_position(float(a), float(b)) for a, b in zip(g["s"], g["ey"])])
+    assert np.array_equal(xy, g["xy"])
