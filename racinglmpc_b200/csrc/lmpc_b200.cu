@@ -701,6 +701,7 @@ int lmpc_store_create(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, i
 }  // extern "C" (the helper below has C++ linkage)
 static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss_cap, int model_cap, int Tmax) {
     if (!h || !mp || ss_cap < 0 || model_cap <= 0 || Tmax < 16) return fail(LMPC_E_INVALID, "bad store arguments");
+    if (Tmax > (32 << K1_JBITS)) return fail(LMPC_E_INVALID, "Tmax above 4096 rows per lap is not supported by the neighbour scan");
     if (h->has_store) return fail(LMPC_E_STATE, "store already created");
     if (mp->trToUse < 1 || mp->trToUse > K1_MAXLAPS || mp->trToUse > model_cap) return fail(LMPC_E_INVALID, "trToUse out of range");
     if (mp->MaxNumPoint < 1 || mp->MaxNumPoint > K1_MAXPTS) return fail(LMPC_E_INVALID, "MaxNumPoint must be <= 7");

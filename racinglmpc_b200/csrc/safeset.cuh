@@ -48,6 +48,15 @@ __device__ __forceinline__ double curvature_lookup(const ModelConst& m, double s
     return 0.0;
 }
 
+// 1 / x for a normal, finite x to ~1 ulp: hardware seed (20 bits) + two Newton steps; no slow-path call, so no registers are
+// parked in local memory around it
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    return fma(fma(-x, r, 1.0), r, r);
+}
+
 // (dist, idx) lexicographic "less": ties go to the lower row index
 __device__ __forceinline__ bool cand_less(double d1, int i1, double d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
 
@@ -102,6 +111,9 @@ constexpr int K1_MAXLAPS = 8;    // trToUse supported
 constexpr int K1_TILE = 512;     // lap rows staged in shared memory per pass (fp32 features)
 constexpr int K1_LOCAL = 3;      // entries of the lane-local candidate list
 constexpr int K1_CAND = 32;      // exact re-scoring buffer per warp
+constexpr unsigned K1_JBITS = 7; // low mantissa bits of a scan key that hold the lane's row counter: laps of up to 32 * 128 rows
+constexpr unsigned K1_JMASK = (1u << K1_JBITS) - 1u;
+constexpr float K1_FAR = 1.0e18f; // feature value of the padding rows of a tile (farther than any stored row, no overflow)
 
 struct K1Args {
     int batch, N, wpb, pts_stride;   // warps per block; doubles of per-warp scratch (see k1_pts_stride)
@@ -114,11 +126,11 @@ struct K1Args {
                           //        4 = a single neighbour in a lap — cases where the reference raises,
                           //        32 = more than K1_CAND rows within rounding distance of the k-th neighbour)
 };
-// per-warp scratch: selected points [7*trToUse][10] (x0 x1 x2 u0 u1 K y0 y1 y2 1) | normal equations 45 (+3 pad)
-//                   | two augmented systems 5x6 + 5x7 (+3 pad)
+// per-warp scratch: selected points [7*trToUse][15] (x0 x1 x2 delta a 1 | y0 y1 y2 | K*(x0 x1 x2 delta a 1)) | normal
+//                   equations 45 (+3 pad) | staging of the closed-form record entries (17, +3 pad)
 //                   | re-scoring buffer: K1_CAND exact distances + K1_CAND row indices | the query point (5 doubles, +1 pad)
-constexpr int K1_PW = 10;        // doubles per selected point
-__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * K1_PW + 48 + 68 + K1_CAND + K1_CAND / 2 + 6; }
+constexpr int K1_PW = 15;        // doubles per selected point
+__host__ __device__ inline int k1_pts_stride(int trToUse) { return K1_MAXPTS * trToUse * K1_PW + 48 + 20 + K1_CAND + K1_CAND / 2 + 6; }
 
 // The reference's distance of one stored row to the query (PM.py:185-186): diff = (Data - x) * scaling, 1-norm summed left to
 // right (numpy semantics for 5 columns), in IEEE fp64 with no contraction: the value np.argsort ranks.
@@ -134,15 +146,23 @@ __device__ __noinline__ double k1_exact_dist(const ModelConst& m, const double* 
 }
 
 // grid = (B, ceil(N / wpb)); one warp per horizon step (= query point).  Per stored lap:
-//   1. the CTA stages the lap's five regression features as fp32, feature-major, in shared memory (tiles of K1_TILE rows) and
-//      every warp scans the tile for its own query with an fp32 distance -- ten full-rate instructions per row instead of
-//      fourteen half-rate fp64 ones -- keeping the K1_LOCAL best rows of every lane in registers;
-//   2. the warp merges the lane lists: g = k-th smallest fp32 distance; every row with an fp32 distance within the rounding
-//      margin of g is re-scored with the reference's exact fp64 distance (global memory, a few rows) and the exact k nearest
-//      are selected on the key (distance, row) -- bit for bit the rows np.argsort picks (PM.py:189), ties to the lower row;
-//   3. a lane list that may have dropped such a row (its last entry is still within the margin) makes the warp re-collect
-//      from global memory with the now known threshold (rare: more than K1_LOCAL near-ties in one lane).
+//   1. the CTA stages the lap's five regression features as fp32 in shared memory (tiles of K1_TILE rows, padded to whole
+//      batches of 32 with far-away rows) and every warp scans the tile for its own query with an fp32 distance -- ten full-rate
+//      instructions per row instead of fourteen half-rate fp64 ones.  Each lane keeps its K1_LOCAL smallest rows as packed keys
+//      (distance bits | row counter) maintained by five integer min / max: the loop has no branch;
+//   2. G = the k-th smallest lane minimum bounds the k-th smallest distance from above; every listed row with a key within the
+//      rounding margin of G is re-scored with the reference's exact fp64 distance (global memory, ~9 rows) and the exact k
+//      nearest are selected on the key (distance, row) -- bit for bit the rows np.argsort picks (PM.py:189), ties to the lower
+//      row; the bandwidth test (PM.py:187-191) is made on the exact distances of the candidates;
+//   3. a lane list that may have dropped such a row (all its entries are within the margin) makes the warp re-collect from
+//      global memory with the now known threshold (rare: K1_LOCAL + 1 of the ~9 nearest rows in one lane).
 // HBM traffic is one pass over the used laps per CTA; the scan is instruction-issue bound.
+// record entry e of (A | B | C) -> staged value (see the kernel's last block); -1 = written by the regression lanes
+__constant__ signed char K1_ABC_SRC[54] = {
+    -1, -1, -1, 0, 0, 0,   -1, -1, -1, 0, 0, 0,   -1, -1, -1, 0, 0, 0,      // A rows 0..2
+    3, 4, 2, 5, 0, 6,      7, 8, 0, 9, 1, 10,     11, 12, 0, 13, 0, 1,      // A rows 3..5
+    0, -1,  -1, 0,  -1, 0,  0, 0,  0, 0,  0, 0,                             // B
+    -1, -1, -1, 14, 15, 16};                                                // C
 #ifndef LMPC_K1_MINBLOCKS
 #define LMPC_K1_MINBLOCKS 3
 #endif
@@ -160,8 +180,8 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
     double* pts = wbase;                                               // this warp's scratch
     const int np_max = K1_MAXPTS * m.trToUse;
     double* ne = pts + (size_t)np_max * K1_PW;                         // 48
-    double* sys = ne + 48;                                             // 30 + 35 (+3)
-    double* cbd = sys + 68;                                            // exact distances of the re-scored rows [K1_CAND]
+    double* sys = ne + 48;                                             // 17 (+3)
+    double* cbd = sys + 20;                                            // exact distances of the re-scored rows [K1_CAND]
     int* cbi = reinterpret_cast<int*>(cbd + K1_CAND);                  // their row indices [K1_CAND]
 
     const int ii = active ? i : 0;
@@ -174,9 +194,8 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
     const float f0 = (float)qv[0], f1 = (float)qv[1], f2 = (float)qv[2], f3 = (float)qv[3], f4 = (float)qv[4];
     const float s0 = (float)m.scaling[0], s1 = (float)m.scaling[1], s2 = (float)m.scaling[2], s3 = (float)m.scaling[3], s4 = (float)m.scaling[4];
     const float qsum = s0 * fabsf(f0) + s1 * fabsf(f1) + s2 * fabsf(f2) + s3 * fabsf(f3) + s4 * fabsf(f4);
-    const float hf = (float)m.h;
-    const float h_lo = hf;
     const int kk = m.MaxNumPoint;
+    const double rh = fast_rcp(m.h);
     int flags = 0, npts = 0;
 
     for (int c = 0; c < m.trToUse; ++c) {
@@ -185,97 +204,78 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
         const double* X = a.pool.x + lap * a.pool.Tmax * 6;
         const double* U = a.pool.u + lap * a.pool.Tmax * 2;
         const int T = a.pool.len[lap];
-        // lane-local candidate lists, ascending in the fp32 distance (earlier rows first on ties: rows arrive in order)
-        float ld[K1_LOCAL];
-        int li[K1_LOCAL];
-#pragma unroll
-        for (int j = 0; j < K1_LOCAL; ++j) { ld[j] = 3.0e38f; li[j] = 0x7fffffff; }
-        int cnt = 0;
-        float band = 3.0e38f;                                // smallest |d32 - h| seen: rows near the bandwidth need the exact test
-        float amax = 0.0f;                                   // largest scaled 1-norm of a stored row: sizes the rounding margin
+        // lane-local candidate lists: the K1_LOCAL smallest KEYS a lane has seen, ascending.  A key is the fp32 distance with its
+        // low K1_JBITS mantissa bits replaced by the lane's row counter j (row t = 32 j + lane): non-negative floats order like
+        // their bit patterns, so three unsigned min / two max per row keep the list sorted -- no branch, no index registers.
+        unsigned k0 = 0xffffffffu, k1 = 0xffffffffu, k2 = 0xffffffffu;
         for (int t0 = 0; t0 < T - 1; t0 += K1_TILE) {
             const int rows = min(K1_TILE, T - 1 - t0);      // rows 0..T-2 are candidates (PM.py:183)
+            const int rows32 = (rows + 31) & ~31;            // the last batch is padded with far-away rows: the scan has no bounds test
             __syncthreads();                                 // previous tile fully consumed
-            for (int r = threadIdx.x; r < rows; r += nthr) {            // one 48 B + one 16 B row per thread -> feature-major fp32
-                const double2 v01 = *reinterpret_cast<const double2*>(X + (size_t)(t0 + r) * 6);
-                const double v2 = X[(size_t)(t0 + r) * 6 + 2];
-                const double2 uu = *reinterpret_cast<const double2*>(U + (size_t)(t0 + r) * 2);
-                tile4[r] = make_float4((float)v01.x, (float)v01.y, (float)v2, (float)uu.x);
-                tile1[r] = (float)uu.y;
+            for (int r = threadIdx.x; r < rows32; r += nthr) {          // one 48 B + one 16 B row per thread -> fp32
+                if (r < rows) {
+                    const double2 v01 = *reinterpret_cast<const double2*>(X + (size_t)(t0 + r) * 6);
+                    const double v2 = X[(size_t)(t0 + r) * 6 + 2];
+                    const double2 uu = *reinterpret_cast<const double2*>(U + (size_t)(t0 + r) * 2);
+                    tile4[r] = make_float4((float)v01.x, (float)v01.y, (float)v2, (float)uu.x);
+                    tile1[r] = (float)uu.y;
+                } else {
+                    tile4[r] = make_float4(K1_FAR, K1_FAR, K1_FAR, K1_FAR);
+                    tile1[r] = K1_FAR;
+                }
             }
             __syncthreads();
             if (active) {
-                for (int rb = 0; rb < rows; rb += 32) {
-                    const int r = rb + lane;
-                    if (r < rows) {
-                        const float4 xv = tile4[r];
-                        const float x4 = tile1[r];
-                        float d = s0 * fabsf(xv.x - f0);
-                        d = fmaf(s1, fabsf(xv.y - f1), d);
-                        d = fmaf(s2, fabsf(xv.z - f2), d);
-                        d = fmaf(s3, fabsf(xv.w - f3), d);
-                        d = fmaf(s4, fabsf(x4 - f4), d);
-                        amax = fmaxf(amax, d);               // d + qsum bounds the row's own scaled norm
-                        const int t = t0 + r;
-                        cnt += (d < h_lo) ? 1 : 0;
-                        band = fminf(band, fabsf(d - hf));   // a row this close to the bandwidth is decided in fp64 afterwards
-                        if (d < ld[K1_LOCAL - 1]) {
-                            ld[K1_LOCAL - 1] = d; li[K1_LOCAL - 1] = t;
-#pragma unroll
-                            for (int j = K1_LOCAL - 1; j > 0; --j) {
-                                if (ld[j] < ld[j - 1]) {
-                                    const float td = ld[j]; ld[j] = ld[j - 1]; ld[j - 1] = td;
-                                    const int ti = li[j]; li[j] = li[j - 1]; li[j - 1] = ti;
-                                }
-                            }
-                        }
-                    }
+                unsigned j = (unsigned)(t0 >> 5);
+#pragma unroll 4
+                for (int rb = 0; rb < rows32; rb += 32, ++j) {
+                    const float4 xv = tile4[rb + lane];
+                    const float x4 = tile1[rb + lane];
+                    float d = s0 * fabsf(xv.x - f0);
+                    d = fmaf(s1, fabsf(xv.y - f1), d);
+                    d = fmaf(s2, fabsf(xv.z - f2), d);
+                    d = fmaf(s3, fabsf(xv.w - f3), d);
+                    d = fmaf(s4, fabsf(x4 - f4), d);
+                    const unsigned key = (__float_as_uint(d) & ~K1_JMASK) | j;
+                    const unsigned a1 = max(k0, key), a2 = max(k1, key);
+                    k0 = min(k0, key);
+                    k1 = min(k1, a1);
+                    k2 = min(k2, a2);
                 }
             }
         }
         if (!active) continue;
-        if (__any_sync(0xffffffffu, band <= hf * 1e-3f)) {    // rare: some row is within 0.1 % of the bandwidth -> exact recount
-            cnt = 0;
-            for (int t = lane; t < T - 1; t += 32) cnt += (k1_exact_dist(m, X, U, t, qv) < m.h) ? 1 : 0;
+        // ---- G = an upper bound of the k-th smallest key: the k-th smallest of the 32 lane minima (k distinct rows are at or
+        //      below it); one REDUX.MIN per round
+        unsigned G = 0xffffffffu;
+        {
+            unsigned cur = k0;
+            for (int rnd = 0; rnd < kk; ++rnd) {
+                G = __reduce_min_sync(0xffffffffu, cur);
+                cur = (cur == G) ? 0xffffffffu : cur;
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        }
-        // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside
-        const int ksel = cnt >= kk ? kk : cnt;
-        if (cnt == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
-        // ---- merge: g = k-th smallest fp32 distance over all lane lists (non-negative floats order like their bit patterns:
-        //      one REDUX.MIN per round); the lists are not consumed, a head counter per lane walks them
-        int hp = 0;
-        float g = 3.0e38f;
-        for (int rnd = 0; rnd < kk; ++rnd) {
-            float hd = 3.0e38f;
-#pragma unroll
-            for (int j = 0; j < K1_LOCAL; ++j) hd = (hp == j) ? ld[j] : hd;
-            const unsigned mn = __reduce_min_sync(0xffffffffu, __float_as_uint(hd));
-            g = __uint_as_float(mn);
-            const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(hd) == mn);
-            if (lane == (__ffs(who) - 1)) ++hp;
-        }
-        // |d32 - d64| < (|row| + |query|) 4.2e-7 (inputs rounded to fp32, five fused terms); a row of the exact top-k is within
-        // twice that of g.  amax + qsum bounds the scaled norm of every row of the lap.
-        const float thr = g + (amax + 2.0f * qsum) * 1.2e-6f;
-        int nl = 0;
-#pragma unroll
-        for (int j = 0; j < K1_LOCAL; ++j) nl += (ld[j] <= thr && li[j] != 0x7fffffff) ? 1 : 0;   // (unused list slots hold +inf)
-        const bool saturated = __any_sync(0xffffffffu, nl == K1_LOCAL);   // that lane may have dropped a row within the threshold
+        // Threshold.  A key understates its fp32 distance by < 2^-(23-K1_JBITS) relative (1.53e-5); |d32 - d64| < (|row| + |query|)
+        // 4.2e-7 in the scaled 1-norm (inputs rounded to fp32, five fused terms) and |row| <= d + |query|.  The k rows behind G have
+        // d64 < G (1 + 1.53e-5) + (G + 2 qsum) 4.3e-7, so every row of the exact top-k -- and, when fewer than k rows lie inside the
+        // bandwidth h, every row inside it (then G >= h - margin) -- has a key below
+        //     thr = G (1 + 3.2e-5) + (G + 2 qsum) 1.3e-6.
+        const float Gf = __uint_as_float(G & ~K1_JMASK);
+        const bool open = !(Gf < K1_FAR * 1e-3f);                   // fewer than k lanes hold a row: everything stored is a candidate
+        const float thrf = open ? 3.0e38f : fmaf(Gf, 3.2e-5f, Gf) + (Gf + 2.0f * qsum) * 1.3e-6f;
+        const unsigned thrk = __float_as_uint(thrf) | K1_JMASK;
+        const int nrow = T - 1;
+        const bool in0 = k0 <= thrk && (int)(((k0 & K1_JMASK) << 5) + lane) < nrow && k0 != 0xffffffffu;
+        const bool in1 = k1 <= thrk && (int)(((k1 & K1_JMASK) << 5) + lane) < nrow && k1 != 0xffffffffu;
+        const bool in2 = k2 <= thrk && (int)(((k2 & K1_JMASK) << 5) + lane) < nrow && k2 != 0xffffffffu;
+        const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
         int nc = 0;
-        if (!saturated) {
-            int off = nl;                                  // inclusive scan of the per-lane counts
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
-            nc = __shfl_sync(0xffffffffu, off, 31);
-            off -= nl;
-#pragma unroll
-            for (int j = 0; j < K1_LOCAL; ++j)
-                if (j < nl && off + j < K1_CAND) cbi[off + j] = li[j];
+        if (m2 == 0u) {                                    // no lane list is full of candidates: nothing was dropped
+            const unsigned lt = (1u << lane) - 1u;
+            const int c0 = __popc(m0), c1 = __popc(m1);
+            if (in0) { const int pos = __popc(m0 & lt); cbi[pos] = (int)(((k0 & K1_JMASK) << 5) + lane); }
+            if (in1) { const int pos = c0 + __popc(m1 & lt); if (pos < K1_CAND) cbi[pos] = (int)(((k1 & K1_JMASK) << 5) + lane); }
+            nc = c0 + c1;
         } else {                                           // rare: re-collect from global memory with the known threshold
             for (int t0 = 0; t0 < T - 1; t0 += 32) {
                 const int t = t0 + lane;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
                     d = fmaf(s2, fabsf((float)xr[2] - f2), d);
                     d = fmaf(s3, fabsf((float)ur[0] - f3), d);
                     d = fmaf(s4, fabsf((float)ur[1] - f4), d);
-                    in = d <= thr;
+                    in = d <= thrf;
                 }
                 const unsigned mask = __ballot_sync(0xffffffffu, in);
                 const int pos = nc + __popc(mask & ((1u << lane) - 1u));
@@ -298,36 +298,39 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
         }
         if (nc > K1_CAND) { flags |= 32; nc = K1_CAND; }
         __syncwarp();
-        // ---- exact re-scoring and selection of the k nearest on the key (distance, row): kk rounds of warp arg-min; distances
-        //      are non-negative doubles, so their bit patterns order like unsigned integers and three 32-bit REDUX.MIN (high
-        //      word, low word, row) find the winner
-        // The lane that holds a winning candidate writes that point itself: features, kernel weight (PM.py:193) and the
-        // next-row targets -- no second pass over the selected rows.
+        int ksel = 0;
+        // ---- exact re-scoring and selection of the k nearest on the key (distance, row): every candidate lane counts the
+        //      candidates that precede it (a handful of broadcast shared-memory reads) -- its rank in np.argsort's order.
+        // The lane that holds a winning candidate writes that point itself: features, next-row targets and the kernel-weighted
+        // features (PM.py:193) -- no second pass over the selected rows.
         {
             double cd = 1e300;
             int ci = 0x7fffffff;
-            if (lane < nc) { ci = cbi[lane]; cd = k1_exact_dist(m, X, U, ci, qv); }
-            const double mine = cd;
-            const int mrow = ci;
-            int rank = -1;
-            for (int r = 0; r < kk; ++r) {
-                const unsigned hi = (unsigned)__double2hiint(cd), lo = (unsigned)__double2loint(cd);
-                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-                const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-                const bool eq = (hi == mh) && (lo == ml);
-                const int wi = (int)__reduce_min_sync(0xffffffffu, eq ? (unsigned)ci : 0xffffffffu);
-                if (eq && ci == wi && ci != 0x7fffffff) { rank = r; cd = 1e300; ci = 0x7fffffff; }
+            if (lane < nc) { ci = cbi[lane]; cd = k1_exact_dist(m, X, U, ci, qv); cbd[lane] = cd; }
+            // PM.py:187-191: >= MaxNumPoint neighbours inside the bandwidth -> the MaxNumPoint closest, else all inside.  Every row
+            // inside the bandwidth is a candidate whenever fewer than k are (see the threshold), so counting candidates decides it.
+            const int inside = __popc(__ballot_sync(0xffffffffu, cd < m.h));
+            ksel = inside >= kk ? kk : inside;
+            if (inside == 1) flags |= 4;    // np.squeeze() makes this case raise in the reference
+            __syncwarp();
+            int rank = 0;
+            for (int j = 0; j < nc; ++j) {
+                const double dj = cbd[j];
+                const int ij = cbi[j];
+                rank += (dj < cd || (dj == cd && ij < ci)) ? 1 : 0;
             }
-            if (rank >= 0 && rank < ksel) {
+            if (lane < nc && rank < ksel) {
                 double* P = pts + (size_t)(npts + rank) * K1_PW;
-                const double* xr = X + (size_t)mrow * 6;
-                const double* ur = U + (size_t)mrow * 2;
-                const double rr = mine / m.h;
-                P[0] = xr[0]; P[1] = xr[1]; P[2] = xr[2]; P[3] = ur[0]; P[4] = ur[1];
-                P[5] = (1.0 - rr * rr) * 3.0 / 4.0;
+                const double* xr = X + (size_t)ci * 6;
+                const double* ur = U + (size_t)ci * 2;
+                const double rr = cd * rh;
+                const double Kw = (1.0 - rr * rr) * 3.0 / 4.0;
+                const double z0 = xr[0], z1 = xr[1], z2 = xr[2], z3 = ur[0], z4 = ur[1];
+                P[0] = z0; P[1] = z1; P[2] = z2; P[3] = z3; P[4] = z4; P[5] = 1.0;
                 P[6] = xr[6]; P[7] = xr[7]; P[8] = xr[8];       // row + 1 (PM.py:163: y = xStored[it][index + 1, yIndex])
-                P[9] = 1.0;
+                P[9] = Kw * z0; P[10] = Kw * z1; P[11] = Kw * z2; P[12] = Kw * z3; P[13] = Kw * z4; P[14] = Kw;
             }
+            __syncwarp();                                   // cbd / cbi are rewritten for the next lap
         }
         npts += ksel;
     }
@@ -336,7 +339,8 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
 
     // ---- normal equations (PM.py:141-168).  entries: Qvx(15) Qlat(15) bvx(5) bvy(5) bwz(5) ----
     for (int e = lane; e < 45; e += 32) {
-        // entry e = sum_p P[ir] * K * P[ic]; feature columns of a point row: 0..2 state, 3 delta, 4 a, 9 the constant 1
+        // entry e = sum_p (K z)[ir] * P[ic]; columns of a point row: 0..2 state, 3 delta, 4 a, 5 the constant 1, 6..8 targets,
+        // 9..14 the kernel-weighted features
         int ir, ic;
         bool diag = false;
         if (e < 30) {
@@ -345,160 +349,106 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
             // (r, cc), r <= cc, of the idx-th entry of the upper triangle of a 5 x 5 matrix
             const int r = (idx >= 5) + (idx >= 9) + (idx >= 12) + (idx >= 14);
             const int cc = idx - (r * 5 - r * (r - 1) / 2) + r;
-            ir = (r < 3) ? r : (r == 3 ? (lat ? 3 : 4) : 9);
-            ic = (cc < 3) ? cc : (cc == 3 ? (lat ? 3 : 4) : 9);
+            ir = (r < 3) ? r : (r == 3 ? (lat ? 3 : 4) : 5);
+            ic = (cc < 3) ? cc : (cc == 3 ? (lat ? 3 : 4) : 5);
             diag = (r == cc);
         } else {
             const int which = (e - 30) / 5, r = (e - 30) % 5;   // 0 vx, 1 vy, 2 wz
             const int lat = which > 0;
-            ir = (r < 3) ? r : (r == 3 ? (lat ? 3 : 4) : 9);
+            ir = (r < 3) ? r : (r == 3 ? (lat ? 3 : 4) : 5);
             ic = 6 + which;
         }
         double acc = 0.0;
         const double* P = pts;
-        for (int p = 0; p < npts; ++p, P += K1_PW) acc += P[ir] * P[5] * P[ic];
+        for (int p = 0; p < npts; ++p, P += K1_PW) acc = fma(P[9 + ir], P[ic], acc);
         if (diag) acc += m.lamb;
         ne[e] = acc;
     }
     __syncwarp();
-    // ---- two augmented systems in shared memory: S1 = [Qvx | bvx] (5 x 6), S2 = [Qlat | bvy bwz] (5 x 7);
-    //      Gaussian elimination with partial pivoting, one lane per column (lanes 0..5 and 8..14)
-    double* S1 = sys;
-    double* S2 = sys + 30;
-    for (int e = lane; e < 65; e += 32) {
-        const bool second = e >= 30;
-        const int f = second ? e - 30 : e;
-        const int w_ = second ? 7 : 6;
-        const int r = f / w_, cc = f % w_;
-        double v;
-        if (cc < 5) {
-            const int lo = r < cc ? r : cc, hi = r < cc ? cc : r;
-            v = ne[(second ? 15 : 0) + lo * 5 - lo * (lo - 1) / 2 + (hi - lo)];
-        } else {
-            v = ne[(second ? 35 + 5 * (cc - 5) : 30) + r];
-        }
-        (second ? S2 : S1)[f] = v;
-    }
-    __syncwarp();
+    // ---- three 5 x 5 solves in registers, one per lane (0: vx, 1: vy, 2: wz): the matrices are Gram matrices, so symmetric
+    //      elimination without pivoting is stable; only the upper triangle is kept
+    double th[5];
     {
-        const bool in1 = lane < 6, in2 = lane >= 8 && lane < 15;
-        double* Sm = in2 ? S2 : S1;
-        const int w_ = in2 ? 7 : 6;
-        const int col = in2 ? lane - 8 : lane;
+        const int sy = lane < 2 ? lane : 2;
+        const double* qa = ne + (sy == 0 ? 0 : 15);
+        const double* qr = ne + 30 + 5 * sy;
+        double A5[5][5];                      // upper triangle; a pivot is replaced by its reciprocal once used
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+#pragma unroll
+            for (int cc = r; cc < 5; ++cc) A5[r][cc] = qa[r * 5 - r * (r - 1) / 2 + (cc - r)];
+            th[r] = qr[r];
+        }
         bool ok = true;
-        for (int cpiv = 0; cpiv < 5; ++cpiv) {
-            // pivot search (lane redundant within each system)
-            int piv = cpiv;
-            double best = fabs(Sm[cpiv * w_ + cpiv]);
-            for (int r = cpiv + 1; r < 5; ++r) {
-                const double v = fabs(Sm[r * w_ + cpiv]);
-                if (v > best) { best = v; piv = r; }
-            }
-            if (!(best > 0.0)) ok = false;
-            __syncwarp();
-            if ((in1 || in2) && piv != cpiv) {               // swap rows, one column per lane
-                const double t = Sm[cpiv * w_ + col];
-                Sm[cpiv * w_ + col] = Sm[piv * w_ + col];
-                Sm[piv * w_ + col] = t;
-            }
-            __syncwarp();
-            const double pv = Sm[cpiv * w_ + cpiv];
-            const double inv = (pv != 0.0) ? 1.0 / pv : 0.0;
-            double f[5];
 #pragma unroll
-            for (int r = 0; r < 5; ++r) f[r] = Sm[r * w_ + cpiv] * inv;   // multipliers (read before any update)
-            const double prow = Sm[cpiv * w_ + col];
-            __syncwarp();
-            if ((in1 || in2) && col > cpiv) {
+        for (int c = 0; c < 5; ++c) {
+            const double pv = A5[c][c];
+            if (!(pv > 1e-280)) ok = false;
+            const double inv = (pv > 1e-280) ? fast_rcp(pv) : 0.0;
+            A5[c][c] = inv;
 #pragma unroll
-                for (int r = 0; r < 5; ++r)
-                    if (r > cpiv) Sm[r * w_ + col] -= f[r] * prow;
+            for (int r = c + 1; r < 5; ++r) {
+                const double f = A5[c][r] * inv;
+#pragma unroll
+                for (int j = r; j < 5; ++j) A5[r][j] = fma(-f, A5[c][j], A5[r][j]);
+                th[r] = fma(-f, th[c], th[r]);
             }
-            __syncwarp();
         }
-        if (!ok) flags |= 1;
-        // back substitution: rhs columns (lane 5 of S1; lanes 13, 14 of S2)
-        if ((in1 && col == 5) || (in2 && col >= 5)) {
-            double xs_[5];
 #pragma unroll
-            for (int r = 4; r >= 0; --r) {
-                double v = Sm[r * w_ + col];
+        for (int r = 4; r >= 0; --r) {
+            double v = th[r];
 #pragma unroll
-                for (int j = 4; j > r; --j) v -= Sm[r * w_ + j] * xs_[j];
-                const double dg = Sm[r * w_ + r];
-                xs_[r] = (dg != 0.0) ? v / dg : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < 5; ++r) Sm[r * w_ + col] = xs_[r];
+            for (int j = r + 1; j < 5; ++j) v = fma(-A5[r][j], th[j], v);
+            th[r] = v * A5[r][r];
         }
-        __syncwarp();
+        if (__any_sync(0xffffffffu, !ok && lane < 3)) flags |= 1;
     }
-    // theta_vx = S1[:,5], theta_vy = S2[:,5], theta_wz = S2[:,6]
 
     // ---- A, B, C (PM.py:66-135) ----
     double* out = a.abc + ((size_t)b * a.N + i) * 54;
-    const double vx = xl[0], vy = xl[1], wz = xl[2], epsi = xl[3], s = xl[4], ey = xl[5];
-    const double dt = m.dt;
-    int okc = 1;
-    const double cur = curvature_lookup(m, s, &okc);
-    if (!okc) flags |= 2;
-    const double den = 1.0 - cur * ey;
-    double se, ce;
-    sincos(epsi, &se, &ce);
-    for (int e = lane; e < 54; e += 32) {
-        double v = 0.0;
-        if (e < 18) {                       // rows 0..2 of A: regression coefficients on (vx, vy, wz)
-            const int r = e / 6, cc = e % 6;
-            if (cc < 3) v = (r == 0) ? S1[cc * 6 + 5] : S2[cc * 7 + 5 + (r - 1)];
-        } else if (e < 36) {                // rows 3..5 of A: Jacobian of the curvilinear kinematics
-            const int r = e / 6, cc = e % 6;
-            if (r == 3) {
-                v = cc == 0 ? -dt * ce / den * cur : cc == 1 ? dt * se / den * cur : cc == 2 ? dt
-                    : cc == 3 ? 1.0 - dt * (-vx * se - vy * ce) / den * cur : cc == 4 ? 0.0
-                    : dt * (vx * ce - vy * se) / (den * den) * cur * (-cur);
-            } else if (r == 4) {
-                v = cc == 0 ? dt * (ce / den) : cc == 1 ? -dt * (se / den) : cc == 2 ? 0.0
-                    : cc == 3 ? dt * (-vx * se - vy * ce) / den : cc == 4 ? 1.0
-                    : -dt * (vx * ce - vy * se) / (den * den) * (-cur);
-            } else {
-                v = cc == 0 ? dt * se : cc == 1 ? dt * ce : cc == 2 ? 0.0 : cc == 3 ? dt * (vx * ce - vy * se)
-                    : cc == 4 ? 0.0 : 1.0;
-            }
-        } else if (e < 48) {
-            const int r = (e - 36) >> 1, cc = (e - 36) & 1;
-            if (r == 0 && cc == 1) v = S1[3 * 6 + 5];          // vx row uses the acceleration input (PM.py:29,70)
-            else if (r == 1 && cc == 0) v = S2[3 * 7 + 5];     // lateral rows use the steering input (PM.py:30,78,82)
-            else if (r == 2 && cc == 0) v = S2[3 * 7 + 6];
-        } else {
-            const int r = e - 48;
-            if (r == 0) v = S1[4 * 6 + 5];
-            else if (r == 1) v = S2[4 * 7 + 5];
-            else if (r == 2) v = S2[4 * 7 + 6];
-            else {
-                // C_r = f_r(x) - A_r x, products summed left to right like np.dot on 6 terms
-                double A3[6];
-                double fx;
-                if (r == 3) {
-                    A3[0] = -dt * ce / den * cur; A3[1] = dt * se / den * cur; A3[2] = dt;
-                    A3[3] = 1.0 - dt * (-vx * se - vy * ce) / den * cur; A3[4] = 0.0;
-                    A3[5] = dt * (vx * ce - vy * se) / (den * den) * cur * (-cur);
-                    fx = epsi + dt * (wz - (vx * ce - vy * se) / (1.0 - cur * ey) * cur);
-                } else if (r == 4) {
-                    A3[0] = dt * (ce / den); A3[1] = -dt * (se / den); A3[2] = 0.0;
-                    A3[3] = dt * (-vx * se - vy * ce) / den; A3[4] = 1.0;
-                    A3[5] = -dt * (vx * ce - vy * se) / (den * den) * (-cur);
-                    fx = s + dt * ((vx * ce - vy * se) / (1.0 - cur * ey));
-                } else {
-                    A3[0] = dt * se; A3[1] = dt * ce; A3[2] = 0.0; A3[3] = dt * (vx * ce - vy * se); A3[4] = 0.0; A3[5] = 1.0;
-                    fx = ey + dt * (vx * se + vy * ce);
-                }
-                double dsum = 0.0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) dsum += A3[j] * xl[j];
-                v = fx - dsum;
-            }
+    if (lane < 3) {                          // rows 0..2: regression coefficients on (vx, vy, wz), the input and the constant
+        out[lane * 6 + 0] = th[0]; out[lane * 6 + 1] = th[1]; out[lane * 6 + 2] = th[2];
+        out[36 + 2 * lane + (lane == 0 ? 1 : 0)] = th[3];   // vx uses the acceleration input, the lateral rows the steering (PM.py:29-30)
+        out[48 + lane] = th[4];
+    }
+    // rows 3..5: Jacobian of the curvilinear kinematics; every lane evaluates the few distinct values, lane 3 stages them and the
+    // warp writes the record through an index table
+    {
+        const double vx = xl[0], vy = xl[1], wz = xl[2], epsi = xl[3], sc = xl[4], ey = xl[5];
+        const double dt = m.dt;
+        int okc = 1;
+        const double cur = curvature_lookup(m, sc, &okc);
+        if (!okc) flags |= 2;
+        const double den = 1.0 - cur * ey;
+        const double rden = fast_rcp(den), rden2 = rden * rden;
+        double se, ce;
+        sincos(epsi, &se, &ce);
+        const double vl = vx * ce - vy * se;          // longitudinal speed along the centre line
+        const double vt = -vx * se - vy * ce;
+        const double a30 = -dt * ce * rden * cur, a31 = dt * se * rden * cur, a33 = 1.0 - dt * vt * rden * cur;
+        const double a35 = dt * vl * rden2 * cur * (-cur);
+        const double a40 = dt * (ce * rden), a41 = -dt * (se * rden), a43 = dt * vt * rden, a45 = -dt * vl * rden2 * (-cur);
+        const double a50 = dt * se, a51 = dt * ce, a53 = dt * vl;
+        // C_r = f_r(x) - A_r x, products summed left to right like np.dot on 6 terms
+        const double f3 = epsi + dt * (wz - vl * rden * cur);
+        const double f4 = sc + dt * (vl * rden);
+        const double f5 = ey + dt * (vx * se + vy * ce);
+        const double c3 = f3 - (a30 * vx + a31 * vy + dt * wz + a33 * epsi + 0.0 * sc + a35 * ey);
+        const double c4 = f4 - (a40 * vx + a41 * vy + 0.0 * wz + a43 * epsi + sc + a45 * ey);
+        const double c5 = f5 - (a50 * vx + a51 * vy + 0.0 * wz + a53 * epsi + 0.0 * sc + ey);
+        double* vals = sys;
+        if (lane == 3) {
+            vals[0] = 0.0; vals[1] = 1.0; vals[2] = dt;
+            vals[3] = a30; vals[4] = a31; vals[5] = a33; vals[6] = a35;
+            vals[7] = a40; vals[8] = a41; vals[9] = a43; vals[10] = a45;
+            vals[11] = a50; vals[12] = a51; vals[13] = a53;
+            vals[14] = c3; vals[15] = c4; vals[16] = c5;
         }
-        out[e] = v;
+        __syncwarp();
+        for (int e = lane; e < 54; e += 32) {
+            const int k = K1_ABC_SRC[e];
+            if (k >= 0) out[e] = vals[k];
+        }
     }
     if (lane == 0 && flags) atomicOr(&a.status[b], flags);
 }
