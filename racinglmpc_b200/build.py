@@ -5,8 +5,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "lmpc_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "ftocp_pdip.cuh"), os.path.join(HERE, "csrc", "safeset.cuh"),
-        os.path.join(HERE, "..", "include", "lmpc_b200.h")]
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("ftocp_pdip.cuh", "safeset.cuh", "lapbooks.cuh", "probe.cuh")] + \
+       [os.path.join(HERE, "..", "include", "lmpc_b200.h")]
 OUT = os.path.join(HERE, "liblmpc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

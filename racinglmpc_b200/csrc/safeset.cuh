@@ -108,7 +108,10 @@ __device__ __forceinline__ bool solve5(double (&A)[5][5], double (&b)[NR][5]) {
 
 constexpr int K1_MAXPTS = 7;     // MaxNumPoint supported by the register top-k
 constexpr int K1_MAXLAPS = 8;    // trToUse supported
-constexpr int K1_TILE = 512;     // lap rows staged in shared memory per pass (fp32 features)
+#ifndef LMPC_K1_TILE
+#define LMPC_K1_TILE 512
+#endif
+constexpr int K1_TILE = LMPC_K1_TILE;     // lap rows staged in shared memory per pass (fp32 features)
 constexpr int K1_LOCAL = 3;      // entries of the lane-local candidate list
 constexpr int K1_CAND = 32;      // exact re-scoring buffer per warp
 constexpr unsigned K1_JBITS = 7; // low mantissa bits of a scan key that hold the lane's row counter: laps of up to 32 * 128 rows
