@@ -184,8 +184,10 @@ struct Work {
     double hv[8];                   // h~ = r~ + A~' p
 #endif
     // --- terminal block ---
-    double Wm[TM], Wi[TM];
+    alignas(16) double Wm[TM], Wi[TM];
     double sbar[6], yT[6];
+    alignas(16) double red[8];      // warp sums of up to eight values at once (wsumv)
+    alignas(16) double tv[8];       // 6-vectors handed from the lanes that compute them to the whole warp
     int flag;
 };
 
@@ -428,6 +430,35 @@ struct Pdip {
         }
     }
 
+    // Warp sums of NV <= 8 per-lane values at once; every lane receives all of them (and w.red keeps a copy until the next
+    // call).  Tensor-core form: A = e_i 1' selects row i, B carries value i of the 32 lanes, so D[i][n] collects the four-lane
+    // partial sums of value i; a product with the all-ones matrix then adds the eight partial sums: NV + 2 MMAs instead of
+    // 15 NV shuffle / add instructions.
+    template <int NV>
+    static LMPC_HD void wsumv(W& w, double (&v)[NV]) {
+        static_assert(NV >= 1 && NV <= 8, "up to eight values");
+        wsync();                                    // earlier readers of red are done
+#if LMPC_MMA
+        const int lane = LMPC_LANE;
+        const int r = lane >> 2;
+        Frag Da{0.0, 0.0}, Db{0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double sel = (r == i) ? 1.0 : 0.0;
+            if (i & 1) dmma(Db.a, Db.b, sel, v[i], Db.a, Db.b);
+            else dmma(Da.a, Da.b, sel, v[i], Da.a, Da.b);
+        }
+        const Frag T = prod(Frag{1.0, 1.0}, Frag{Da.a + Db.a, Da.b + Db.b});   // T[m][i] = sum_n D[i][n]
+        if (lane < 4) st2(&w.red[2 * lane], T.a, T.b);
+        wsync();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = w.red[i];
+#else
+#pragma unroll
+        for (int i = 0; i < NV; ++i) w.red[i] = v[i];
+#endif
+    }
+
     // xi = SS lam - x_N, yT = -T xi (both derived every iteration: the terminal equality and the
     // xi-stationarity row then hold by construction).  Returns sum(lam) - 1.
     static LMPC_HD double terminal_state(W& w, RG& g, const FtocpConst& c) {
@@ -438,9 +469,13 @@ struct Pdip {
             sl += g.lam[r];
         }
         double xi[6];
+        {
+            double v[7] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], sl};
+            wsumv<7>(w, v);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) xi[a] = wsum(acc[a]) - w.x[N * 6 + a];
-        sl = wsum(sl);
+            for (int a = 0; a < 6; ++a) xi[a] = v[a] - w.x[N * 6 + a];
+            sl = v[6];
+        }
         wsync();   // previous readers of yT are done
         FOR_LANES(a, 6) {
             double y = 0.0;
@@ -464,15 +499,41 @@ struct Pdip {
 #pragma unroll
             for (int a = 0; a < 6; ++a) acc[a] += w.SS[a * M + row] * di;
         }
-        double delta = wsum(dl);
+        double sums[7] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], dl};
+        wsumv<7>(w, sums);
+        const double delta = sums[6];
         const double idelta = recip(delta);
-        double sb[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) sb[a] = wsum(acc[a]) * idelta;
 #pragma unroll
         for (int a = 0; a < 6; ++a)
-            if (LMPC_LANE == (a % LMPC_NLANE)) w.sbar[a] = sb[a];   // same value on every lane
+            if (LMPC_LANE == (a % LMPC_NLANE)) w.sbar[a] = sums[a] * idelta;   // same value on every lane
         wsync();
+#if LMPC_MMA
+        // W = Tinv + S~ diag(d4i) S~' on the tensor cores: one m8n8k4 step per four safe-set points.  Lane (r, q) supplies
+        // S~[r][4j+q] d4i[4j+q] as the A element and S~[r][4j+q] as the B element (rows 6, 7 are zero); two accumulators.
+        {
+            static_assert(M % 4 == 0 || M == 0, "safe-set size must be a multiple of four");
+            const int lane = sweep_lane();
+            const int r = lane >> 2, q = lane & 3;
+            const double m6 = (r < 6) ? 1.0 : 0.0;
+            const double sb_r = w.sbar[r < 6 ? r : 0];
+            const double* Sr = &w.SS[(r < 6 ? r : 0) * M + q];
+            const double* Dq = &w.d4i[q];
+            Frag Wa{0.0, 0.0}, Wb{0.0, 0.0};
+#pragma unroll 4
+            for (int j = 0; j + 1 < M / 4; j += 2) {
+                const double s0 = (Sr[4 * j] - sb_r) * m6, s1 = (Sr[4 * j + 4] - sb_r) * m6;
+                dmma(Wa.a, Wa.b, s0 * Dq[4 * j], s0, Wa.a, Wa.b);
+                dmma(Wb.a, Wb.b, s1 * Dq[4 * j + 4], s1, Wb.a, Wb.b);
+            }
+            if ((M / 4) & 1) {
+                const int j = M / 4 - 1;
+                const double s0 = (Sr[4 * j] - sb_r) * m6;
+                dmma(Wa.a, Wa.b, s0 * Dq[4 * j], s0, Wa.a, Wa.b);
+            }
+            if (r < 6 && q < 3)
+                st2(&w.Wm[r * 6 + 2 * q], Wa.a + Wb.a + c.Tinv[r * 6 + 2 * q], Wa.b + Wb.b + c.Tinv[r * 6 + 2 * q + 1]);
+        }
+#else
         // W (21 unique entries), four partial accumulators each
         FOR_LANES(e, 21) {
             int a = 0, b = e;
@@ -494,6 +555,7 @@ struct Pdip {
             w.Wm[a * 6 + b] = v;
             w.Wm[b * 6 + a] = v;
         }
+#endif
         wsync();
         // lane-redundant 6x6 Cholesky, triangular inverse and Wi = Linv' Linv
         double L[21];   // packed lower, row i: i(i+1)/2 + j
@@ -553,9 +615,11 @@ struct Pdip {
 #pragma unroll
             for (int a = 0; a < 6; ++a) acc[a] += (w.SS[a * M + row] - w.sbar[a]) * t;
         }
+        double v[7] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], sb};
+        wsumv<7>(w, v);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) c1[a] = -wsum(acc[a]) - w.sbar[a] * b1;
-        beta = b1 - wsum(sb);
+        for (int a = 0; a < 6; ++a) c1[a] = -v[a] - w.sbar[a] * b1;
+        beta = b1 - v[6];
     }
 
     // ---------------------------------------------------------------- backward sweeps ----
@@ -1194,16 +1258,18 @@ LMPC_SWEEP_UNROLL
     // evaluated THROUGH the recovered dlam removes it (oracle/pdip_model.py W_REFINE).
     static LMPC_HD double terminal_recover(W& w, RG& g, const FtocpConst& c, const double* c1, double beta,
                                            double delta, double b1) {
-        double v[6], dyT[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) v[a] = w.dx[N * 6 + a] + c1[a];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
+        // the 6 x 6 products run one row per lane; the results travel through shared memory
+        double dyT[6];
+        wsync();                                   // earlier readers of tv are done
+        FOR_LANES(a, 6) {
             double t = 0.0;
 #pragma unroll
-            for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * v[b];
-            dyT[a] = t;
+            for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * (w.dx[N * 6 + b] + c1[b]);
+            w.tv[a] = t;
         }
+        wsync();
+#pragma unroll
+        for (int a = 0; a < 6; ++a) dyT[a] = w.tv[a];
         const double dy1t = -beta * recip(delta);
         double acc[6] = {0, 0, 0, 0, 0, 0};
         FOR_SLOTS(r, row, R4) {
@@ -1215,22 +1281,27 @@ LMPC_SWEEP_UNROLL
 #pragma unroll
             for (int a = 0; a < 6; ++a) acc[a] += (w.SS[a * M + row] - w.sbar[a]) * t;
         }
-        double e[6], ddy[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            double t = w.dx[N * 6 + a] - w.sbar[a] * b1 - wsum(acc[a]);
+        wsumv<6>(w, acc);                          // also leaves the sums in w.red
+        FOR_LANES(a, 6) {                          // residual of the terminal equality through the recovered dlam (tv is free: dyT is in registers)
+            double t = w.dx[N * 6 + a] - w.sbar[a] * b1 - w.red[a];
 #pragma unroll
             for (int b = 0; b < 6; ++b) t -= c.Tinv[a * 6 + b] * dyT[b];
-            e[a] = t;
+            w.tv[a] = t;
         }
+        wsync();
+        FOR_LANES(a, 6) {                          // (red is free: its sums were consumed above)
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * w.tv[b];
+            w.red[a] = t;
+        }
+        wsync();
+        double ddy[6];
         double sdy = 0.0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            double t = 0.0;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) t += w.Wi[a * 6 + b] * e[b];
-            ddy[a] = t;
-            sdy += w.sbar[a] * (dyT[a] + t);
+            ddy[a] = w.red[a];
+            sdy += w.sbar[a] * (dyT[a] + ddy[a]);
         }
         FOR_SLOTS(r, row, R4) {
             double t = 0.0;
