@@ -59,24 +59,48 @@ namespace lmpc {
 #define LMPC_NLANE 32
 #define LMPC_LANE ((int)(threadIdx.x & 31))
 __device__ __forceinline__ void wsync() { __syncwarp(); }
-__device__ __forceinline__ double wsum(double v) {
+#ifndef LMPC_RED_INLINE
+#define LMPC_RED_INLINE 1
+#endif
+#if LMPC_RED_INLINE
+#define LMPC_RED_ATTR __forceinline__
+#else
+#define LMPC_RED_ATTR __noinline__      // one copy of each butterfly: the kernels are instruction-cache bound
+#endif
+__device__ LMPC_RED_ATTR double wsum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ double wmin(double v) {
+__device__ LMPC_RED_ATTR double wmin(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ double wmax(double v) {
+__device__ LMPC_RED_ATTR double wmax(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// max / min of NON-NEGATIVE values (|.|, step bounds): such doubles order like their bit patterns, so two 32-bit REDUX
+// (high word, then the low words of the lanes that tie on it) replace five shuffle + NaN-aware fmax rounds (~50 instructions)
+__device__ __forceinline__ double wmax_nn(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)__double2loint(v) : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double wmin_nn(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? (unsigned)__double2loint(v) : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
 #else
 #define LMPC_NLANE 1
 #define LMPC_LANE 0
+inline double wmax_nn(double v) { return v; }
+inline double wmin_nn(double v) { return v; }
 inline void wsync() {}
 inline double wsum(double v) { return v; }
 inline double wmin(double v) { return v; }
@@ -1152,7 +1176,7 @@ LMPC_SWEEP_UNROLL
         wsync();
         double ru_max = 0.0;
         FOR_LANES(e, N * 2) ru_max = fmax(ru_max, fabs(w.ru[e >> 1][e & 1]));
-        return wmax(ru_max);
+        return wmax_nn(ru_max);
     }
 
     // Gradient-only backward sweep for a new right-hand side (corrector / recentring): c_k = M'(A~'c + g_k), f_k.
@@ -1410,7 +1434,7 @@ LMPC_SWEEP_UNROLL
                 }
                 snapped = true;
             }
-            rd_loc = wmax(rd_loc);
+            rd_loc = wmax_nn(rd_loc);
             r_prim = fabs(rone);
             if (it > 0 && step_prev < 1e299) {      // (not right after a (re)start: there is no previous step to extrapolate from)
                 // The input-stationarity residual is linear in the iterate and every variable moved by the same step
@@ -1494,7 +1518,7 @@ LMPC_SWEEP_UNROLL
                     g.p4[r] = g.dlam[r] * dn4;
                 }
             }
-            const double a_aff = wmin(ratio_bound(rn, rd, 1.0));
+            const double a_aff = wmin_nn(ratio_bound(rn, rd, 1.0));
             // complementarity after the affine step.  With p = dw*dnu and dw*nu + w*dnu = -w*nu:
             //   (w + a dw)(nu + a dnu) = w nu (1 - a) + a^2 p
             double comp_aff = 0.0;
@@ -1590,7 +1614,7 @@ LMPC_SWEEP_UNROLL
                         dn4_[r] = dn4;
                     }
                 }
-                const double amax = wmin(ratio_bound(rn, rd, 1e300));
+                const double amax = wmin_nn(ratio_bound(rn, rd, 1e300));
                 al = fmin(1.0, 0.995 * amax);
                 if (!(al > 0.0) || !(al <= 1.0)) { bad_step = true; break; }
                 // Stay in a wide neighbourhood of the central path, min_i w_i nu_i >= gamma * mean: without it
@@ -1645,7 +1669,7 @@ LMPC_SWEEP_UNROLL
             double dmax = 0.0;
             FOR_LANES(e, (N + 1) * 6) { const double d = al * w.dx[e]; w.x[e] += d; dmax = fmax(dmax, fabs(d)); }
             FOR_LANES(e, N * 2) { const double d = al * w.du[e]; w.u[e] += d; dmax = fmax(dmax, fabs(d)); }
-            step_prev = wmax(dmax);
+            step_prev = wmax_nn(dmax);
             wsync();
         }
 
@@ -1665,7 +1689,7 @@ LMPC_SWEEP_UNROLL
 #endif
             rdyn = fmax(rdyn, fabs(w.x[(k + 1) * 6 + a] - v));
         }
-        r_prim = fmax(r_prim, wmax(rdyn));
+        r_prim = fmax(r_prim, wmax_nn(rdyn));
         if (warm != nullptr && (warm_restarted || (warm_started && status != ST_SOLVED)) && LMPC_LANE == 0) *warm_valid = 0;
         info.status = status;
         info.iters = it;
