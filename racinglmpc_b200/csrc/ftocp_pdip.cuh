@@ -26,6 +26,7 @@
 // A "phase" never reads shared memory that another lane writes in the same phase.
 #pragma once
 #include <math.h>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define LMPC_HD __host__ __device__ __forceinline__
@@ -113,6 +114,13 @@ inline double wmax(double v) { return v; }
 #define FOR_LANES(e, n) for (int e = LMPC_LANE; e < (n); e += LMPC_NLANE)
 #endif
 #define NSLOT(CNT) (((CNT) + LMPC_NLANE - 1) / LMPC_NLANE)
+// Horizons from LMPC_STREAM_MIN_N on do not stage the stage model (A | B | C, 44 % of the per-stage footprint) in shared memory:
+// the tensor-core sweeps read their fragments of it straight from global memory / L2, one stage ahead of their use, which
+// doubles the warps an SM holds at N = 48.  Tensor-core build only.
+#ifndef LMPC_STREAM_MIN_N
+#define LMPC_STREAM_MIN_N 32
+#endif
+constexpr bool stream_model(int N) { return LMPC_MMA && N >= LMPC_STREAM_MIN_N; }
 // condensed Hessian weight of lane row (k, i) / input-bound row (k, j): per-stage 8-vector (tensor-core path) or flat arrays
 #if LMPC_MMA
 #define LMPC_WDT(w, k, i, row) (w).Wd[k][i]
@@ -164,7 +172,10 @@ struct Work {
     // As loaded: per stage A (36, row major a*6+b) | B (12, a*2+q) | C (6).  prepare_model() transposes A and B in
     // place, after which ABC[k][j*6 + c] = [A_k B_k](c, j), j < 8: every dot product of the sweeps then runs over a
     // contiguous, 16 B-aligned 6-vector (LDS.128).
-    alignas(16) double ABC[N][54];
+    static constexpr bool STREAM = stream_model(N);
+    alignas(16) double ABC[STREAM ? 1 : N][54];
+    const double* gabc;             // STREAM: this instance's stage model in global memory (stage k at gabc + k * gstage)
+    int gstage;                     // STREAM: doubles between two stage records
     alignas(16) double SS[6 * MM];  // SS[a*M + l]      (PC.py:411 SS_PointSelectedTot, 6 x M)
     double Qfun[MM];                // Qfun_SelectedTot (PC.py:412)
     double uOld[2];                 // OldInput         (PC.py:136,247)
@@ -987,13 +998,44 @@ struct Pdip {
 
     // Lane-constant addressing of the stage-data fragments.  A lane whose fragment entry is a structural constant (identity /
     // zero rows of A~ and M) reads it from w.cst with stride 0, so the sweeps contain no lane-dependent branches.
+    // Offsets are doubles from sweep_base(): the staged model in shared memory, or -- STREAM -- the instance's model in global
+    // memory, in which case the shared-memory operands (constants, gains) sit at 64-bit generic-address distances from it.
+    static constexpr bool STREAM = W::STREAM;
+    using Off = typename std::conditional<STREAM, long long, int>::type;
     struct LaneMap {
         int r, q;
-        int at_a, at_b, at_step;   // D layout of A~' : (A~[2q][r], A~[2q+1][r]), doubles from &ABC[0][0]; per-stage step
-        int af, af_step;           // D layout of A~  : (A~[r][2q], A~[r][2q+1]) as one 16-byte load
-        int mf, mf_step;           // D layout of M   : rows 6,7 = K (from Kst), identity elsewhere
-        int mt_a, mt_b, mt_step;   // D layout of M'  : (M[2q][r], M[2q+1][r]); q == 3 -> (K0[r], K1[r])
+        Off at_a, at_b; int at_step;   // D layout of A~' : (A~[2q][r], A~[2q+1][r]); per-stage step
+        Off af; int af_step;           // D layout of A~  : (A~[r][2q], A~[r][2q+1]) as one 16-byte load
+        Off mf; int mf_step;           // D layout of M   : rows 6,7 = K (from Kst), identity elsewhere
+        Off mt_a, mt_b; int mt_step;   // D layout of M'  : (M[2q][r], M[2q+1][r]); q == 3 -> (K0[r], K1[r])
+        Off cst;                       // the constant block (1,0 | 0,1 | 0,0)
     };
+    // base address of the stage model as the sweeps see it.  STREAM: a global pointer made opaque, so that the compiler treats
+    // base + offset as a generic address (the offsets of the shared-memory operands leave the global allocation)
+    static LMPC_HD const double* sweep_base(const W& w) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (STREAM) {
+            const double* p = w.gabc;
+            asm volatile("" : "+l"(p));
+            return p;
+        }
+#endif
+        return &w.ABC[0][0];
+    }
+    static LMPC_HD Off base_off(const W& w, const double* base, const double* p) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (STREAM) {
+            (void)w;
+            const double* q = p;                    // generic address of the shared-memory operand
+            asm volatile("" : "+l"(q));
+            return (Off)(((long long)(size_t)q - (long long)(size_t)base) / 8);
+        }
+#endif
+        (void)base;
+        return (Off)(p - &w.ABC[0][0]);
+    }
+    static constexpr int STAGE = 54;
+    static LMPC_HD int stage_step(const W& w) { if constexpr (STREAM) return w.gstage; else return STAGE; }
     // The lane id the sweeps derive their roles from.  Made opaque to the optimiser on purpose: otherwise every role mask and
     // address of a sweep is hoisted out of the interior-point loop and stays live (in registers or spilled) across the row loops.
     static LMPC_HD int sweep_lane() {
@@ -1008,20 +1050,23 @@ struct Pdip {
         m.r = lane >> 2;
         m.q = lane & 3;
         const int r = m.r, q = m.q;
-        const int abc0 = 0;
-        const int cst0 = (int)(&w.cst[0] - &w.ABC[0][0]);
-        const int kst0 = (int)(&w.Kst[0][0] - &w.ABC[0][0]);
+        const double* base = sweep_base(w);
+        const Off abc0 = 0;
+        const Off cst0 = base_off(w, base, &w.cst[0]);
+        const Off kst0 = base_off(w, base, &w.Kst[0][0]);
+        const int stg = stage_step(w);
+        m.cst = cst0;
         // A~ = [A B; 0 I], A row major (a*6+b) at 0, B (a*2+j) at 36
         if (q < 3) {
             m.at_a = abc0 + ((r < 6) ? (2 * q) * 6 + r : 36 + (2 * q) * 2 + (r - 6));
             m.at_b = abc0 + ((r < 6) ? (2 * q + 1) * 6 + r : 36 + (2 * q + 1) * 2 + (r - 6));
-            m.at_step = 54;
+            m.at_step = stg;
         } else {                       // rows 6,7 of A~: (delta(r==6), delta(r==7))
             m.at_a = cst0 + ((r == 6) ? 0 : 1);
             m.at_b = cst0 + ((r == 7) ? 0 : 1);
             m.at_step = 0;
         }
-        if (r < 6) { m.af = abc0 + ((q < 3) ? r * 6 + 2 * q : 36 + 2 * r); m.af_step = 54; }
+        if (r < 6) { m.af = abc0 + ((q < 3) ? r * 6 + 2 * q : 36 + 2 * r); m.af_step = stg; }
         else { m.af = cst0 + ((q == 3) ? ((r == 6) ? 0 : 2) : 4); m.af_step = 0; }
         if (r >= 6) { m.mf = kst0 + (r - 6) * 8 + 2 * q; m.mf_step = 16; }
         else { m.mf = cst0 + ((r == 2 * q) ? 0 : ((r == 2 * q + 1) ? 2 : 4)); m.mf_step = 0; }
@@ -1080,7 +1125,7 @@ struct Pdip {
         const int lane = sweep_lane();
         const LaneMap lm = lane_map(w, lane);
         const int r = lm.r, q = lm.q;
-        const double* base = &w.ABC[0][0];
+        const double* base = sweep_base(w);
         // constant part of the stage Hessian in D layout: blkdiag(2Q, 2R)
         Frag Hc{0.0, 0.0};
         if (r < 6 && q < 3) Hc = Frag{c.Q2[r * 6 + 2 * q], c.Q2[r * 6 + 2 * q + 1]};
@@ -1184,7 +1229,7 @@ LMPC_SWEEP_UNROLL
         const int lane = sweep_lane();
         const LaneMap lm = lane_map(w, lane);
         const int r = lm.r, q = lm.q;
-        const double* base = &w.ABC[0][0];
+        const double* base = sweep_base(w);
         Frag Vf = terminal_vec<false>(w, c1, r, q);
         const double* pa = base + lm.at_a + (N - 1) * lm.at_step;
         const double* pb_ = base + lm.at_b + (N - 1) * lm.at_step;
@@ -1195,6 +1240,8 @@ LMPC_SWEEP_UNROLL
         const double* psi = &w.Sinv[N - 1][0];
         double* pfs = &w.fst[N - 1][0];
         Frag At{*pa, *pb_}, Mt{*ma, *mb}, Gn = ld2(pg), Sn = ld2(psi);
+        Frag At2 = At;                 // STREAM: the model comes from L2, so its fragments are fetched two stages ahead
+        if constexpr (STREAM) { pa -= lm.at_step; pb_ -= lm.at_step; At2 = Frag{*pa, *pb_}; }
         double S2n = psi[2];
 LMPC_SWEEP_UNROLL
         for (int k = N - 1; k >= 0; --k) {
@@ -1202,9 +1249,17 @@ LMPC_SWEEP_UNROLL
             const double s11 = S2n;
             {   // prefetch the next stage's operands off the dependent chain (k == 0 re-reads stage 0)
                 const int st = (k > 0) ? 1 : 0;
-                pa -= st * lm.at_step; pb_ -= st * lm.at_step; ma -= st * lm.mt_step; mb -= st * lm.mt_step;
+                ma -= st * lm.mt_step; mb -= st * lm.mt_step;
                 pg -= st * g_step; psi -= st * 4;
-                At = Frag{*pa, *pb_};
+                if constexpr (STREAM) {
+                    const int s2 = (k > 1) ? 1 : 0;
+                    pa -= s2 * lm.at_step; pb_ -= s2 * lm.at_step;
+                    At = At2;
+                    At2 = Frag{*pa, *pb_};
+                } else {
+                    pa -= st * lm.at_step; pb_ -= st * lm.at_step;
+                    At = Frag{*pa, *pb_};
+                }
                 Mt = Frag{*ma, *mb};
                 Gn = ld2(pg);
                 Sn = ld2(psi);
@@ -1223,7 +1278,7 @@ LMPC_SWEEP_UNROLL
     static LMPC_HD void forward(W& w) {
         const int lane = sweep_lane();
         const LaneMap lm = lane_map(w, lane);
-        const double* base = &w.ABC[0][0];
+        const double* base = sweep_base(w);
         const double* pf = base + lm.af;
         const double* pm = base + lm.mf;
         const double* pc = (lane == 3) ? &w.fst[0][0] : &w.cst[4];
@@ -1233,13 +1288,22 @@ LMPC_SWEEP_UNROLL
         const int o_step = (lane < 3) ? 6 : 2;
         Frag Wf{0.0, 0.0};
         Frag Af = ld2(pf), Mf = ld2(pm), Cf = ld2(pc);
+        Frag Af2 = Af;                 // STREAM: two stages ahead (see backward_rhs)
+        if constexpr (STREAM) { pf += lm.af_step; Af2 = ld2(pf); }
 LMPC_SWEEP_UNROLL
         for (int k = 0; k < N; ++k) {
             const Frag AF = Af, MF = Mf, CF = Cf;
             {   // prefetch the next stage's operands off the dependent chain (the last stage re-reads itself)
                 const int st = (k + 1 < N) ? 1 : 0;
-                pf += st * lm.af_step; pm += st * lm.mf_step; pc += st * c_step;
-                Af = ld2(pf);
+                pm += st * lm.mf_step; pc += st * c_step;
+                if constexpr (STREAM) {
+                    pf += ((k + 2 < N) ? 1 : 0) * lm.af_step;
+                    Af = Af2;
+                    Af2 = ld2(pf);
+                } else {
+                    pf += st * lm.af_step;
+                    Af = ld2(pf);
+                }
                 Mf = ld2(pm);
                 Cf = ld2(pc);
             }
@@ -1256,9 +1320,10 @@ LMPC_SWEEP_UNROLL
     static LMPC_HD void rollout(W& w, const double* x0) {
         const int lane = sweep_lane();
         const LaneMap lm = lane_map(w, lane);
-        const double* pf = &w.ABC[0][0] + lm.af;
-        const double* pc = (lane < 3) ? &w.ABC[0][48 + 2 * lane] : &w.cst[4];
-        const int c_step = (lane < 3) ? 54 : 0;
+        const double* base = sweep_base(w);
+        const double* pf = base + lm.af;
+        const double* pc = base + ((lane < 3) ? (Off)(48 + 2 * lane) : lm.cst + 4);
+        const int c_step = (lane < 3) ? stage_step(w) : 0;
         Frag Wf{0.0, 0.0};
 #pragma unroll
         for (int h = 0; h < 3; ++h)
@@ -1677,12 +1742,13 @@ LMPC_SWEEP_UNROLL
         double rdyn = 0.0;
         FOR_LANES(e, N * 6) {
             int k = e / 6, a = e % 6;
-            const double* T = &w.ABC[k][0];
 #if LMPC_MMA
+            const double* T = sweep_base(w) + (long long)k * stage_step(w);
             double v = T[48 + a] + T[36 + a * 2] * w.u[k * 2] + T[37 + a * 2] * w.u[k * 2 + 1];      // stage record as loaded
 #pragma unroll
             for (int b = 0; b < 6; ++b) v += T[a * 6 + b] * w.x[k * 6 + b];
 #else
+            const double* T = &w.ABC[k][0];
             double v = T[48 + a] + T[36 + a] * w.u[k * 2] + T[42 + a] * w.u[k * 2 + 1];              // transposed in place
 #pragma unroll
             for (int b = 0; b < 6; ++b) v += T[b * 6 + a] * w.x[k * 6 + b];

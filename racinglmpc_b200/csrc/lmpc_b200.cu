@@ -95,7 +95,7 @@ struct KernelSmem {
 #endif
 // what shared memory allows (about 992 B per stage + 3.5 KB for a safe set + 1 KB reserved per CTA), capped by the register target
 constexpr int ftocp_min_blocks(int N, int M) {
-    const int by_smem = 227 * 1024 / (992 * N + (M > 0 ? 74 * M : 0) + 448 + 1024);
+    const int by_smem = 227 * 1024 / ((lmpc::stream_model(N) ? 560 : 992) * N + (M > 0 ? 74 * M : 0) + 448 + 1024);
     const int by_regs = M > 0 ? LMPC_LB_LMPC : LMPC_LB_MPC;
     return by_smem < 1 ? 1 : (by_smem < by_regs ? by_smem : by_regs);
 }
@@ -112,10 +112,14 @@ __global__ void __launch_bounds__(32, ftocp_min_blocks(N, M)) ftocp_kernel(const
     // ---- stage the instance's model into shared memory (TMA 1-D bulk copies) ----
     if (lane == 0) {
         mbar_init(&ks.bar, 1);
-        uint32_t bytes = N * 54 * 8 + (M > 0 ? (6 * M + M) * 8 : 0);
+        constexpr bool STREAM = Work<N, M, NCX, NCU>::STREAM;   // long horizons read the stage model in place (ftocp_pdip.cuh)
+        uint32_t bytes = (STREAM ? 0 : N * 54 * 8) + (M > 0 ? (6 * M + M) * 8 : 0);
         mbar_expect_tx(&ks.bar, bytes);
         const double* src = a.abc + (long long)b * a.abc_inst_stride;
-        if (a.abc_stage_stride == 54) {
+        w.gabc = src;
+        w.gstage = (int)a.abc_stage_stride;
+        if (STREAM) {
+        } else if (a.abc_stage_stride == 54) {
             bulk_g2s(&w.ABC[0][0], src, N * 54 * 8, &ks.bar);
         } else {
             for (int k = 0; k < N; ++k) bulk_g2s(&w.ABC[k][0], src + (long long)k * a.abc_stage_stride, 54 * 8, &ks.bar);
