@@ -178,7 +178,7 @@ struct Work {
     int gstage;                     // STREAM: doubles between two stage records
     alignas(16) double SS[6 * MM];  // SS[a*M + l]      (PC.py:411 SS_PointSelectedTot, 6 x M)
     double Qfun[MM];                // Qfun_SelectedTot (PC.py:412)
-    double uOld[2];                 // OldInput         (PC.py:136,247)
+    alignas(16) double uOld[2];     // OldInput         (PC.py:136,247)
     // --- iterate ---
     alignas(16) double x[(N + 1) * 6];
     alignas(16) double dx[(N + 1) * 6];
@@ -704,6 +704,7 @@ struct Pdip {
         return v;
     }
 
+#if !LMPC_MMA
     // Stage gradients for the costate / input-residual recursion (embarrassingly parallel over stages).
     static LMPC_HD void stage_gradients(W& w, const FtocpConst& c) {
         FOR_LANES(e, N * 8) {
@@ -724,15 +725,10 @@ struct Pdip {
 #pragma unroll
                 for (int jj = 0; jj < NCU; ++jj) v += c.Fu[jj * 2 + r] * w.dx[N * NCX + k * NCU + jj];
             }
-#if LMPC_MMA
-            // row 0: full stage gradient for the predictor right-hand side (adds the eliminated rows' contribution), row 1: -gst
-            w.gv[k][j] = v + ((j < 6) ? rhs_x(w, c, k, j) : rhs_u(w, c, k, j - 6));
-            w.gv[k][8 + j] = -v;
-#else
             w.gst[k][j] = v;
-#endif
         }
     }
+#endif
 
     static constexpr int KF = (NCX > NCU ? NCX : NCU);
 #if !LMPC_MMA
@@ -1078,9 +1074,80 @@ struct Pdip {
     // Right-hand side rows of the eliminated inequality constraints for a NEW right-hand side (corrector): row 0 of gv becomes
     // stage gradient + (Fx' ex | Fu' eu); row 1 (= -stage gradient, written by stage_gradients) is kept.
     static LMPC_HD void stage_rhs(W& w, const FtocpConst& c) {
-        FOR_LANES(e, N * 8) {
-            const int k = e >> 3, j = e & 7;
-            w.gv[k][j] = ((j < 6) ? rhs_x(w, c, k, j) : rhs_u(w, c, k, j - 6)) - w.gv[k][8 + j];
+        const int lane = sweep_lane();
+        const int r = lane >> 2, q = lane & 3;
+        const Frag FaT = fa_t_frag(c, r, q);
+#pragma unroll
+        for (int t = 0; t < (N + 7) / 8; ++t) {
+            const int k = 8 * t + r;
+            const bool live = k < N;
+            const int kk = live ? k : N - 1;
+            const Frag R = prod(row_frag(&w.ex[kk * NCX], &w.eu[kk * NCU], q), FaT);
+            if (live) {
+                const Frag G = ld2(&w.gv[k][8 + 2 * q]);
+                st2(&w.gv[k][2 * q], R.a - G.a, R.b - G.b);
+            }
+        }
+    }
+
+    // D layout of Fa', Fa = [Fx 0; 0 Fu; 0 I2] (constraint rows x stage variables)
+    static LMPC_HD Frag fa_t_frag(const FtocpConst& c, int r, int q) {
+        Frag FaT{0.0, 0.0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = 2 * q + h;
+            double v = 0.0;
+            if (row < NCX) v = (r < 6) ? c.Fx[row * 6 + r] : 0.0;
+            else if (row < NCX + NCU) v = (r >= 6) ? c.Fu[(row - NCX) * 2 + (r - 6)] : 0.0;
+            else if (row >= 6) v = (r == row) ? 1.0 : 0.0;
+            if (h == 0) FaT.a = v; else FaT.b = v;
+        }
+        return FaT;
+    }
+    // entries (2q, 2q+1) of one stage's per-constraint-row vector (lane rows | input rows | 0 0), as an A operand
+    static LMPC_HD Frag row_frag(const double* px, const double* pu, int q) {
+        Frag v{0.0, 0.0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = 2 * q + h;
+            double t = 0.0;
+            if (row < NCX) t = px[row];
+            else if (row < NCX + NCU) t = pu[row - NCX];
+            if (h == 0) v.a = t; else v.b = t;
+        }
+        return v;
+    }
+
+    // Stage gradients for the costate / input-residual recursion, eight stages per tensor-core tile:
+    //   G = (x_k | u_k) blkdiag(2Q, 2R) + (nu1_k | nu2_k) Fa + (qx | input-rate terms),   R = (ex_k | eu_k) Fa
+    // gv row 0 = G + R (predictor right-hand side incl. the eliminated rows' contribution), row 1 = -G.
+    static LMPC_HD void stage_gradients(W& w, const FtocpConst& c) {
+        const int lane = sweep_lane();
+        const int r = lane >> 2, q = lane & 3;
+        Frag Hc{0.0, 0.0};
+        if (r < 6 && q < 3) Hc = Frag{c.Q2[r * 6 + 2 * q], c.Q2[r * 6 + 2 * q + 1]};
+        if (r >= 6 && q == 3) Hc = Frag{c.R2[(r - 6) * 2], c.R2[(r - 6) * 2 + 1]};
+        const Frag FaT = fa_t_frag(c, r, q);
+        const Frag Cq = (q < 3) ? Frag{c.qx[2 * q], c.qx[2 * q + 1]} : Frag{0.0, 0.0};
+#pragma unroll
+        for (int t = 0; t < (N + 7) / 8; ++t) {
+            const int k = 8 * t + r;
+            const bool live = k < N;
+            const int kk = live ? k : N - 1;
+            const Frag Z = ld2((q < 3) ? &w.x[kk * 6 + 2 * q] : &w.u[kk * 2]);
+            // input-rate terms (PC.py:233-242): dR2 (u_k - u_{k-1}) + dR2 (u_k - u_{k+1}), the latter not at the last stage
+            const Frag uk = ld2(&w.u[kk * 2]);
+            const Frag up = ld2((kk == 0) ? &w.uOld[0] : &w.u[(kk - 1) * 2]);
+            const Frag un = ld2(&w.u[((kk < N - 1) ? kk + 1 : kk) * 2]);      // (last stage: u_k - u_k = 0)
+            Frag C0 = Cq;
+            if (q == 3) C0 = Frag{c.dR2[0] * ((uk.a - up.a) + (uk.a - un.a)), c.dR2[1] * ((uk.b - up.b) + (uk.b - un.b))};
+            Frag G = prod_add(Z, Hc, C0);
+            G = prod_add(row_frag(&w.dx[kk * NCX], &w.dx[N * NCX + kk * NCU], q), FaT, G);
+            const Frag R = prod(row_frag(&w.ex[kk * NCX], &w.eu[kk * NCU], q), FaT);
+            if (live) {
+                st2(&w.gv[k][2 * q], G.a + R.a, G.b + R.b);
+                st2(&w.gv[k][8 + 2 * q], -G.a, -G.b);
+            }
         }
     }
 
@@ -1132,16 +1199,7 @@ struct Pdip {
         if (r >= 6 && q == 3) Hc = Frag{c.R2[(r - 6) * 2], c.R2[(r - 6) * 2 + 1]};
         // D layout of Fa', Fa = [Fx 0; 0 Fu; 0 I2]: rows 6,7 select the inputs, their weights Wd[k][6..7] carry the input-rate
         // cost (2 dR2, the last stage 1 dR2) so that the variable part of the stage Hessian is ONE product Fa' diag(Wd_k) Fa
-        Frag FaT{0.0, 0.0};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int row = 2 * q + h;
-            double v = 0.0;
-            if (row < NCX) v = (r < 6) ? c.Fx[row * 6 + r] : 0.0;
-            else if (row < NCX + NCU) v = (r >= 6) ? c.Fu[(row - NCX) * 2 + (r - 6)] : 0.0;
-            else if (row >= 6) v = (r == row) ? 1.0 : 0.0;
-            if (h == 0) FaT.a = v; else FaT.b = v;
-        }
+        const Frag FaT = fa_t_frag(c, r, q);
         // lane roles as 0/1 factors (selects on doubles cost two instructions each, a multiply-add one)
         const double m_x = (r < 6) ? 1.0 : 0.0;                               // column r of Y comes from S (else: the -dR2 constant)
         const double y0c = (r == 6) ? -c.dR2[0] : 0.0, y1c = (r == 7) ? -c.dR2[1] : 0.0;

@@ -8,7 +8,8 @@ marks = []
 for m in sys.argv[4:]:
     ln, lab = m.split(":", 1); marks.append((int(ln), lab))
 marks.sort()
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+ksel = ["-k", "regex:" + os.environ["PROF_KERNEL"]] if os.environ.get("PROF_KERNEL") else []     # reports that hold several kernels
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = [i for i, r in enumerate(rows) if '# Samples' in r][0]
 H = rows[hi]; ci = H.index('# Samples'); ce = H.index('Instructions Executed'); data = rows[hi + 1:]
