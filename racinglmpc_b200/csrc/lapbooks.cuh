@@ -311,10 +311,11 @@ __global__ void __launch_bounds__(256) pool_import_kernel(int batch, LapPool ss,
             if (s_ss >= 0) s_md = book_md_add(k, b, lt);
         }
         __syncthreads();
+        const int c_ss = s_ss, c_md = s_md;                       // private copies: thread 0 rewrites the shared ones next round
         const double* R = rows + (size_t)s_src * Tpad * 9;
-        if (s_ss >= 0) {
+        if (c_ss >= 0) {
             const int T = min(len, min(Tpad, ss.Tmax));
-            const size_t lap = ss.lap_index(b, s_ss);
+            const size_t lap = ss.lap_index(b, c_ss);
             for (int e = threadIdx.x; e < T * 9; e += blockDim.x) {
                 const int t = e / 9, j = e - t * 9;
                 const double v = R[e];
@@ -324,9 +325,9 @@ __global__ void __launch_bounds__(256) pool_import_kernel(int batch, LapPool ss,
             }
             if (threadIdx.x == 0) { ss.len[lap] = T; if (took) atomicAdd(took, 1); }
         }
-        if (s_md >= 0) {                                          // the model stores the lap as driven: rows up to the finish line
+        if (c_md >= 0) {                                          // the model stores the lap as driven: rows up to the finish line
             const int Tm = min(lt, min(len, model.Tmax));
-            const size_t lap = model.lap_index(b, s_md);
+            const size_t lap = model.lap_index(b, c_md);
             for (int e = threadIdx.x; e < Tm * 8; e += blockDim.x) {
                 const int t = e >> 3, j = e & 7;
                 const double v = R[t * 9 + j];
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(256) pool_import_kernel(int batch, LapPool ss,
             if (threadIdx.x == 0) model.len[lap] = Tm;
         }
         __syncthreads();
-        if (threadIdx.x == 0 && s_ss == -2 && flags_or) flags_or[b] |= 64;
+        if (threadIdx.x == 0 && c_ss == -2 && flags_or) flags_or[b] |= 64;
     }
     if (threadIdx.x == 0 && given > 0) book_refresh(k, b);
 }
