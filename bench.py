@@ -49,7 +49,7 @@ SS_BYTES_PER_SOLVE = (6 * 48 + 48 + 6 * 48 + 2 * 48) * 8           # selected sa
 FLOPS_PER_ITER = 12 * 2 * (288 + 216 + 126 + 72 + 36 + 48) + 4 * 12 * 2 * 126 + 4000
 FLOPS_PER_ITER_LMPC = FLOPS_PER_ITER + 2 * 48 * (21 + 6 * 6) + 2000       # + simplex terminal block (W assembly, recoveries)
 # fp64 tensor-core instructions issued per iteration: 12 stages x (11 factor + 4 corrector gradient + 2 x 4 forward)
-DMMA_PER_ITER = 12 * (11 + 4 + 8)
+DMMA_PER_ITER = 12 * (11 + 4 + 8) + 2 * 6 + 2 * 2     # sweeps per stage + stage-gradient / right-hand-side tiles of 8 stages
 
 
 def dist_env():
