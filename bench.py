@@ -329,28 +329,33 @@ def leg_config1(args, rank, world, local, dev):
     # only and is stopped before the host-timed leg (measured: 2.6-3.4 M/s with it running, 3.9 M/s without)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end: the public host API, used the way a caller streams batch after batch: two batches in flight (solve_async on
-    # buffer sets 0/1, wait before a set is reused), pinned host buffers; every step's inputs are copied H2D and every step's results
+    # ---- end-to-end: the public host API, used the way a caller streams batch after batch: three batches in flight (solve_async on
+    # rotating buffer sets, wait before a set is reused), pinned host buffers; every step's inputs are copied H2D and every step's results
     # D2H inside the timed region
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    # pinned host buffers from the library's allocator: pages on the NUMA node of the GPU's PCIe link (lmpc_host_alloc)
+    from racinglmpc_b200 import _native as nat
+    pin = lambda a: nat.pinned_like(np.ascontiguousarray(a), device=local)
     h_x0, h_u, h_abc = pin(x0), pin(uold), pin(abc)
-    outs = [{k: torch.from_numpy(v).pin_memory().numpy() for k, v in solver.alloc_outputs(False).items()} for _ in range(2)]
+    nslot = max(1, min(4, int(os.environ.get("LMPC_B200_E2E_SLOTS", "3"))))   # batches in flight (measurement knob)
+    outs = [{k: pin(v) for k, v in solver.alloc_outputs(False).items()} for _ in range(nslot)]
     for i in range(max(args.warmup, 3) + 20):   # untimed; long enough to bring the clocks back up after the pinning pause
-        slot = i & 1
-        if i >= 2:
+        slot = i % nslot
+        if i >= nslot:
             solver.wait(slot)
         solver.solve_async(slot, h_x0, h_u, h_abc, outs[slot])
-    solver.wait(0); solver.wait(1)
+    for sl in range(nslot):
+        solver.wait(sl)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        slot = i & 1
-        if i >= 2:
-            solver.wait(slot)                  # results of step i-2 are on the host before its buffer set is reused
+        slot = i % nslot
+        if i >= nslot:
+            solver.wait(slot)                  # results of step i-nslot are on the host before its buffer set is reused
         solver.solve_async(slot, h_x0, h_u, h_abc, outs[slot])
-    solver.wait(0); solver.wait(1)
+    for sl in range(nslot):
+        solver.wait(sl)
     torch.cuda.synchronize()
-    out = outs[(args.steps - 1) & 1]
+    out = outs[(args.steps - 1) % nslot]
     e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
     late = solver.late_accepts
     solver.close()
@@ -414,7 +419,8 @@ def leg_config2(args, rank, world, local, dev, steps=None, with_e2e=True):
     ok = float(np.mean((res["status"] == 1) & (res["flags"] == 0)))
     e2e = None
     if with_e2e:       # host x0 in, results out through the public API
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        from racinglmpc_b200 import _native as nat
+        pin = lambda a: nat.pinned_like(np.ascontiguousarray(a), device=local)
         h_x0 = pin(data["x0"])
         out = {k: pin(v) for k, v in c.alloc_step_outputs().items()}
         reset(); c.step(h_x0, out=out, want_ss=False)
@@ -495,8 +501,10 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": HORIZON,
                        "l2": "flushed between timed steps (256 MiB memset on the same stream)",
-                       "e2e_mode": "public host API with two batches in flight (solve_async/wait, double-buffered device inputs), pinned host "
-                                   "buffers; every step copies its inputs H2D and its results D2H inside the timed region",
+                       "e2e_mode": "public host API with three batches in flight (solve_async/wait on rotating buffer sets), pinned host "
+                                   "buffers from lmpc_host_alloc (pages on the GPU's NUMA node); every step copies its inputs H2D and its results D2H "
+                                   "inside the timed region",
+                       "host_numa_node": int(_native.lib().lmpc_host_numa_node(local)),
                        "tolerance": "r_prim, r_dual <= 1e-9, gap <= 1e-11 (unscaled inf-norm), last primal step <= 1e-7",
                        "solved_fraction": float(np.mean(r1["status"] == 1)), "ipm_iters_mean": float(iters.mean()),
                        "ipm_iters_max": int(iters.max()), "max_resid": float(r1["resid"].max()), "late_accepts": r1["late"]},

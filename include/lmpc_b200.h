@@ -91,6 +91,18 @@ long long lmpc_kernel_launches(lmpc_handle* h); /* kernels launched by this hand
  * Synchronises the handle's streams; -1 on error.  0 on every recorded BASELINE workload (tests assert it). */
 long long lmpc_late_accepts(lmpc_handle* h);
 
+/* Pinned host memory for the arrays handed to the `_host` / `_host_async` entry points (no reference counterpart: NumPy arrays
+ * in the reference never leave the host).  The pages are placed on the NUMA node the device's PCIe link hangs off
+ * (/sys/bus/pci/devices/<bus id>/numa_node; an anonymous mapping bound with mbind(MPOL_PREFERRED), touched, then pinned with
+ * cudaHostRegister), which is what a single DMA stream needs to run at link rate on a multi-socket host; zero-filled.
+ * lmpc_host_numa_node: that node, -1 = unknown / switched off with LMPC_B200_NUMA=off (LMPC_B200_NUMA=<n> forces node n).
+ * lmpc_host_page_nodes: node of n (<= 64) evenly sampled pages of a block (diagnostics).  Plain pinned or pageable arrays remain
+ * valid arguments of every entry point. */
+int lmpc_host_alloc(int device, size_t bytes, void** out);
+int lmpc_host_free(void* p);
+int lmpc_host_numa_node(int device);
+int lmpc_host_page_nodes(const void* p, size_t bytes, int n, int* nodes_out);
+
 /* ---- FTOCP solve with the model given by the caller ("fixed A/B/C") ---------------------------------
  * Replaces, per instance: buildCost + buildEqConstr + addTerminalComponents + osqp_solve_qp +
  * unpackSolution (PredictiveControllers.py:110-137,200-283) for an MPC-type problem (no safe set).
@@ -122,9 +134,10 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
                          double* uPred, double* slack, double* lambd, double* slackTerminal, double* zt,
                          double* zt_u, int* status, int* iters, double* resid);
 /* Asynchronous forms of the two *_host entry points, for streaming batch after batch: the call enqueues the copies and the
- * solve on buffer set `slot` (0 or 1; the second set of device buffers is allocated on first use) and returns;
+ * solve on buffer set `slot` (0 .. 3; the further sets of device buffers are allocated on first use) and returns;
  * lmpc_host_wait(h, slot) returns once the results of that slot are in the caller's output arrays.  With two batches in
- * flight the H2D copy of one overlaps the solve of the other.  All host arrays must stay valid (and should be pinned) until
+ * flight the H2D copy of one overlaps the solve of the other; a third keeps the copy engine busy while the host waits for the
+ * oldest batch and enqueues the next (measured: 8.7 -> see DESIGN §4 M solves/s on configs[1]).  All host arrays must stay valid (and should be pinned) until
  * the wait; a slot must be waited for before it is reused.  lmpc_solve_*_host == *_async(slot 0) + lmpc_host_wait(0). */
 int lmpc_solve_mpc_host_async(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
                               long long abc_inst_stride, long long abc_stage_stride, double* xPred, double* uPred,

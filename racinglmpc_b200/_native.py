@@ -112,6 +112,10 @@ def lib():
     L.lmpc_rollout_stats.argtypes = [_vp, _vp]
     L.lmpc_pool_export_dev.argtypes = [_vp, C.c_int, C.c_int, C.c_longlong, _vp, _vp]
     L.lmpc_pool_import_dev.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, _vp, _vp]
+    L.lmpc_host_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(_vp)]
+    L.lmpc_host_free.argtypes = [_vp]
+    L.lmpc_host_numa_node.argtypes = [C.c_int]
+    L.lmpc_host_page_nodes.argtypes = [_vp, C.c_size_t, C.c_int, _vp]
     L.lmpc_sizeof_params.restype = C.c_int
     L.lmpc_sizeof_model_params.restype = C.c_int
     assert L.lmpc_sizeof_params() == C.sizeof(Params), "lmpc_params ABI mismatch"
@@ -149,6 +153,50 @@ def probe_fp64(device=0):
     check(lib().lmpc_probe_fp64(int(device), out.ctypes.data_as(_vp)))
     keys = ("dfma_tflops", "dmma_tflops", "lat_dfma", "lat_dmma_acc", "lat_dmma_a", "lat_lds", "lat_shfl64", "lat_rsqrt")
     return dict(zip(keys, (float(v) for v in out)))
+
+
+class _PinnedBlock:
+    """Owner of one lmpc_host_alloc block; freed when the last ndarray viewing it dies."""
+
+    def __init__(self, device, nbytes):
+        p = _vp()
+        check(lib().lmpc_host_alloc(int(device), max(int(nbytes), 1), C.byref(p)))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().lmpc_host_free(_vp(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64, device=0):
+    """Zero-filled C-contiguous ndarray in pinned host memory on the device's NUMA node (lmpc_host_alloc): the
+    buffers to hand to the ``*_host`` / ``solve_async`` entry points."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    blk = _PinnedBlock(device, n * dt.itemsize)
+    buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(blk.ptr)
+    a = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    buf._lmpc_owner = blk            # ndarray.base -> buf -> blk: the block lives as long as any view of it
+    return a
+
+
+def page_nodes(a, n=8):
+    """NUMA node of ``n`` evenly sampled pages of a host ndarray (diagnostics of the pinned allocator)."""
+    out = np.zeros(n, np.int32)
+    check(lib().lmpc_host_page_nodes(a.ctypes.data_as(_vp), a.nbytes, int(n), out.ctypes.data_as(_vp)))
+    return out.tolist()
+
+
+def pinned_like(a, device=0):
+    """Copy of ``a`` (any array-like) in pinned host memory on the device's NUMA node."""
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype, device)
+    out[...] = a
+    return out
 
 
 def exported_symbols():

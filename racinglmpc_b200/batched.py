@@ -96,10 +96,10 @@ class BatchedFTOCP:
         return o
 
     def solve_async(self, slot, x0, uOld, abc, out, SS_sel=None, Qfun_sel=None, Succ_SS=None, Succ_uSS=None):
-        """Enqueue a host-path solve on buffer set ``slot`` (0 or 1) and return at once; ``wait(slot)`` completes it.
+        """Enqueue a host-path solve on buffer set ``slot`` (0 .. 3) and return at once; ``wait(slot)`` completes it.
         Every array (inputs and the ``out`` dict of ``alloc_outputs``) must be C-contiguous float64/int32, should be pinned,
         and must stay alive and untouched until the wait.  Two slots in flight overlap the copies of one batch with the solve
-        of the other."""
+        of the other; three keep the copy engine busy across the host's wait / enqueue of the next batch."""
         B, N, M = self.B, self.N, self.M
         for a in (x0, uOld, abc):
             if not (isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype == np.float64):

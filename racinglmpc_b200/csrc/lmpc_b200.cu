@@ -14,6 +14,12 @@
 #include <stdlib.h>
 #include <string>
 #include <new>
+#include <ctype.h>
+#include <unistd.h>
+#include <sys/syscall.h>
+#include <sys/mman.h>
+#include <map>
+#include <mutex>
 
 #include "../../include/lmpc_b200.h"
 #include "ftocp_pdip.cuh"
@@ -87,6 +93,10 @@ struct KernelSmem {
 
 // resident CTAs (= warps) per SM the register allocation is held to: horizons up to 14 are bounded by registers and shared
 // memory alike; longer horizons by shared memory only
+#define LMPC_HOST_SLOTS 4              // buffer sets (batches in flight) of the asynchronous host entry points
+#ifndef LMPC_STEP_SPLIT_DEFAULT
+#define LMPC_STEP_SPLIT_DEFAULT 1     // instance ranges of the pipelined device-resident step (1 = one launch sequence)
+#endif
 #ifndef LMPC_LB_MPC
 #define LMPC_LB_MPC 16
 #endif
@@ -199,8 +209,12 @@ struct lmpc_handle {
     FtocpConst c;
     int batch, device, N, M;
     cudaStream_t stream;
-    cudaStream_t cstream[8];   // chunk pipelines of the *_host entry points (H2D | kernel | D2H overlap), 4 streams per slot
-    int hb_chunks[2];
+    cudaStream_t cstream[4 * LMPC_HOST_SLOTS];   // chunk pipelines of the *_host entry points (H2D | kernel | D2H overlap), 4 streams per slot
+    int hb_chunks[LMPC_HOST_SLOTS];
+    // pipelined device-resident step: the batch is cut into step_split instance ranges, each running its kernel sequence on its
+    // own stream (cstream[0..3]) between a fork and a join event on `stream`
+    int step_split;
+    cudaEvent_t ev_fork, ev_join[4];
     bool trace_on;
     cudaEvent_t tev[4][3], t0ev;
     long long launches;
@@ -214,13 +228,12 @@ struct lmpc_handle {
     int* d_warm_valid;
     long long warm_stride;
     int warm_mode;
-    bool use_warm_next;
-    // second buffer set of the asynchronous host entry points (slot 1; allocated on first use)
+    // further buffer sets of the asynchronous host entry points (slots 1 .. LMPC_HOST_SLOTS - 1; each allocated on first use)
     struct HostBufs {
         double *x0, *uOld, *abc, *SS, *Qfun, *SuccSS, *SuccU, *xPred, *uPred, *slack, *lambd, *slackT, *zt, *ztu, *resid;
         int *status, *iters;
-    } hb1;
-    bool has_hb1;
+    } hbx[LMPC_HOST_SLOTS - 1];
+    bool has_hbx[LMPC_HOST_SLOTS - 1];
     // lap stores + controller state (lmpc_store_create)
     bool has_store;
     ModelConst mc;
@@ -345,6 +358,7 @@ static void free_null(T*& p) { if (p) cudaFree(p); p = nullptr; }
 static void free_store(lmpc_handle* h) {
     free_null(h->ss.x); free_null(h->ss.u); free_null(h->ss.q); free_null(h->ss.len);
     free_null(h->mdl.x); free_null(h->mdl.u); free_null(h->mdl.len);
+    free_null(h->mdl.f4); free_null(h->mdl.f1); free_null(h->mdl.stale);
     free_null(h->d_used); free_null(h->d_sel); free_null(h->d_isprev); free_null(h->d_prevslot); free_null(h->d_timeStep);
     free_null(h->d_hasPred); free_null(h->d_flags); free_null(h->d_minidx); free_null(h->d_xLin); free_null(h->d_uLin);
     free_null(h->d_ztState); free_null(h->d_ztFixed); free_null(h->d_OldInput); free_null(h->d_xPredPrev); free_null(h->d_tmpx);
@@ -365,12 +379,12 @@ static void free_rollout(lmpc_handle* h) {
     h->has_rollout = false;
 }
 
-static void free_hb1(lmpc_handle* h) {
-    lmpc_handle::HostBufs& q = h->hb1;
+static void free_hbx(lmpc_handle* h, int i) {
+    lmpc_handle::HostBufs& q = h->hbx[i];
     free_null(q.x0); free_null(q.uOld); free_null(q.abc); free_null(q.SS); free_null(q.Qfun); free_null(q.SuccSS); free_null(q.SuccU);
     free_null(q.xPred); free_null(q.uPred); free_null(q.slack); free_null(q.lambd); free_null(q.slackT); free_null(q.zt); free_null(q.ztu);
     free_null(q.resid); free_null(q.status); free_null(q.iters);
-    h->has_hb1 = false;
+    h->has_hbx[i] = false;
 }
 
 static int create_device_side(lmpc_handle* h) {
@@ -378,7 +392,11 @@ static int create_device_side(lmpc_handle* h) {
     int rc = configure(h->N, h->M > 0 ? h->M : 0);
     if (rc != LMPC_OK) return rc;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4 * LMPC_HOST_SLOTS; ++i) CK(cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    h->step_split = LMPC_STEP_SPLIT_DEFAULT;
+    if (const char* e = getenv("LMPC_B200_STEP_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 4) h->step_split = v; }   // tuning knob
     const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
 #define DALLOC(ptr, count) CK(cudaMalloc((void**)&h->ptr, sizeof(*h->ptr) * (count)))
     DALLOC(d_x0, B * 6); DALLOC(d_uOld, B * 2); DALLOC(d_abc, B * N * 54);
@@ -399,6 +417,92 @@ int lmpc_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+// ---- pinned host memory next to the GPU ----------------------------------------------------------------------------------
+// The `_host` entry points move 21.5 MB per configs[1] step over PCIe; on a two-socket host the link runs at full speed
+// only from the memory of the socket the GPU hangs off.  lmpc_host_alloc asks the kernel for pages on that NUMA node
+// (mbind on an anonymous mapping; raw syscalls, libnuma is not in the image) and pins them.
+static int gpu_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[96];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+int lmpc_host_numa_node(int device) {
+    const char* e = getenv("LMPC_B200_NUMA");      // 0 / off: plain pinned memory (A/B measurements); an integer >= 0 forces a node
+    if (e && (!strcmp(e, "off") || !strcmp(e, "-1"))) return -1;
+    if (e && isdigit((unsigned char)e[0]) && strcmp(e, "auto")) return atoi(e);
+    return gpu_numa_node(device);
+}
+// Pages come from an anonymous mapping of this process bound to the node with mbind() and touched here, then pinned with
+// cudaHostRegister: cudaHostAlloc's pages are allocated inside the driver and were measured to ignore the caller's memory policy
+// (profiles/r2_numa_probe.json: all on node 0 with the GPU on node 1, single-stream H2D 23 instead of 52 GB/s).
+static std::mutex g_host_mu;
+static std::map<void*, size_t> g_host_blocks;      // base -> mapped bytes
+int lmpc_host_alloc(int device, size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(LMPC_E_INVALID, "lmpc_host_alloc: null out or zero size");
+    *out = nullptr;
+    CK(cudaSetDevice(device));
+    const size_t gran = 2u << 20;                                   // whole 2 MiB units: eligible for transparent huge pages
+    const size_t len = (bytes + gran - 1) / gran * gran;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return fail(LMPC_E_CUDA, "lmpc_host_alloc: mmap failed");
+    const int node = lmpc_host_numa_node(device);
+#ifdef SYS_mbind
+    if (node >= 0 && node < 1024) {
+        unsigned long mask[1024 / (8 * sizeof(unsigned long))] = {0};
+        mask[node / (8 * sizeof(unsigned long))] = 1UL << (node % (8 * sizeof(unsigned long)));
+        // MPOL_PREFERRED (1): fall back to other nodes rather than fail when the node is short of memory; errors (seccomp,
+        // cpuset without that node) leave the default policy in place
+        (void)syscall(SYS_mbind, p, (unsigned long)len, 1, mask, 1024UL, 0U);
+    }
+#endif
+    memset(p, 0, len);                                              // first touch: the pages exist (on the bound node) before they are pinned
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        munmap(p, len);
+        return fail(LMPC_E_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    { std::lock_guard<std::mutex> g(g_host_mu); g_host_blocks[p] = len; }
+    *out = p;
+    return LMPC_OK;
+}
+int lmpc_host_free(void* p) {
+    if (!p) return LMPC_OK;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> g(g_host_mu);
+        auto it = g_host_blocks.find(p);
+        if (it == g_host_blocks.end()) return fail(LMPC_E_INVALID, "lmpc_host_free: not a block of lmpc_host_alloc");
+        len = it->second;
+        g_host_blocks.erase(it);
+    }
+    cudaError_t e = cudaHostUnregister(p);
+    munmap(p, len);
+    if (e != cudaSuccess) return fail(LMPC_E_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+    return LMPC_OK;
+}
+/* NUMA node of up to n pages of a host block, sampled evenly (move_pages query): nodes_out[n]; diagnostics for the allocator. */
+int lmpc_host_page_nodes(const void* p, size_t bytes, int n, int* nodes_out) {
+    if (!p || !nodes_out || n <= 0 || n > 64) return fail(LMPC_E_INVALID, "lmpc_host_page_nodes: bad argument");
+#ifdef SYS_move_pages
+    void* pages[64];
+    const size_t ps = 4096, np = bytes / ps > 0 ? bytes / ps : 1;
+    for (int i = 0; i < n; ++i) pages[i] = (void*)(((uintptr_t)p & ~(uintptr_t)(ps - 1)) + (np * i / n) * ps);
+    if (syscall(SYS_move_pages, 0, (unsigned long)n, pages, nullptr, nodes_out, 0) != 0)
+        return fail(LMPC_E_STATE, "move_pages query failed");
+    return LMPC_OK;
+#else
+    return fail(LMPC_E_STATE, "move_pages is not available");
+#endif
 }
 
 int lmpc_create(const lmpc_params* p, int batch, int device, lmpc_handle** out) {
@@ -437,11 +541,11 @@ int lmpc_destroy(lmpc_handle* h) {
     if (!h) return LMPC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 8; ++i) if (h->cstream[i]) cudaStreamSynchronize(h->cstream[i]);
+    for (int i = 0; i < 4 * LMPC_HOST_SLOTS; ++i) if (h->cstream[i]) cudaStreamSynchronize(h->cstream[i]);
     // every pointer freed here is either a live allocation or still null (handle memory is zero-initialised)
     free_rollout(h);
     free_store(h);
-    free_hb1(h);
+    for (int i = 0; i < LMPC_HOST_SLOTS - 1; ++i) free_hbx(h, i);
     double* dbl[] = {h->d_x0, h->d_uOld, h->d_abc, h->d_SS, h->d_Qfun, h->d_SuccSS, h->d_SuccU, h->d_xPred, h->d_uPred,
                      h->d_slack, h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid};
     for (double* q : dbl) cudaFree(q);
@@ -449,7 +553,9 @@ int lmpc_destroy(lmpc_handle* h) {
     cudaFree(h->d_iters);
     cudaFree(h->d_late);
     if (h->stream) cudaStreamDestroy(h->stream);
-    for (int i = 0; i < 8; ++i) if (h->cstream[i]) cudaStreamDestroy(h->cstream[i]);
+    for (int i = 0; i < 4 * LMPC_HOST_SLOTS; ++i) if (h->cstream[i]) cudaStreamDestroy(h->cstream[i]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < 4; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     delete h;
     return LMPC_OK;
 }
@@ -467,7 +573,7 @@ long long lmpc_late_accepts(lmpc_handle* h) {
     if (cudaSetDevice(h->device) != cudaSuccess) return -1;
     unsigned long long v = 0;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
-    for (int i = 0; i < 8; ++i) if (cudaStreamSynchronize(h->cstream[i]) != cudaSuccess) return -1;
+    for (int i = 0; i < 4 * LMPC_HOST_SLOTS; ++i) if (cudaStreamSynchronize(h->cstream[i]) != cudaSuccess) return -1;
     if (cudaMemcpy(&v, h->d_late, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (long long)v;
 }
@@ -498,11 +604,8 @@ int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, co
     a.xPred = xPred; a.uPred = uPred; a.slack = slack; a.lambd = lambd; a.slackT = slackTerminal;
     a.zt = zt; a.ztu = zt_u; a.status = status; a.iters = iters; a.resid = resid;
     a.late = h->d_late;
-    a.warm = nullptr; a.warm_valid = nullptr; a.warm_stride = 0;
-    if (h->use_warm_next) {          // set by the device-resident step only: these QPs belong to persistent controllers
-        a.warm = h->d_warm; a.warm_valid = h->d_warm_valid; a.warm_stride = h->warm_stride;
-        h->use_warm_next = false;
-    }
+    a.warm = nullptr; a.warm_valid = nullptr; a.warm_stride = 0;    // caller-supplied QPs start cold; the controllers of the
+                                                                    // device-resident step carry warm-start records (step_range)
     return launch(h, a, lm, h->stream);
 }
 
@@ -519,24 +622,25 @@ static int host_bufs(lmpc_handle* h, int slot, lmpc_handle::HostBufs& b) {
              h->d_lambd, h->d_slackT, h->d_zt, h->d_ztu, h->d_resid, h->d_status, h->d_iters};
         return LMPC_OK;
     }
-    if (!h->has_hb1) {
+    const int xi = slot - 1;
+    if (!h->has_hbx[xi]) {
         const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
-        lmpc_handle::HostBufs& q = h->hb1;
-#define DA1(ptr, count) do { if (cudaMalloc((void**)&q.ptr, sizeof(*q.ptr) * (count)) != cudaSuccess) { free_hb1(h); \
-                              return fail(LMPC_E_CUDA, "cudaMalloc of the second host-path buffer set failed"); } } while (0)
+        lmpc_handle::HostBufs& q = h->hbx[xi];
+#define DA1(ptr, count) do { if (cudaMalloc((void**)&q.ptr, sizeof(*q.ptr) * (count)) != cudaSuccess) { free_hbx(h, xi); \
+                              return fail(LMPC_E_CUDA, "cudaMalloc of a further host-path buffer set failed"); } } while (0)
         DA1(x0, B * 6); DA1(uOld, B * 2); DA1(abc, B * N * 54);
         DA1(SS, B * 6 * M); DA1(Qfun, B * M); DA1(SuccSS, B * 6 * M); DA1(SuccU, B * 2 * M);
         DA1(xPred, B * (N + 1) * 6); DA1(uPred, B * N * 2); DA1(slack, B * N * 2);
         DA1(lambd, B * M); DA1(slackT, B * 6); DA1(zt, B * 6); DA1(ztu, B * 2);
         DA1(resid, B * 3); DA1(status, B); DA1(iters, B);
 #undef DA1
-        h->has_hb1 = true;
+        h->has_hbx[xi] = true;
     }
-    b = h->hb1;
+    b = h->hbx[xi];
     return LMPC_OK;
 }
 
-// Enqueue one host-buffer solve on buffer set / stream group `slot` (0 or 1) WITHOUT waiting for it.
+// Enqueue one host-buffer solve on buffer set / stream group `slot` (0 .. LMPC_HOST_SLOTS - 1) WITHOUT waiting for it.
 static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, const double* uOld, const double* abc,
                               long long abc_inst_stride, long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel,
                               const double* Succ_SS, const double* Succ_uSS, double* xPred, double* uPred, double* slack,
@@ -545,7 +649,7 @@ static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, c
     if (!h || !x0 || !uOld || !abc || !xPred || !uPred || !status || !iters || !resid) return fail(LMPC_E_INVALID, "null argument");
     const bool lm = (SS_sel != nullptr);
     if (lm && (h->M <= 0 || !Qfun_sel)) return fail(LMPC_E_INVALID, "handle was created without a safe set (numSS_Points == 0)");
-    if (slot < 0 || slot > 1) return fail(LMPC_E_INVALID, "slot must be 0 or 1");
+    if (slot < 0 || slot >= LMPC_HOST_SLOTS) return fail(LMPC_E_INVALID, "slot must be 0 .. 3");
     CK(cudaSetDevice(h->device));
     const size_t B = h->batch, N = h->N, M = h->M > 0 ? h->M : 1;
     const size_t D = sizeof(double);
@@ -631,7 +735,7 @@ static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const 
                               double* resid) {
     const int rc = enqueue_host_solve_impl(h, slot, x0, uOld, abc, abc_inst_stride, abc_stage_stride, SS_sel, Qfun_sel, Succ_SS, Succ_uSS,
                                            xPred, uPred, slack, lambd, slackTerminal, zt, zt_u, status, iters, resid);
-    if (rc != LMPC_OK && h && slot >= 0 && slot <= 1) {
+    if (rc != LMPC_OK && h && slot >= 0 && slot < LMPC_HOST_SLOTS) {
         const std::string msg = g_err;
         for (int i = 0; i < 4; ++i) cudaStreamSynchronize(h->cstream[4 * slot + i]);
         g_err = msg;
@@ -641,7 +745,7 @@ static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const 
 
 
 int lmpc_host_wait(lmpc_handle* h, int slot) {
-    if (!h || slot < 0 || slot > 1) return fail(LMPC_E_INVALID, "bad handle or slot");
+    if (!h || slot < 0 || slot >= LMPC_HOST_SLOTS) return fail(LMPC_E_INVALID, "bad handle or slot");
     CK(cudaSetDevice(h->device));
     const int nchunk = h->hb_chunks[slot] > 0 ? h->hb_chunks[slot] : 4;
     for (int ci = 0; ci < nchunk; ++ci) CK(cudaStreamSynchronize(h->cstream[4 * slot + ci]));
@@ -734,6 +838,8 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     DA(h->ss.len, int, B * h->ss.cap);
     DA(h->mdl.x, double, B * model_cap * Tmax * 6); DA(h->mdl.u, double, B * model_cap * Tmax * 2); h->mdl.q = nullptr;
     DA(h->mdl.len, int, B * model_cap);
+    DA(h->mdl.f4, float4, B * model_cap * Tmax); DA(h->mdl.f1, float, B * model_cap * Tmax); DA(h->mdl.stale, int, B * model_cap);
+    h->ss.f4 = nullptr; h->ss.f1 = nullptr; h->ss.stale = nullptr;
     DA(h->d_used, int, B * K1_MAXLAPS); DA(h->d_sel, int, B * 8); DA(h->d_isprev, int, B * 8); DA(h->d_prevslot, int, B);
     DA(h->d_timeStep, int, B); DA(h->d_hasPred, int, B); DA(h->d_flags, int, B); DA(h->d_minidx, int, B * 8);
     DA(h->d_xLin, double, B * (N + 1) * 6); DA(h->d_uLin, double, B * N * 2); DA(h->d_ztState, double, B * 6);
@@ -770,6 +876,7 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     }
     CK(cudaMemsetAsync(h->ss.len, 0, sizeof(int) * B * h->ss.cap, h->stream));
     CK(cudaMemsetAsync(h->mdl.len, 0, sizeof(int) * B * model_cap, h->stream));
+    CK(cudaMemsetAsync(h->mdl.stale, 0, sizeof(int) * B * model_cap, h->stream));
     CK(cudaMemsetAsync(h->d_used, 0, sizeof(int) * B * K1_MAXLAPS, h->stream));
     CK(cudaMemsetAsync(h->d_sel, 0, sizeof(int) * B * 8, h->stream));
     CK(cudaMemsetAsync(h->d_isprev, 0, sizeof(int) * B * 8, h->stream));
@@ -800,6 +907,7 @@ static int put_lap(lmpc_handle* h, LapPool& pool, int inst, int slot, int T, con
     CK(cudaMemcpyAsync(pool.x + lap * pool.Tmax * 6, x, sizeof(double) * T * 6, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(pool.u + lap * pool.Tmax * 2, u, sizeof(double) * T * 2, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(pool.len + lap, &T, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (pool.stale) CK(cudaMemsetAsync(pool.stale + lap, 1, sizeof(int), h->stream));   // the fp32 shadow of this lap is out of date
     CK(cudaStreamSynchronize(h->stream));   // T lives on the caller's stack
     return LMPC_OK;
 }
@@ -864,7 +972,7 @@ int lmpc_ss_add_point(lmpc_handle* h, const double* x, const double* u) {
     CK(cudaMemcpyAsync(h->d_tmpx, x, sizeof(double) * h->batch * 6, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_tmpu, u, sizeof(double) * h->batch * 2, cudaMemcpyHostToDevice, h->stream));
     ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, h->d_tmpx, h->d_tmpu, 2,
-                                                                        h->mc.TrackLength, h->d_flags, h->d_dropped);
+                                                                        h->mc.TrackLength, h->d_flags, h->d_dropped, 0);
     CK(cudaGetLastError());
     h->launches += 1;
     int dropped = 0;
@@ -899,9 +1007,11 @@ int lmpc_ss_patch_row(lmpc_handle* h, int inst, int slot, int row, const double*
         return fail(LMPC_E_INVALID, "bad patch arguments");
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->ss.x + (h->ss.lap_index(inst, slot) * h->ss.Tmax + row) * 6, x6, sizeof(double) * 6, cudaMemcpyHostToDevice, h->stream));
-    if (also_model_slot >= 0 && also_model_slot < h->mdl.cap)
+    if (also_model_slot >= 0 && also_model_slot < h->mdl.cap) {
         CK(cudaMemcpyAsync(h->mdl.x + (h->mdl.lap_index(inst, also_model_slot) * h->mdl.Tmax + row) * 6, x6, sizeof(double) * 6,
                            cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(h->mdl.stale + h->mdl.lap_index(inst, also_model_slot), 1, sizeof(int), h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return LMPC_OK;
 }
@@ -940,29 +1050,36 @@ int lmpc_state_get(lmpc_handle* h, double* xLin, double* uLin, double* zt, doubl
     return LMPC_OK;
 }
 
-static int launch_k1(lmpc_handle* h) {
+static int launch_k1(lmpc_handle* h, int b0 = 0, int nb = -1, cudaStream_t st = nullptr) {
+    if (nb < 0) nb = h->batch;
+    if (!st) st = h->stream;
     K1Args a;
-    a.batch = h->batch; a.N = h->N;
+    a.batch = h->batch; a.N = h->N; a.b0 = b0;
     a.wpb = h->N < 12 ? h->N : 12;
     a.pts_stride = k1_pts_stride(h->mc.trToUse);
     a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
-    dim3 grid(h->batch, (h->N + a.wpb - 1) / a.wpb);
-    size_t smem = sizeof(float) * 5 * K1_TILE + sizeof(double) * (size_t)a.pts_stride * a.wpb;
-    knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, h->stream>>>(h->mc, a);
+    // laps written since the last scan get their fp32 feature rows first (one warp per lap slot, a flag test when nothing changed)
+    model_shadow_refresh_kernel<<<(nb * h->mdl.cap + 7) / 8, 256, 0, st>>>(h->mdl, b0 * h->mdl.cap, (b0 + nb) * h->mdl.cap);
     CK(cudaGetLastError());
-    h->launches += 1;
+    dim3 grid(nb, (h->N + a.wpb - 1) / a.wpb);
+    size_t smem = sizeof(float) * 5 * 2 * K1_TILE + sizeof(double) * (size_t)a.pts_stride * a.wpb;
+    knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, st>>>(h->mc, a);
+    CK(cudaGetLastError());
+    h->launches += 2;
     return LMPC_OK;
 }
 
-static int launch_k2(lmpc_handle* h, const double* d_x0) {
+static int launch_k2(lmpc_handle* h, const double* d_x0, int b0 = 0, int nb = -1, cudaStream_t st = nullptr) {
+    if (nb < 0) nb = h->batch;
+    if (!st) st = h->stream;
     K2Args a;
-    a.batch = h->batch; a.N = h->N; a.numSS_it = h->p.numSS_it; a.P = h->M / h->p.numSS_it;
+    a.batch = h->batch; a.N = h->N; a.b0 = b0; a.numSS_it = h->p.numSS_it; a.P = h->M / h->p.numSS_it;
     a.TrackLength = h->mc.TrackLength;
     a.x0 = d_x0; a.zt = h->d_ztState; a.pool = h->ss; a.sel = h->d_sel; a.is_prev = h->d_isprev;
     a.timeStep = h->d_timeStep; a.has_pred = h->d_hasPred; a.xPred = h->d_xPredPrev;
     a.SS_sel = h->d_SS; a.Qfun_sel = h->d_Qfun; a.Succ_SS = h->d_SuccSS; a.Succ_uSS = h->d_SuccU;
     a.zt_fixed = h->d_ztFixed; a.status = h->d_flags; a.min_index = h->d_minidx;
-    ss_select_kernel<<<h->batch, 32 * a.numSS_it, 0, h->stream>>>(a);
+    ss_select_kernel<<<nb, 32 * a.numSS_it, 0, st>>>(a);
     CK(cudaGetLastError());
     h->launches += 1;
     return LMPC_OK;
@@ -1003,8 +1120,9 @@ int lmpc_select_host(lmpc_handle* h, const double* x0, double* SS_sel, double* Q
     return LMPC_OK;
 }
 
-static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev);
-int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) { return step_dev_impl(h, mode, x0_dev, nullptr); }
+struct StepTail;
+static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev, const StepTail* tail);
+int lmpc_step_dev(lmpc_handle* h, int mode, const double* x0_dev) { return step_dev_impl(h, mode, x0_dev, nullptr, nullptr); }
 
 // The same step with CUDA events between its kernels: ms4 = durations of K1 (regression), K2 (selection; 0 for mode 0), the QP
 // kernel and the state shift.  Measurement support (bench.py's per-kernel rooflines); synchronises.
@@ -1013,7 +1131,7 @@ int lmpc_step_profile(lmpc_handle* h, int mode, const double* x0_dev, float* ms4
     CK(cudaSetDevice(h->device));
     cudaEvent_t ev[5];
     for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&ev[i]));
-    int rc = step_dev_impl(h, mode, x0_dev, ev);
+    int rc = step_dev_impl(h, mode, x0_dev, ev, nullptr);
     if (rc == LMPC_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(LMPC_E_CUDA, "stream synchronisation failed");
     if (rc == LMPC_OK)
         for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms4[i], ev[i], ev[i + 1]);
@@ -1022,40 +1140,89 @@ int lmpc_step_profile(lmpc_handle* h, int mode, const double* x0_dev, float* ms4
 }
 }  // extern "C"
 
-static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev) {
+// K1 -> K2 -> QP -> shift (PC.py:110-137) for the controllers [b0, b0 + nb) on stream st.  `tail` (rollouts) appends what
+// Simulator.sim does with the result for the same controllers: addPoint (mode 1) and dynModel.
+struct StepTail { const double* xc; SimArgs sim; };
+static int step_range(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev, int b0, int nb, cudaStream_t st, const StepTail* tail) {
+    int rc;
+    const size_t N = h->N, M = h->M > 0 ? h->M : 1, lo = b0;
+    const bool lm = mode == 1;
+    if ((rc = launch_k1(h, b0, nb, st)) != LMPC_OK) return rc;                       // PC.py:117
+    if (ev) CK(cudaEventRecord(ev[1], st));
+    if (lm && (rc = launch_k2(h, x0_dev, b0, nb, st)) != LMPC_OK) return rc;         // PC.py:121
+    if (ev) CK(cudaEventRecord(ev[2], st));
+    FtocpArgs a;                                                                     // PC.py:124-125
+    a.batch = nb;
+    a.x0 = x0_dev + lo * 6; a.uOld = h->d_OldInput + lo * 2;
+    a.abc = h->d_abc + lo * N * 54; a.abc_inst_stride = (long long)N * 54; a.abc_stage_stride = 54;
+    a.SS = lm ? h->d_SS + lo * 6 * M : nullptr; a.Qfun = lm ? h->d_Qfun + lo * M : nullptr;
+    a.SuccSS = lm ? h->d_SuccSS + lo * 6 * M : nullptr; a.SuccU = lm ? h->d_SuccU + lo * 2 * M : nullptr;
+    a.xPred = h->d_xPred + lo * (N + 1) * 6; a.uPred = h->d_uPred + lo * N * 2; a.slack = h->d_slack + lo * N * 2;
+    a.lambd = lm ? h->d_lambd + lo * M : nullptr; a.slackT = lm ? h->d_slackT + lo * 6 : nullptr;
+    a.zt = lm ? h->d_zt + lo * 6 : nullptr; a.ztu = lm ? h->d_ztu + lo * 2 : nullptr;
+    a.status = h->d_status + lo; a.iters = h->d_iters + lo; a.resid = h->d_resid + lo * 3;
+    a.late = h->d_late;
+    a.warm = nullptr; a.warm_valid = nullptr; a.warm_stride = 0;
+    if (h->d_warm) { a.warm = h->d_warm + lo * h->warm_stride; a.warm_valid = h->d_warm_valid + lo; a.warm_stride = h->warm_stride; }
+    if ((rc = launch(h, a, lm, st)) != LMPC_OK) return rc;
+    if (ev) CK(cudaEventRecord(ev[3], st));
+    ShiftArgs sa;
+    sa.batch = h->batch; sa.N = h->N; sa.lmpc = mode; sa.b0 = b0;
+    sa.xPred = h->d_xPred; sa.uPred = h->d_uPred; sa.zt_in = h->d_zt; sa.ztu_in = h->d_ztu;
+    sa.xLin = h->d_xLin; sa.uLin = h->d_uLin; sa.zt = h->d_ztState; sa.OldInput = h->d_OldInput; sa.xPredPrev = h->d_xPredPrev;
+    sa.timeStep = h->d_timeStep; sa.has_pred = h->d_hasPred;
+    shift_state_kernel<<<nb, 64, 0, st>>>(sa);                                       // PC.py:129-137
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (ev) CK(cudaEventRecord(ev[4], st));
+    if (tail) {
+        if (lm) {                                                                    // SysModel.py:38 -> PC.py:466-476
+            ss_add_point_kernel<<<(nb + 127) / 128, 128, 0, st>>>(b0 + nb, h->ss, h->d_prevslot, tail->xc, h->d_uPred, (long long)h->N * 2,
+                                                                  h->mc.TrackLength, h->d_flags, nullptr, b0);
+            CK(cudaGetLastError());
+            h->launches += 1;
+        }
+        SimArgs sim = tail->sim;                                                     // SysModel.py:40 (dynModel)
+        sim.b0 = b0; sim.b1 = b0 + nb;
+        sim_step_kernel<<<(nb + 127) / 128, 128, 0, st>>>(h->mc, sim);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    return LMPC_OK;
+}
+
+// The whole batch: one launch sequence on the handle's stream, or -- step_split > 1 -- one per instance range, each on its own
+// stream between a fork and a join on the handle's stream.  The controllers are independent (PC.py:317-333), so the ranges only
+// share the GPU: the regression scan of one range (issue-bound) runs under the interior-point solves of another (latency-bound)
+// and the last waves of one range's solves are filled by the next range's.  Results are bit-identical to the unsplit step.
+static int step_dev_impl(lmpc_handle* h, int mode, const double* x0_dev, cudaEvent_t* ev, const StepTail* tail) {
     int rc = need_store(h);
     if (rc) return rc;
     if (!x0_dev || (mode != 0 && mode != 1)) return fail(LMPC_E_INVALID, "bad mode or null x0");
     if (mode == 1 && h->M <= 0) return fail(LMPC_E_INVALID, "LMPC step on a handle without a safe set");
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
-    if (ev) CK(cudaEventRecord(ev[0], h->stream));
-    if ((rc = launch_k1(h)) != LMPC_OK) return rc;                      // PC.py:117
-    if (ev) CK(cudaEventRecord(ev[1], h->stream));
-    if (mode == 1 && (rc = launch_k2(h, x0_dev)) != LMPC_OK) return rc;  // PC.py:121
-    if (ev) CK(cudaEventRecord(ev[2], h->stream));
-    if (h->d_warm) {
-        if (h->warm_mode != mode) {                  // records of the other problem type are not comparable
-            CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * h->batch, h->stream));
-            h->warm_mode = mode;
-        }
-        h->use_warm_next = true;
+    if (h->d_warm && h->warm_mode != mode) {             // records of the other problem type are not comparable
+        CK(cudaMemsetAsync(h->d_warm_valid, 0, sizeof(int) * h->batch, h->stream));
+        h->warm_mode = mode;
     }
-    rc = lmpc_solve_lmpc_dev(h, x0_dev, h->d_OldInput, h->d_abc, (long long)h->N * 54, 54, mode == 1 ? h->d_SS : nullptr,
-                             mode == 1 ? h->d_Qfun : nullptr, mode == 1 ? h->d_SuccSS : nullptr, mode == 1 ? h->d_SuccU : nullptr,
-                             h->d_xPred, h->d_uPred, h->d_slack, mode == 1 ? h->d_lambd : nullptr, mode == 1 ? h->d_slackT : nullptr,
-                             mode == 1 ? h->d_zt : nullptr, mode == 1 ? h->d_ztu : nullptr, h->d_status, h->d_iters, h->d_resid);  // PC.py:124-125
-    if (rc) return rc;
-    if (ev) CK(cudaEventRecord(ev[3], h->stream));
-    ShiftArgs sa;
-    sa.batch = h->batch; sa.N = h->N; sa.lmpc = mode;
-    sa.xPred = h->d_xPred; sa.uPred = h->d_uPred; sa.zt_in = h->d_zt; sa.ztu_in = h->d_ztu;
-    sa.xLin = h->d_xLin; sa.uLin = h->d_uLin; sa.zt = h->d_ztState; sa.OldInput = h->d_OldInput; sa.xPredPrev = h->d_xPredPrev;
-    sa.timeStep = h->d_timeStep; sa.has_pred = h->d_hasPred;
-    shift_state_kernel<<<h->batch, 64, 0, h->stream>>>(sa);             // PC.py:129-137
-    CK(cudaGetLastError());
-    h->launches += 1;
-    if (ev) CK(cudaEventRecord(ev[4], h->stream));
+    if (ev) CK(cudaEventRecord(ev[0], h->stream));
+    int split = ev ? 1 : h->step_split;                  // the per-kernel timing of lmpc_step_profile needs the kernels back to back
+    if (split > h->batch / 256) split = h->batch / 256;  // ranges below a few hundred controllers only add launches
+    if (split <= 1) return step_range(h, mode, x0_dev, ev, 0, h->batch, h->stream, tail);
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    for (int r = 0; r < split; ++r) {
+        const int b0 = (int)((long long)h->batch * r / split), b1 = (int)((long long)h->batch * (r + 1) / split);
+        cudaStream_t st = h->cstream[r];
+        CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+        if ((rc = step_range(h, mode, x0_dev, nullptr, b0, b1 - b0, st, tail)) != LMPC_OK) break;
+        CK(cudaEventRecord(h->ev_join[r], st));
+    }
+    if (rc != LMPC_OK) {                                  // ranges already enqueued finish before the error is reported
+        for (int r = 0; r < split; ++r) cudaStreamSynchronize(h->cstream[r]);
+        return rc;
+    }
+    for (int r = 0; r < split; ++r) CK(cudaStreamWaitEvent(h->stream, h->ev_join[r], 0));
     return LMPC_OK;
 }
 extern "C" {
@@ -1208,6 +1375,18 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     const double* xc = h->d_rx[h->cur];
+    if (z_host) CK(cudaMemcpyAsync(h->d_z, z_host, sizeof(double) * h->batch * 3, cudaMemcpyHostToDevice, h->stream));
+    StepTail tail;
+    tail.xc = xc;
+    SimArgs& sa = tail.sim;
+    sa.batch = h->batch; sa.x = xc; sa.xg = h->d_rg[h->cur]; sa.u = h->d_uPred; sa.u_stride = (long long)h->N * 2;
+    sa.z = z_host ? h->d_z : nullptr; sa.seed = seed; sa.step = h->sim_step;
+    sa.xn = h->d_rx[h->cur ^ 1]; sa.xgn = h->d_rg[h->cur ^ 1];
+    sa.cl_x = h->d_clx; sa.cl_u = h->d_clu; sa.cl_len = h->d_cllen; sa.Tcl = h->Tcl; sa.done = h->d_done; sa.active = nullptr;
+    sa.flags = h->d_flags; sa.status = h->d_status; sa.health = h->d_health;
+    // the trace of the chosen controllers reads the step's results and the state before dynModel: it has to sit between the
+    // solve and the simulator, so a traced batch runs the simulator for the whole batch after it
+    const bool fused_tail = !h->has_trace && mode != 2;
     if (mode == 2) {
         CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * h->batch, h->stream));
         // LTI MPC with the per-instance model identified by lmpc_rollout_sysid (main.py:72-80); like the reference's LTI
@@ -1215,31 +1394,26 @@ int lmpc_rollout_step(lmpc_handle* h, int mode, const double* z_host, unsigned l
         rc = lmpc_solve_mpc_dev(h, xc, h->d_OldInput, h->d_abc_lti, 54, 0, h->d_xPred, h->d_uPred, h->d_slack, h->d_status, h->d_iters,
                                 h->d_resid);
     } else {
-        rc = lmpc_step_dev(h, mode, xc);
+        rc = step_dev_impl(h, mode, xc, nullptr, fused_tail ? &tail : nullptr);
     }
     if (rc) return rc;
-    if (mode == 1) {
-        ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, xc, h->d_uPred,
-                                                                            (long long)h->N * 2, h->mc.TrackLength, h->d_flags, nullptr);
+    if (!fused_tail) {
+        if (mode == 1) {
+            ss_add_point_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->batch, h->ss, h->d_prevslot, xc, h->d_uPred,
+                                                                                (long long)h->N * 2, h->mc.TrackLength, h->d_flags, nullptr, 0);
+            CK(cudaGetLastError());
+            h->launches += 1;
+        }
+        if (h->has_trace) {
+            trace_step_kernel<<<h->tr.n, 128, 0, h->stream>>>(h->tr, xc, h->d_rg[h->cur], h->d_uPred, (long long)h->N * 2, h->d_xPred,
+                                                            mode == 1 ? h->d_SS : nullptr, h->has_books ? h->bk.lap_n : nullptr);
+            CK(cudaGetLastError());
+            h->launches += 1;
+        }
+        sim_step_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->mc, sa);
         CK(cudaGetLastError());
         h->launches += 1;
     }
-    if (h->has_trace) {
-        trace_step_kernel<<<h->tr.n, 128, 0, h->stream>>>(h->tr, xc, h->d_rg[h->cur], h->d_uPred, (long long)h->N * 2, h->d_xPred,
-                                                        mode == 1 ? h->d_SS : nullptr, h->has_books ? h->bk.lap_n : nullptr);
-        CK(cudaGetLastError());
-        h->launches += 1;
-    }
-    if (z_host) CK(cudaMemcpyAsync(h->d_z, z_host, sizeof(double) * h->batch * 3, cudaMemcpyHostToDevice, h->stream));
-    SimArgs sa;
-    sa.batch = h->batch; sa.x = xc; sa.xg = h->d_rg[h->cur]; sa.u = h->d_uPred; sa.u_stride = (long long)h->N * 2;
-    sa.z = z_host ? h->d_z : nullptr; sa.seed = seed; sa.step = h->sim_step;
-    sa.xn = h->d_rx[h->cur ^ 1]; sa.xgn = h->d_rg[h->cur ^ 1];
-    sa.cl_x = h->d_clx; sa.cl_u = h->d_clu; sa.cl_len = h->d_cllen; sa.Tcl = h->Tcl; sa.done = h->d_done; sa.active = nullptr;
-    sa.flags = h->d_flags; sa.status = h->d_status; sa.health = h->d_health;
-    sim_step_kernel<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->mc, sa);
-    CK(cudaGetLastError());
-    h->launches += 1;
     h->cur ^= 1;
     h->sim_step += 1;
     return LMPC_OK;

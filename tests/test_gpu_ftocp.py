@@ -151,26 +151,43 @@ def test_device_pointer_entry_matches_host_entry():
     s.close()
 
 
-def test_async_host_entry_two_slots_match_the_synchronous_call():
-    """lmpc_solve_mpc_host_async on buffer sets 0 and 1 (two batches in flight) returns exactly what the synchronous entry
-    point returns for the same inputs, also when a slot is reused."""
+def test_async_host_entry_slots_match_the_synchronous_call():
+    """lmpc_solve_mpc_host_async on buffer sets 0 .. 3 (up to four batches in flight) returns exactly what the synchronous
+    entry point returns for the same inputs, also when a slot is reused; host arrays from the library's pinned allocator
+    (lmpc_host_alloc) and from torch's."""
     _need_gpu()
+    from racinglmpc_b200 import _native as nat
     B, N = 256, 12
     x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
     s = BatchedFTOCP(rp.mpc_params(N), batch=B)
     ref = s.solve(x0, uold, abc)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    ins = [(pin(x0), pin(uold), pin(abc)), (pin(x0[::-1]), pin(uold[::-1]), pin(abc[::-1]))]
-    outs = [{k: pin(v) for k, v in s.alloc_outputs(False).items()} for _ in range(2)]
+    tpin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    lpin = lambda a: nat.pinned_like(np.ascontiguousarray(a))
+    perm = [np.arange(B), np.arange(B)[::-1], np.roll(np.arange(B), 7), np.roll(np.arange(B), 100)[::-1]]
+    pins = [tpin, lpin, lpin, tpin]
+    ins = [(pins[i](x0[perm[i]]), pins[i](uold[perm[i]]), pins[i](abc[perm[i]])) for i in range(4)]
+    outs = [{k: pins[i](v) for k, v in s.alloc_outputs(False).items()} for i in range(4)]
+    assert all(np.array_equal(ins[1][j], (x0, uold, abc)[j][perm[1]]) for j in range(3))       # the pinned copies hold the data
     for rep in range(3):
-        for slot in (0, 1):
+        for slot in range(4):
             if rep:
                 s.wait(slot)
             s.solve_async(slot, *ins[slot], outs[slot])
-    s.wait(0); s.wait(1)
-    for k in ("xPred", "uPred", "slack", "status", "iters", "resid"):
-        assert np.array_equal(outs[0][k], ref[k]), k
-        assert np.array_equal(outs[1][k], ref[k][::-1]), k
+    for slot in range(4):
+        s.wait(slot)
+    for i in range(4):
+        for k in ("xPred", "uPred", "slack", "status", "iters", "resid"):
+            assert np.array_equal(outs[i][k], ref[k][perm[i]]), (i, k)
     with pytest.raises(ValueError):
         s.solve_async(0, x0[::2], uold, abc, outs[0])          # non-contiguous view: refused, not silently copied
+    with pytest.raises(nat.NativeError):
+        s.solve_async(4, *ins[0], outs[0])                     # only four buffer sets
     s.close()
+    # the allocator's blocks: zero-filled, writable, freed with the last view
+    a = nat.pinned_empty((3, 5), np.float64)
+    assert a.shape == (3, 5) and not a.any() and a.flags.c_contiguous and a.flags.writeable
+    a[...] = 1.5
+    v = a[1]
+    del a
+    assert v.sum() == 7.5
+    assert len(nat.page_nodes(v, 1)) == 1
