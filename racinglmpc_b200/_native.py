@@ -67,6 +67,7 @@ def lib():
     L.lmpc_solve_mpc_host_async.argtypes = [_vp, C.c_int, _vp, _vp, _vp, ll, ll, _vp, _vp, _vp, _vp, _vp, _vp]
     L.lmpc_solve_lmpc_host_async.argtypes = [_vp, C.c_int, _vp, _vp, _vp, ll, ll] + [_vp] * 14
     L.lmpc_host_wait.argtypes = [_vp, C.c_int]
+    L.lmpc_host_chunks.argtypes = [_vp, C.c_int]
     ip = C.POINTER(C.c_int)
     L.lmpc_store_create.argtypes = [_vp, C.POINTER(ModelParams), C.c_int, C.c_int, C.c_int]
     L.lmpc_model_put_lap.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]

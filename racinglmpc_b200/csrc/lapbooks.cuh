@@ -136,7 +136,7 @@ __device__ inline int book_refresh(const LapBooks& k, int b) {
 __device__ inline void copy_lap_block(const LapPool& pool, size_t lap, const double* cx, const double* cu, int T) {
     for (int e = threadIdx.x; e < T * 6; e += blockDim.x) pool.x[lap * pool.Tmax * 6 + e] = cx[e];
     for (int e = threadIdx.x; e < T * 2; e += blockDim.x) pool.u[lap * pool.Tmax * 2 + e] = cu[e];
-    if (threadIdx.x == 0) { pool.len[lap] = T; pool.mark(lap); }
+    if (threadIdx.x == 0) pool.len[lap] = T;
 }
 
 // Lap hand-over of every controller whose lap just ended (done[b] != 0), bookkeeping included: main.py:113-119
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) pool_import_kernel(int batch, LapPool ss,
                 if (j < 6) model.x[(lap * model.Tmax + t) * 6 + j] = v;
                 else model.u[(lap * model.Tmax + t) * 2 + (j - 6)] = v;
             }
-            if (threadIdx.x == 0) { model.len[lap] = Tm; model.mark(lap); }
+            if (threadIdx.x == 0) model.len[lap] = Tm;
         }
         __syncthreads();
         if (threadIdx.x == 0 && c_ss == -2 && flags_or) flags_or[b] |= 64;

@@ -211,6 +211,8 @@ struct lmpc_handle {
     cudaStream_t stream;
     cudaStream_t cstream[4 * LMPC_HOST_SLOTS];   // chunk pipelines of the *_host entry points (H2D | kernel | D2H overlap), 4 streams per slot
     int hb_chunks[LMPC_HOST_SLOTS];
+    bool hb_pending[LMPC_HOST_SLOTS];            // enqueued and not yet waited for
+    bool hb_lone;                                // set by the synchronous entry points: the batch being enqueued runs alone
     // pipelined device-resident step: the batch is cut into step_split instance ranges, each running its kernel sequence on its
     // own stream (cstream[0..3]) between a fork and a join event on `stream`
     int step_split;
@@ -358,7 +360,6 @@ static void free_null(T*& p) { if (p) cudaFree(p); p = nullptr; }
 static void free_store(lmpc_handle* h) {
     free_null(h->ss.x); free_null(h->ss.u); free_null(h->ss.q); free_null(h->ss.len);
     free_null(h->mdl.x); free_null(h->mdl.u); free_null(h->mdl.len);
-    free_null(h->mdl.f4); free_null(h->mdl.f1); free_null(h->mdl.stale);
     free_null(h->d_used); free_null(h->d_sel); free_null(h->d_isprev); free_null(h->d_prevslot); free_null(h->d_timeStep);
     free_null(h->d_hasPred); free_null(h->d_flags); free_null(h->d_minidx); free_null(h->d_xLin); free_null(h->d_uLin);
     free_null(h->d_ztState); free_null(h->d_ztFixed); free_null(h->d_OldInput); free_null(h->d_xPredPrev); free_null(h->d_tmpx);
@@ -669,7 +670,14 @@ static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, c
     }
     // Chunk pipeline: the batch is cut into up to four instance ranges, each on its own stream, so that the H2D copy
     // of range i+1, the solve of range i and the D2H copy of range i-1 overlap (PCIe is full duplex).
-    int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    // A batch enqueued through the asynchronous entry points shares the device with the batches of the other buffer sets: that
+    // overlap is already there, every further piece is ten more driver calls on the enqueueing thread and one more under-filled
+    // last wave.  Measured on configs[1] (4096 QPs, three sets in flight, tools/e2e_probe.py): 9.2-9.6 M solves/s in one or two
+    // pieces, 8.3-8.6 M in four; a lone synchronous batch: 3.1 M uncut, 3.7 M in two, 3.9 M in four.
+    bool others = false;
+    for (int sl = 0; sl < LMPC_HOST_SLOTS; ++sl) others |= (sl != slot && h->hb_pending[sl]);
+    const bool lone = h->hb_lone && !others;
+    int nchunk = B >= 2048 ? (lone ? 4 : 2) : (B >= 512 ? 2 : 1);
     if (const char* e = getenv("LMPC_B200_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 4 && (size_t)v <= B) nchunk = v; }   // tuning knob
     const bool trace = slot == 0 && getenv("LMPC_B200_TRACE") != nullptr;
     if (trace) {
@@ -722,6 +730,7 @@ static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, c
         if (trace) cudaEventRecord(h->tev[ci][2], s);
     }
     h->hb_chunks[slot] = nchunk;
+    h->hb_pending[slot] = true;
     return LMPC_OK;
 }
 
@@ -744,11 +753,18 @@ static int enqueue_host_solve(lmpc_handle* h, int slot, const double* x0, const 
 }
 
 
+/* Instance ranges the most recent enqueue on `slot` was cut into (diagnostics of the chunk policy); -1 on a bad argument. */
+int lmpc_host_chunks(lmpc_handle* h, int slot) {
+    if (!h || slot < 0 || slot >= LMPC_HOST_SLOTS) return -1;
+    return h->hb_chunks[slot];
+}
+
 int lmpc_host_wait(lmpc_handle* h, int slot) {
     if (!h || slot < 0 || slot >= LMPC_HOST_SLOTS) return fail(LMPC_E_INVALID, "bad handle or slot");
     CK(cudaSetDevice(h->device));
     const int nchunk = h->hb_chunks[slot] > 0 ? h->hb_chunks[slot] : 4;
     for (int ci = 0; ci < nchunk; ++ci) CK(cudaStreamSynchronize(h->cstream[4 * slot + ci]));
+    h->hb_pending[slot] = false;
     if (slot == 0 && h->trace_on) {
         for (int i = 0; i < nchunk; ++i) {
             float a_ = 0, b_ = 0, c_ = 0;
@@ -781,8 +797,10 @@ int lmpc_solve_lmpc_host(lmpc_handle* h, const double* x0, const double* uOld, c
                          long long abc_stage_stride, const double* SS_sel, const double* Qfun_sel, const double* Succ_SS,
                          const double* Succ_uSS, double* xPred, double* uPred, double* slack, double* lambd,
                          double* slackTerminal, double* zt, double* zt_u, int* status, int* iters, double* resid) {
+    if (h) h->hb_lone = true;
     int rc = enqueue_host_solve(h, 0, x0, uOld, abc, abc_inst_stride, abc_stage_stride, SS_sel, Qfun_sel, Succ_SS, Succ_uSS, xPred, uPred,
                                 slack, lambd, slackTerminal, zt, zt_u, status, iters, resid);
+    if (h) h->hb_lone = false;
     if (rc) return rc;
     return lmpc_host_wait(h, 0);
 }
@@ -838,8 +856,6 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     DA(h->ss.len, int, B * h->ss.cap);
     DA(h->mdl.x, double, B * model_cap * Tmax * 6); DA(h->mdl.u, double, B * model_cap * Tmax * 2); h->mdl.q = nullptr;
     DA(h->mdl.len, int, B * model_cap);
-    DA(h->mdl.f4, float4, B * model_cap * Tmax); DA(h->mdl.f1, float, B * model_cap * Tmax); DA(h->mdl.stale, int, B * model_cap);
-    h->ss.f4 = nullptr; h->ss.f1 = nullptr; h->ss.stale = nullptr;
     DA(h->d_used, int, B * K1_MAXLAPS); DA(h->d_sel, int, B * 8); DA(h->d_isprev, int, B * 8); DA(h->d_prevslot, int, B);
     DA(h->d_timeStep, int, B); DA(h->d_hasPred, int, B); DA(h->d_flags, int, B); DA(h->d_minidx, int, B * 8);
     DA(h->d_xLin, double, B * (N + 1) * 6); DA(h->d_uLin, double, B * N * 2); DA(h->d_ztState, double, B * 6);
@@ -876,7 +892,6 @@ static int store_create_impl(lmpc_handle* h, const lmpc_model_params* mp, int ss
     }
     CK(cudaMemsetAsync(h->ss.len, 0, sizeof(int) * B * h->ss.cap, h->stream));
     CK(cudaMemsetAsync(h->mdl.len, 0, sizeof(int) * B * model_cap, h->stream));
-    CK(cudaMemsetAsync(h->mdl.stale, 0, sizeof(int) * B * model_cap, h->stream));
     CK(cudaMemsetAsync(h->d_used, 0, sizeof(int) * B * K1_MAXLAPS, h->stream));
     CK(cudaMemsetAsync(h->d_sel, 0, sizeof(int) * B * 8, h->stream));
     CK(cudaMemsetAsync(h->d_isprev, 0, sizeof(int) * B * 8, h->stream));
@@ -907,7 +922,6 @@ static int put_lap(lmpc_handle* h, LapPool& pool, int inst, int slot, int T, con
     CK(cudaMemcpyAsync(pool.x + lap * pool.Tmax * 6, x, sizeof(double) * T * 6, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(pool.u + lap * pool.Tmax * 2, u, sizeof(double) * T * 2, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(pool.len + lap, &T, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if (pool.stale) CK(cudaMemsetAsync(pool.stale + lap, 1, sizeof(int), h->stream));   // the fp32 shadow of this lap is out of date
     CK(cudaStreamSynchronize(h->stream));   // T lives on the caller's stack
     return LMPC_OK;
 }
@@ -1007,11 +1021,9 @@ int lmpc_ss_patch_row(lmpc_handle* h, int inst, int slot, int row, const double*
         return fail(LMPC_E_INVALID, "bad patch arguments");
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->ss.x + (h->ss.lap_index(inst, slot) * h->ss.Tmax + row) * 6, x6, sizeof(double) * 6, cudaMemcpyHostToDevice, h->stream));
-    if (also_model_slot >= 0 && also_model_slot < h->mdl.cap) {
+    if (also_model_slot >= 0 && also_model_slot < h->mdl.cap)
         CK(cudaMemcpyAsync(h->mdl.x + (h->mdl.lap_index(inst, also_model_slot) * h->mdl.Tmax + row) * 6, x6, sizeof(double) * 6,
                            cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemsetAsync(h->mdl.stale + h->mdl.lap_index(inst, also_model_slot), 1, sizeof(int), h->stream));
-    }
     CK(cudaStreamSynchronize(h->stream));
     return LMPC_OK;
 }
@@ -1058,14 +1070,11 @@ static int launch_k1(lmpc_handle* h, int b0 = 0, int nb = -1, cudaStream_t st = 
     a.wpb = h->N < 12 ? h->N : 12;
     a.pts_stride = k1_pts_stride(h->mc.trToUse);
     a.xLin = h->d_xLin; a.uLin = h->d_uLin; a.pool = h->mdl; a.used = h->d_used; a.abc = h->d_abc; a.status = h->d_flags;
-    // laps written since the last scan get their fp32 feature rows first (one warp per lap slot, a flag test when nothing changed)
-    model_shadow_refresh_kernel<<<(nb * h->mdl.cap + 7) / 8, 256, 0, st>>>(h->mdl, b0 * h->mdl.cap, (b0 + nb) * h->mdl.cap);
-    CK(cudaGetLastError());
     dim3 grid(nb, (h->N + a.wpb - 1) / a.wpb);
-    size_t smem = sizeof(float) * 5 * 2 * K1_TILE + sizeof(double) * (size_t)a.pts_stride * a.wpb;
+    size_t smem = sizeof(float) * 5 * K1_TILE + sizeof(double) * (size_t)a.pts_stride * a.wpb;
     knn_ltv_regress_kernel<<<grid, 32 * a.wpb, smem, st>>>(h->mc, a);
     CK(cudaGetLastError());
-    h->launches += 2;
+    h->launches += 1;
     return LMPC_OK;
 }
 

@@ -31,15 +31,7 @@ struct LapPool {
     double* q;      // [B][cap][Tmax]   (nullptr for the model pool)
     int* len;       // [B][cap]
     int cap, Tmax;
-    // fp32 shadow of the five regression features (model pool only, else nullptr): what the k-NN scan of K1 streams -- 20 B per
-    // row instead of 64 B, loadable into shared memory by asynchronous copies without a conversion pass.  Every writer of a model
-    // lap marks it stale; model_shadow_refresh_kernel converts stale laps before the next scan.  The fp64 rows stay the truth:
-    // exact distances, regression features and targets are read from them.
-    float4* f4;     // [B][cap][Tmax] (vx, vy, wz, delta)
-    float* f1;      // [B][cap][Tmax] a
-    int* stale;     // [B][cap]
     __host__ __device__ size_t lap_index(int b, int slot) const { return (size_t)b * cap + slot; }
-    __device__ void mark(size_t lap) const { if (stale) stale[lap] = 1; }
 };
 
 // Track.py:292-310 — wrap by repeated subtraction, first segment with s in [s0, s0+len)
@@ -117,9 +109,9 @@ __device__ __forceinline__ bool solve5(double (&A)[5][5], double (&b)[NR][5]) {
 constexpr int K1_MAXPTS = 7;     // MaxNumPoint supported by the register top-k
 constexpr int K1_MAXLAPS = 8;    // trToUse supported
 #ifndef LMPC_K1_TILE
-#define LMPC_K1_TILE 288
+#define LMPC_K1_TILE 512
 #endif
-constexpr int K1_TILE = LMPC_K1_TILE;     // lap rows staged in shared memory per pass (fp32 features); two such buffers per CTA
+constexpr int K1_TILE = LMPC_K1_TILE;     // lap rows staged in shared memory per pass (fp32 features)
 constexpr int K1_LOCAL = 3;      // entries of the lane-local candidate list
 constexpr int K1_CAND = 32;      // exact re-scoring buffer per warp
 constexpr unsigned K1_JBITS = 7; // low mantissa bits of a scan key that hold the lane's row counter: laps of up to 32 * 128 rows
@@ -158,43 +150,9 @@ __device__ __noinline__ double k1_exact_dist(const ModelConst& m, const double* 
     return d;
 }
 
-// The fp32 shadow of the model pool (LapPool::f4 / f1): one warp per lap slot of the range [lap0, lap1); a slot whose stale flag is
-// clear costs one load.  (float)x is the conversion the scan's rounding margin is derived for.
-__global__ void __launch_bounds__(256) model_shadow_refresh_kernel(LapPool pool, int lap0, int lap1) {
-    const int lap = lap0 + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (lap >= lap1 || !pool.stale || pool.stale[lap] == 0) return;
-    const int T = min(pool.len[lap], pool.Tmax);
-    const double* X = pool.x + (size_t)lap * pool.Tmax * 6;
-    const double* U = pool.u + (size_t)lap * pool.Tmax * 2;
-    float4* F4 = pool.f4 + (size_t)lap * pool.Tmax;
-    float* F1 = pool.f1 + (size_t)lap * pool.Tmax;
-    for (int r = lane; r < T; r += 32) {
-        const double2 v01 = *reinterpret_cast<const double2*>(X + (size_t)r * 6);
-        const double v2 = X[(size_t)r * 6 + 2];
-        const double2 uu = *reinterpret_cast<const double2*>(U + (size_t)r * 2);
-        F4[r] = make_float4((float)v01.x, (float)v01.y, (float)v2, (float)uu.x);
-        F1[r] = (float)uu.y;
-    }
-    __syncwarp();
-    if (lane == 0) pool.stale[lap] = 0;
-}
-
-// 16- and 4-byte asynchronous global -> shared copies (LDGSTS): the tile loads of K1 need no registers and no conversion
-__device__ __forceinline__ void k1_cp16(void* dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void k1_cp4(void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void k1_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPEND>
-__device__ __forceinline__ void k1_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
-
 // grid = (B, ceil(N / wpb)); one warp per horizon step (= query point).  Per stored lap:
-//   1. the CTA stages the lap's five regression features -- fp32, from the pool's shadow rows -- in shared memory (tiles of K1_TILE
-//      rows, padded to whole batches of 32 with far-away rows; asynchronous copies, the next tile of the instance's laps in flight
-//      while the current one is scanned) and every warp scans the tile for its own query with an fp32 distance -- ten full-rate
+//   1. the CTA stages the lap's five regression features as fp32 in shared memory (tiles of K1_TILE rows, padded to whole
+//      batches of 32 with far-away rows) and every warp scans the tile for its own query with an fp32 distance -- ten full-rate
 //      instructions per row instead of fourteen half-rate fp64 ones.  Each lane keeps its K1_LOCAL smallest rows as packed keys
 //      (distance bits | row counter) maintained by five integer min / max: the loop has no branch;
 //   2. G = the k-th smallest lane minimum bounds the k-th smallest distance from above; every listed row with a key within the
@@ -221,9 +179,9 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
     const int lane = threadIdx.x & 31;
     const int nthr = blockDim.x;
     const bool active = (i < a.N);            // all warps take part in the tile loads
-    float4* tile4 = reinterpret_cast<float4*>(k1_smem);                // [2][K1_TILE] : (vx, vy, wz, delta) of a row, one 16-byte load
-    float* tile1 = reinterpret_cast<float*>(k1_smem) + 4 * 2 * K1_TILE;   // [2][K1_TILE] : a
-    double* wbase = reinterpret_cast<double*>(k1_smem + sizeof(float) * 5 * 2 * K1_TILE) + (size_t)wib * a.pts_stride;
+    float4* tile4 = reinterpret_cast<float4*>(k1_smem);                // [K1_TILE] : (vx, vy, wz, delta) of a row, one 16-byte load
+    float* tile1 = reinterpret_cast<float*>(k1_smem) + 4 * K1_TILE;    // [K1_TILE] : a
+    double* wbase = reinterpret_cast<double*>(k1_smem + sizeof(float) * 5 * K1_TILE) + (size_t)wib * a.pts_stride;
     double* pts = wbase;                                               // this warp's scratch
     const int np_max = K1_MAXPTS * m.trToUse;
     double* ne = pts + (size_t)np_max * K1_PW;                         // 48
@@ -245,43 +203,6 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
     const double rh = fast_rcp(m.h);
     int flags = 0, npts = 0;
 
-    // Tile pipeline over the instance's (lap, tile) items: `issue` starts the asynchronous copy of one tile of shadow rows into
-    // buffer `buf` (and pads the last batch of 32 with far-away rows: the scan has no bounds test); item i + 1 is in flight while
-    // item i is scanned.
-    auto issue = [&](int c, int t0, int buf) {
-        const int slot = a.used[(size_t)b * m.trToUse + c];
-        const size_t lap = a.pool.lap_index(b, slot);
-        const int rows = min(K1_TILE, a.pool.len[lap] - 1 - t0);   // rows 0..T-2 are candidates (PM.py:183)
-        const int rows32 = (rows + 31) & ~31;
-        const float4* F4 = a.pool.f4 + lap * a.pool.Tmax + t0;
-        const float* F1 = a.pool.f1 + lap * a.pool.Tmax + t0;
-        float4* d4 = tile4 + buf * K1_TILE;
-        float* d1 = tile1 + buf * K1_TILE;
-        for (int r = threadIdx.x; r < rows32; r += nthr) {
-            if (r < rows) {
-                k1_cp16(d4 + r, F4 + r);
-                k1_cp4(d1 + r, F1 + r);
-            } else {
-                d4[r] = make_float4(K1_FAR, K1_FAR, K1_FAR, K1_FAR);
-                d1[r] = K1_FAR;
-            }
-        }
-        k1_cp_commit();
-    };
-    // the item after (c, t0): next tile of the lap, else the first tile of the next lap with at least one candidate row
-    auto next_item = [&](int c, int t0, int Tc, int& cn, int& tn) {
-        if (t0 + K1_TILE < Tc - 1) { cn = c; tn = t0 + K1_TILE; return true; }
-        for (cn = c + 1; cn < m.trToUse; ++cn) {
-            const int sl = a.used[(size_t)b * m.trToUse + cn];
-            if (a.pool.len[a.pool.lap_index(b, sl)] - 1 > 0) { tn = 0; return true; }
-        }
-        return false;
-    };
-    int buf = 0;
-    {
-        int c0 = -1, t00 = 0;
-        if (next_item(-1, 0, 0, c0, t00)) issue(c0, t00, 0);      // (lap -1 has no rows: picks the first lap that has any)
-    }
     for (int c = 0; c < m.trToUse; ++c) {
         const int slot = a.used[(size_t)b * m.trToUse + c];
         const size_t lap = a.pool.lap_index(b, slot);
@@ -293,22 +214,28 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
         // their bit patterns, so three unsigned min / two max per row keep the list sorted -- no branch, no index registers.
         unsigned k0 = 0xffffffffu, k1 = 0xffffffffu, k2 = 0xffffffffu;
         for (int t0 = 0; t0 < T - 1; t0 += K1_TILE) {
-            const int rows = min(K1_TILE, T - 1 - t0);
-            const int rows32 = (rows + 31) & ~31;
-            k1_cp_wait<0>();                                 // this thread's copies of the current tile have landed ...
-            __syncthreads();                                 // ... everybody's have, and the other buffer is fully consumed
-            {
-                int cn, tn;
-                if (next_item(c, t0, T, cn, tn)) issue(cn, tn, buf ^ 1);
+            const int rows = min(K1_TILE, T - 1 - t0);      // rows 0..T-2 are candidates (PM.py:183)
+            const int rows32 = (rows + 31) & ~31;            // the last batch is padded with far-away rows: the scan has no bounds test
+            __syncthreads();                                 // previous tile fully consumed
+            for (int r = threadIdx.x; r < rows32; r += nthr) {          // one 48 B + one 16 B row per thread -> fp32
+                if (r < rows) {
+                    const double2 v01 = *reinterpret_cast<const double2*>(X + (size_t)(t0 + r) * 6);
+                    const double v2 = X[(size_t)(t0 + r) * 6 + 2];
+                    const double2 uu = *reinterpret_cast<const double2*>(U + (size_t)(t0 + r) * 2);
+                    tile4[r] = make_float4((float)v01.x, (float)v01.y, (float)v2, (float)uu.x);
+                    tile1[r] = (float)uu.y;
+                } else {
+                    tile4[r] = make_float4(K1_FAR, K1_FAR, K1_FAR, K1_FAR);
+                    tile1[r] = K1_FAR;
+                }
             }
+            __syncthreads();
             if (active) {
-                const float4* t4 = tile4 + buf * K1_TILE;
-                const float* t1 = tile1 + buf * K1_TILE;
                 unsigned j = (unsigned)(t0 >> 5);
-#pragma unroll 3
+#pragma unroll 4
                 for (int rb = 0; rb < rows32; rb += 32, ++j) {
-                    const float4 xv = t4[rb + lane];
-                    const float x4 = t1[rb + lane];
+                    const float4 xv = tile4[rb + lane];
+                    const float x4 = tile1[rb + lane];
                     float d = s0 * fabsf(xv.x - f0);
                     d = fmaf(s1, fabsf(xv.y - f1), d);
                     d = fmaf(s2, fabsf(xv.z - f2), d);
@@ -321,7 +248,6 @@ __global__ void __launch_bounds__(32 * 12, LMPC_K1_MINBLOCKS) knn_ltv_regress_ke
                     k2 = min(k2, a2);
                 }
             }
-            buf ^= 1;
         }
         if (!active) continue;
         // ---- G = an upper bound of the k-th smallest key: the k-th smallest of the 32 lane minima (k distinct rows are at or
@@ -667,7 +593,7 @@ __global__ void commit_lap_kernel(LapPool pool, int b, int slot, const double* c
     const size_t lap = pool.lap_index(b, slot);
     for (int e = threadIdx.x; e < T * 6; e += blockDim.x) pool.x[lap * pool.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
     for (int e = threadIdx.x; e < T * 2; e += blockDim.x) pool.u[lap * pool.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
-    if (threadIdx.x == 0) { pool.len[lap] = T; pool.mark(lap); }
+    if (threadIdx.x == 0) pool.len[lap] = T;
 }
 
 // Pack every instance's closed-loop record into rows[B][Tpad][8] = (x | u) + lens[B]: the send buffer of the per-lap
@@ -739,7 +665,7 @@ __global__ void ss_import_laps_kernel(int batch, LapPool ss, LapPool model, cons
             if (j < 6) model.x[(lap * model.Tmax + t) * 6 + j] = v;
             else model.u[(lap * model.Tmax + t) * 2 + (j - 6)] = v;
         }
-        if (threadIdx.x == 0) { model.len[lap] = Tm; model.mark(lap); }
+        if (threadIdx.x == 0) model.len[lap] = Tm;
     }
 }
 
@@ -804,7 +730,7 @@ __global__ void __launch_bounds__(256) commit_laps_kernel(int batch, LapPool ss,
         const size_t lap = model.lap_index(b, model_slot[b]);
         for (int e = threadIdx.x; e < T * 6; e += blockDim.x) model.x[lap * model.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
         for (int e = threadIdx.x; e < T * 2; e += blockDim.x) model.u[lap * model.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
-        if (threadIdx.x == 0) { model.len[lap] = T; model.mark(lap); }
+        if (threadIdx.x == 0) model.len[lap] = T;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1082,7 +1008,7 @@ __global__ void __launch_bounds__(256) seed_from_record_kernel(int batch, LapPoo
             const size_t lap = model.lap_index(b, model_slot0 + c);
             for (int e = threadIdx.x; e < T * 6; e += blockDim.x) model.x[lap * model.Tmax * 6 + e] = cl_x[(size_t)b * Tcl * 6 + e];
             for (int e = threadIdx.x; e < T * 2; e += blockDim.x) model.u[lap * model.Tmax * 2 + e] = cl_u[(size_t)b * Tcl * 2 + e];
-            if (threadIdx.x == 0) { model.len[lap] = T; model.mark(lap); }
+            if (threadIdx.x == 0) model.len[lap] = T;
         }
     }
     for (int e = threadIdx.x; e < (N + 1) * 6; e += blockDim.x) xLin[(size_t)b * (N + 1) * 6 + e] = cl_x[(size_t)b * Tcl * 6 + 6 + e];

@@ -84,7 +84,7 @@ def test_fused_lmpc_step_matches_reference(gold, track):
     c, x0 = _restore(gold, track, keys)
     l0 = c.kernel_launches
     o = c.step(x0)
-    assert c.kernel_launches - l0 == 5                       # shadow refresh + K1 (writes transposed records itself), K2, QP, shift
+    assert c.kernel_launches - l0 == 4                       # K1 (writes transposed records itself), K2, QP, shift
     assert np.all(o["status"] == 1) and np.all(o["flags"] == 0), (o["status"], o["flags"])
     st = c.get_state()
     for b, key in enumerate(keys):
@@ -568,7 +568,7 @@ def test_pipelined_step_is_bit_identical_to_the_single_launch_sequence(track, mo
         return o, r, st, n_step, n_roll
     o1, r1, s1, n1, m1 = run(1)
     o4, r4, s4, n4, m4 = run(4)
-    assert (n1, m1) == (5, 3 * 7) and (n4, m4) == (4 * 5, 3 * 4 * 7), (n1, m1, n4, m4)
+    assert (n1, m1) == (4, 3 * 6) and (n4, m4) == (4 * 4, 3 * 4 * 6), (n1, m1, n4, m4)
     assert np.all(o1["status"] == 1) and np.all(r1["status"] == 1)
     for k in o1:
         assert np.array_equal(o1[k], o4[k]), k
