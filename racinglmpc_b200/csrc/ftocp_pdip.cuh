@@ -51,6 +51,37 @@
 #define LMPC_PRAGMA(x) LMPC_PRAGMA_(x)
 #define LMPC_SWEEP_UNROLL LMPC_PRAGMA(unroll LMPC_SWEEP_UNROLL_N)
 
+// Algorithmic constants of the interior-point method's starting point and step rule.  Macros so that the 1-lane host emulation
+// (tests/support/host_core.cpp) can sweep them on the CPU; the expressions may use the horizon N and LMPC (= a safe set is present).
+// The MPC-type defaults are the result of such a sweep over the BASELINE workloads (4096 LTV-MPC QPs at N = 6 / 12 / 24 / 48;
+// DESIGN.md §2): mean iterations 7.84 / 8.60 / 8.96 / 10.96 with the round-1 constants (0.3, 1, 0.995, back-off 0.8) -> 6.11 / 6.99 /
+// 7.64 / 9.17, confirmed on the device.  LMPC-type QPs keep the
+// round-1 constants: on 953 closed-loop QPs the same change saves 2.6 % of the iterations, and on the device it made the kernel
+// 2.5 % slower and the Monte-Carlo rollouts less robust (12 instead of 2 unsolved steps in 5 M).
+//   LMPC_TUNE_S0        offset of the initial lane slacks above the violation: long roll-outs of the initial input guess start
+//                       farther from the lanes and want more room (N = 48: 18.9 iterations with 0.02, 9.4 with 0.5), short ones
+//                       converge faster from a tight start
+//   LMPC_TUNE_MU0SCALE  initial complementarity of the input bounds and the simplex relative to the mean lane-row product
+//   LMPC_TUNE_MUFLOOR   floor of those products
+//   LMPC_TUNE_STEP      fraction of the step to the boundary
+#ifndef LMPC_TUNE_S0
+#define LMPC_TUNE_S0 (LMPC ? 0.3 : (N <= 16 ? 0.1 : (N <= 24 ? 0.2 : 0.5)))
+#endif
+#ifndef LMPC_TUNE_MUFLOOR
+#define LMPC_TUNE_MUFLOOR 1e-3
+#endif
+#ifndef LMPC_TUNE_MU0SCALE
+#define LMPC_TUNE_MU0SCALE (LMPC ? 1.0 : 0.05)
+#endif
+#ifndef LMPC_TUNE_STEP
+#define LMPC_TUNE_STEP (LMPC ? 0.995 : 0.999)
+#endif
+#ifndef LMPC_TUNE_SIGMA
+#define LMPC_TUNE_SIGMA(s) ((s) * (s) * (s))      // Mehrotra's centring parameter from the affine complementarity ratio
+#endif
+#ifndef LMPC_TUNE_BACKOFF
+#define LMPC_TUNE_BACKOFF (LMPC ? 0.8 : 0.9)       // step reduction until the iterate is back inside the neighbourhood
+#endif
 namespace lmpc {
 
 // ------------------------------------------------------------------------------------------
@@ -241,7 +272,10 @@ struct Regs {
     double y1;
 };
 
-constexpr double CENTRALITY_GAMMA = 0.01;
+#ifndef LMPC_TUNE_GAMMA
+#define LMPC_TUNE_GAMMA 0.01
+#endif
+constexpr double CENTRALITY_GAMMA = LMPC_TUNE_GAMMA;
 constexpr int LATE_ACCEPT_IT = 20;
 constexpr int RECENTRE_AFTER = 3;   // step reductions before the corrector is replaced by a centring step
 
@@ -434,15 +468,15 @@ struct Pdip {
         FOR_SLOTS(r, row, R1) {
             int k = row / NCX, i = row % NCX;
             double fx = dot6(&c.Fx[i * 6], &w.x[k * 6]) - c.bx[i];
-            double s = fmax(fx, 0.0) + 0.3;
+            double s = fmax(fx, 0.0) + LMPC_TUNE_S0;
             double w1 = s - fx;
-            double mur = fmax((c.qs2 * s + c.ql) * (w1 * s) / (w1 + s), 1e-3);
+            double mur = fmax((c.qs2 * s + c.ql) * (w1 * s) / (w1 + s), LMPC_TUNE_MUFLOOR);
             g.s[r] = s;
             g.nu1[r] = mur / w1;
             g.nu3[r] = mur / s;
             mu_acc += mur;
         }
-        const double mu0 = fmax(wsum(mu_acc) / (double)R1, 1e-3);
+        const double mu0 = fmax(LMPC_TUNE_MU0SCALE * wsum(mu_acc) / (double)R1, LMPC_TUNE_MUFLOOR);
         FOR_SLOTS(r, row, R2) {
             int k = row / NCU, j = row % NCU;
             double w2 = c.bu[j] - (c.Fu[j * 2] * w.u[k * 2] + c.Fu[j * 2 + 1] * w.u[k * 2 + 1]);
@@ -1654,7 +1688,7 @@ LMPC_SWEEP_UNROLL
             }
             comp_aff = wsum(comp_aff);
             double sig = comp_aff * recip(comp);
-            sig = sig * sig * sig;
+            sig = LMPC_TUNE_SIGMA(sig);
             const double sm = sig * mu;
 
             // ---- corrector (pass 0), recentring (pass 1, rare) -----------------------------------------
@@ -1738,7 +1772,7 @@ LMPC_SWEEP_UNROLL
                     }
                 }
                 const double amax = wmin_nn(ratio_bound(rn, rd, 1e300));
-                al = fmin(1.0, 0.995 * amax);
+                al = fmin(1.0, LMPC_TUNE_STEP * amax);
                 if (!(al > 0.0) || !(al <= 1.0)) { bad_step = true; break; }
                 // Stay in a wide neighbourhood of the central path, min_i w_i nu_i >= gamma * mean: without it
                 // Mehrotra steps can 2-cycle against a blocking bound (seen on 3 of 4096 workload QPs).
@@ -1767,7 +1801,7 @@ LMPC_SWEEP_UNROLL
                     psum = wsum(psum);
                     if (pmin >= (CENTRALITY_GAMMA / n_ineq) * psum) { inside = true; break; }
                     if (pass == 0 && tries >= RECENTRE_AFTER) break;
-                    al *= 0.8;
+                    al *= LMPC_TUNE_BACKOFF;
                 }
                 if (inside) break;
             }

@@ -157,3 +157,19 @@ def test_lmpc_properties_on_perturbed_problems(gold, track):
         r = kkt.residuals(P, qq, Am, l, u, z, y)
         assert r["r_prim"] < 1e-6 and r["r_dual"] < 1e-6, r
     run()
+
+
+@pytest.mark.parametrize("N,cap_mean,cap_max", [(6, 6.4, 11), (12, 7.3, 16), (24, 8.0, 17), (48, 9.6, 20)])
+def test_iteration_budget_on_the_baseline_workloads(N, cap_mean, cap_max):
+    """The starting point / step rule constants (LMPC_TUNE_* in ftocp_pdip.cuh) were chosen by sweeping them through this
+    emulation on the BASELINE LTV-MPC workloads; this pins the result: every QP solved to the default tolerance, mean and
+    maximum interior-point iterations within the swept optimum's margin (round-1 constants: 7.84 / 8.60 / 8.96 / 10.96 mean)."""
+    B = 256
+    x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
+    c = hc.make_const(rp.mpc_params(N))
+    its = []
+    for b in range(B):
+        sol = hc.solve(c, N, abc[b], x0[b], uold[b])
+        assert sol["status"] == 1 and max(sol["r_prim"], sol["r_dual"]) <= 1.000001e-9 and sol["gap"] <= 1.000001e-11, (N, b)
+        its.append(sol["iters"])
+    assert np.mean(its) <= cap_mean and max(its) <= cap_max, (N, np.mean(its), max(its))
