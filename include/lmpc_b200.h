@@ -149,8 +149,9 @@ int lmpc_solve_lmpc_host_async(lmpc_handle* h, int slot, const double* x0, const
                                double* zt_u, int* status, int* iters, double* resid);
 int lmpc_host_wait(lmpc_handle* h, int slot);
 /* Instance ranges (1 .. 4, each on its own stream: H2D | solve | D2H overlap inside one batch) the most recent enqueue on `slot`
- * was cut into: 4 for a batch of >= 2048 QPs solved through the synchronous entry points, 2 through the asynchronous ones (the
- * overlap then comes from the batches of the other buffer sets, and fewer, larger pieces cost the enqueueing thread less).
+ * was cut into: 4 for a batch of >= 2048 QPs solved through the synchronous entry points; through the asynchronous ones 1 when
+ * another buffer set is in flight (the overlap then comes from the other batches, and fewer, larger pieces cost the enqueueing
+ * thread less), else 2.
  * Diagnostics; -1 on a bad argument. */
 int lmpc_host_chunks(lmpc_handle* h, int slot);
 int lmpc_solve_lmpc_dev(lmpc_handle* h, const double* x0, const double* uOld, const double* abc,

@@ -272,10 +272,12 @@ struct Regs {
     double y1;
 };
 
-#ifndef LMPC_TUNE_GAMMA
-#define LMPC_TUNE_GAMMA 0.01
+#if defined(LMPC_HOST_COUNT) && !defined(__CUDA_ARCH__)
+static long g_host_count[3];     // host emulation only (parameter sweeps): corrector passes, recentring passes, step reductions
 #endif
-constexpr double CENTRALITY_GAMMA = LMPC_TUNE_GAMMA;
+#ifndef LMPC_TUNE_GAMMA
+#define LMPC_TUNE_GAMMA (LMPC ? 0.01 : 0.003)   // width of the central-path neighbourhood: min_i w_i nu_i >= gamma * mean
+#endif
 constexpr int LATE_ACCEPT_IT = 20;
 constexpr int RECENTRE_AFTER = 3;   // step reductions before the corrector is replaced by a centring step
 
@@ -1701,6 +1703,9 @@ LMPC_SWEEP_UNROLL
             bool bad_step = false;
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
+#if defined(LMPC_HOST_COUNT) && !defined(__CUDA_ARCH__)
+                g_host_count[pass] += 1;                 // host emulation only: corrector / recentring passes of a sweep run
+#endif
                 const double tgt = pass ? mu : sm;      // complementarity target
                 const double so = pass ? 0.0 : 1.0;     // second-order (dw*dnu) term on/off
                 FOR_SLOTS(r, row, R1) {
@@ -1799,8 +1804,11 @@ LMPC_SWEEP_UNROLL
                     }
                     pmin = wmin(pmin);
                     psum = wsum(psum);
-                    if (pmin >= (CENTRALITY_GAMMA / n_ineq) * psum) { inside = true; break; }
+                    if (pmin >= (LMPC_TUNE_GAMMA / n_ineq) * psum) { inside = true; break; }
                     if (pass == 0 && tries >= RECENTRE_AFTER) break;
+#if defined(LMPC_HOST_COUNT) && !defined(__CUDA_ARCH__)
+                    g_host_count[2] += 1;                // step reductions
+#endif
                     al *= LMPC_TUNE_BACKOFF;
                 }
                 if (inside) break;

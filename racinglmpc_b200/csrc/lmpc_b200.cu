@@ -672,12 +672,12 @@ static int enqueue_host_solve_impl(lmpc_handle* h, int slot, const double* x0, c
     // of range i+1, the solve of range i and the D2H copy of range i-1 overlap (PCIe is full duplex).
     // A batch enqueued through the asynchronous entry points shares the device with the batches of the other buffer sets: that
     // overlap is already there, every further piece is ten more driver calls on the enqueueing thread and one more under-filled
-    // last wave.  Measured on configs[1] (4096 QPs, three sets in flight, tools/e2e_probe.py): 9.2-9.6 M solves/s in one or two
-    // pieces, 8.3-8.6 M in four; a lone synchronous batch: 3.1 M uncut, 3.7 M in two, 3.9 M in four.
+    // last wave.  Measured on configs[1] (4096 QPs, three sets in flight, tools/e2e_probe.py, two hosts): 8.8-9.6 M solves/s uncut,
+    // 8.7-9.6 M in two pieces, 8.2-8.6 M in four; a lone synchronous batch: 3.1 M uncut, 3.7 M in two, 3.9 M in four.
     bool others = false;
     for (int sl = 0; sl < LMPC_HOST_SLOTS; ++sl) others |= (sl != slot && h->hb_pending[sl]);
     const bool lone = h->hb_lone && !others;
-    int nchunk = B >= 2048 ? (lone ? 4 : 2) : (B >= 512 ? 2 : 1);
+    int nchunk = B >= 2048 ? (lone ? 4 : (others ? 1 : 2)) : (B >= 512 ? (others ? 1 : 2) : 1);
     if (const char* e = getenv("LMPC_B200_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 4 && (size_t)v <= B) nchunk = v; }   // tuning knob
     const bool trace = slot == 0 && getenv("LMPC_B200_TRACE") != nullptr;
     if (trace) {

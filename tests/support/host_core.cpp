@@ -38,4 +38,9 @@ extern "C" int host_core_solve(int N, int M, const FtocpConst* c, const double* 
 #undef CASE
     return -1;
 }
+#ifdef LMPC_HOST_COUNT
+extern "C" void host_core_counts(long* out3, int reset) {
+    for (int i = 0; i < 3; ++i) { out3[i] = lmpc::g_host_count[i]; if (reset) lmpc::g_host_count[i] = 0; }
+}
+#endif
 extern "C" int host_core_const_size() { return (int)sizeof(FtocpConst); }
