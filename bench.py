@@ -272,6 +272,22 @@ def _max_over_ranks(v, dev, world):
     return float(t.item())
 
 
+def _pinner(local):
+    """Host buffers of the end-to-end legs: the library's pinned allocator (lmpc_host_alloc); if the host refuses to register
+    memory (locked-memory limit), torch's pinned allocator -- still pinned, only slower for a single DMA stream."""
+    import torch
+    from racinglmpc_b200 import _native as nat
+
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        try:
+            return nat.pinned_like(a, device=local)
+        except nat.NativeError as e:
+            print("bench: lmpc_host_alloc failed (%s); using torch pinned memory" % e, file=sys.stderr)
+            return torch.from_numpy(a).pin_memory().numpy()
+    return pin
+
+
 def leg_config1(args, rank, world, local, dev):
     """configs[1]: device-timed value + end-to-end through the public host API."""
     import torch
@@ -334,7 +350,7 @@ def leg_config1(args, rank, world, local, dev):
     # D2H inside the timed region
     # pinned host buffers from the library's allocator: pages on the NUMA node of the GPU's PCIe link (lmpc_host_alloc)
     from racinglmpc_b200 import _native as nat
-    pin = lambda a: nat.pinned_like(np.ascontiguousarray(a), device=local)
+    pin = _pinner(local)
     h_x0, h_u, h_abc = pin(x0), pin(uold), pin(abc)
     nslot = max(1, min(4, int(os.environ.get("LMPC_B200_E2E_SLOTS", "3"))))   # batches in flight (measurement knob)
     outs = [{k: pin(v) for k, v in solver.alloc_outputs(False).items()} for _ in range(nslot)]
@@ -420,7 +436,7 @@ def leg_config2(args, rank, world, local, dev, steps=None, with_e2e=True):
     e2e = None
     if with_e2e:       # host x0 in, results out through the public API
         from racinglmpc_b200 import _native as nat
-        pin = lambda a: nat.pinned_like(np.ascontiguousarray(a), device=local)
+        pin = _pinner(local)
         h_x0 = pin(data["x0"])
         out = {k: pin(v) for k, v in c.alloc_step_outputs().items()}
         reset(); c.step(h_x0, out=out, want_ss=False)

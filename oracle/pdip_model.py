@@ -61,9 +61,19 @@ def from_params(p, A, B, C, x0, uOld, SS=None, Qfun=None, Qts=None):
                    p.Fu, np.squeeze(p.bu), A, B, C, x0, np.asarray(uOld, float).ravel(), SS, Qfun, Qts)
 
 
+def kernel_constants(N, lmpc):
+    """The LMPC_TUNE_* defaults of racinglmpc_b200/csrc/ftocp_pdip.cuh as keyword arguments of solve(): problems with a safe
+    set keep the round-1 values, MPC-type problems use the ones swept through the host emulation."""
+    if lmpc:
+        return dict(s0=0.3, mu0_scale=1.0, step=0.995, backoff=0.8, gamma=0.01)
+    return dict(s0=0.1 if N <= 16 else (0.2 if N <= 24 else 0.5), mu0_scale=0.05, step=0.999, backoff=0.9, gamma=0.003)
+
+
 def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_step=1e-7, eps_gap=None, mu0="auto", s0=0.3, gamma=0.01, warm=None, snap_mu=None,
-          warm_theta=0.5):
-    """Returns dict(x[N+1,n], u[N,d], s[N,ncx], lam[m], xi[n], iters, r_prim, r_dual, gap, status)."""
+          warm_theta=0.5, mu0_scale=1.0, step=0.995, backoff=0.8):
+    """Returns dict(x[N+1,n], u[N,d], s[N,ncx], lam[m], xi[n], iters, r_prim, r_dual, gap, status).
+    s0 / mu0_scale / step / backoff / gamma: starting point and step rule (defaults = the kernel's LMPC-type constants;
+    ``solve(qp, **kernel_constants(qp.N, qp.m > 0))`` follows the kernel for either problem type)."""
     N, n, d = qp.N, 6, 2
     Fx, bx, Fu, bu = qp.Fx, qp.bx, qp.Fu, qp.bu
     ncx, ncu, m = Fx.shape[0], Fu.shape[0], qp.m
@@ -110,7 +120,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_step=1e-7, eps_gap=None,
         # every other family is centred at the mean of those products
         mur = (2 * qp.qs_quad * s + qp.qs_lin) * (w1 * s) / (w1 + s)
         nu1, nu3 = mur / w1, mur / s
-        mu0 = max(float(np.mean(mur)), 1e-3)
+        mu0 = max(mu0_scale * float(np.mean(mur)), 1e-3)
         nu2 = mu0 / w2
     else:                                   # centred start: every complementarity product = mu0
         nu1, nu2, nu3 = mu0 / w1, mu0 / w2, mu0 / s
@@ -335,7 +345,7 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_step=1e-7, eps_gap=None,
         cc = solve_rhs(w1 * nu1 + aff["dw1"] * aff["dnu1"] - sm, w2 * nu2 + aff["dw2"] * aff["dnu2"] - sm,
                        s * nu3 + aff["ds"] * aff["dnu3"] - sm,
                        (lam * nu4 + aff["dlam"] * aff["dnu4"] - sm) if lmpc else None)
-        al = min(1.0, 0.995 * max_step(cc, 1e300))        # as the kernel: full step when the boundary is > 1/0.995 away
+        al = min(1.0, step * max_step(cc, 1e300))         # as the kernel: full step when the boundary is > 1/step away
         if gamma > 0.0:
             # stay in a wide neighbourhood of the central path: min_i w_i nu_i >= gamma * mu
             def prods(a):
@@ -352,19 +362,19 @@ def solve(qp, eps=1e-9, max_iter=60, verbose=False, eps_step=1e-7, eps_gap=None,
                     break
                 if RECENTER and tr >= RECENTER_AFTER:
                     break
-                al *= 0.8
+                al *= backoff
             if verbose and not ok_nb:
                 p0 = prods(0.0)
                 print("      neighbourhood backtracking failed: current min/mean %.3e, tries %d" % (p0.min() / p0.mean(), tr))
             if RECENTER and not ok_nb:
                 # pure centring step from the same factorisation: sigma = 1, no second-order term
                 cc = solve_rhs(w1 * nu1 - mu, w2 * nu2 - mu, s * nu3 - mu, (lam * nu4 - mu) if lmpc else None)
-                al = min(1.0, 0.995 * max_step(cc, 1e300))
+                al = min(1.0, step * max_step(cc, 1e300))
                 for tr in range(12):
                     pr = prods(al)
                     if pr.min() >= gamma * pr.mean():
                         break
-                    al *= 0.8
+                    al *= backoff
                 if verbose:
                     print("      recentring step alpha %.3f  -> min/mean %.3e" % (al, pr.min() / pr.mean()))
         if DEBUG_HOOK:

@@ -173,3 +173,19 @@ def test_iteration_budget_on_the_baseline_workloads(N, cap_mean, cap_max):
         assert sol["status"] == 1 and max(sol["r_prim"], sol["r_dual"]) <= 1.000001e-9 and sol["gap"] <= 1.000001e-11, (N, b)
         its.append(sol["iters"])
     assert np.mean(its) <= cap_mean and max(its) <= cap_max, (N, np.mean(its), max(its))
+
+
+@pytest.mark.parametrize("N,B", [(12, 16), (48, 3)])
+def test_numpy_spec_follows_the_kernel_with_its_constants(N, B):
+    """oracle/pdip_model.py is the executable specification of the kernel: with the kernel's constants
+    (pdip_model.kernel_constants) it takes the same number of iterations and lands on the same point as the compiled core."""
+    from oracle import pdip_model as pm
+    x0, uold, abc = workloads.ltv_mpc_batch(B, N=N)
+    p = rp.mpc_params(N)
+    c = hc.make_const(p)
+    for b in range(B):
+        A = abc[b][:, 0:36].reshape(N, 6, 6); Bm = abc[b][:, 36:48].reshape(N, 6, 2); C = abc[b][:, 48:54]
+        ref = pm.solve(pm.from_params(p, A, Bm, C, x0[b], uold[b]), eps=1e-9, eps_gap=1e-11, max_iter=40, **pm.kernel_constants(N, False))
+        sol = hc.solve(c, N, abc[b], x0[b], uold[b])
+        assert ref["status"] == 1 and sol["status"] == 1 and ref["iters"] == sol["iters"], (b, ref["iters"], sol["iters"])
+        assert np.max(np.abs(sol["x"] - ref["x"])) < 1e-10 and np.max(np.abs(sol["u"] - ref["u"])) < 1e-10
