@@ -1,3 +1,5 @@
+# Final evidence capture of a round on one gpurun B200 box: GPU tests, smoke, both bench arms, probes, ncu capture + launch list, sanitizer.
+# Usage: gpurun --timeout 2400 -- "bash tools/gpu_validate.sh"; results land in gpurun_out/ (copy what is to be judged into profiles/).
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
