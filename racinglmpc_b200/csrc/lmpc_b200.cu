@@ -420,10 +420,10 @@ int lmpc_device_count(void) {
     return n;
 }
 
-// ---- pinned host memory next to the GPU ----------------------------------------------------------------------------------
-// The `_host` entry points move 21.5 MB per configs[1] step over PCIe; on a two-socket host the link runs at full speed
-// only from the memory of the socket the GPU hangs off.  lmpc_host_alloc asks the kernel for pages on that NUMA node
-// (mbind on an anonymous mapping; raw syscalls, libnuma is not in the image) and pins them.
+// ---- pinned host memory for the `_host` entry points ----------------------------------------------------------------------
+// The `_host` entry points move 21.5 MB per configs[1] step over PCIe.  lmpc_host_alloc hands out blocks a single DMA stream
+// reads at link rate: an anonymous mapping in whole 2 MiB units (transparent huge pages), placed on the NUMA node the GPU hangs
+// off (mbind; raw syscalls, libnuma is not in the image), touched, then pinned with cudaHostRegister.
 static int gpu_numa_node(int device) {
     char bus[32] = {0};
     if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) return -1;
@@ -438,14 +438,15 @@ static int gpu_numa_node(int device) {
     return node;
 }
 int lmpc_host_numa_node(int device) {
-    const char* e = getenv("LMPC_B200_NUMA");      // 0 / off: plain pinned memory (A/B measurements); an integer >= 0 forces a node
+    const char* e = getenv("LMPC_B200_NUMA");      // "off" / "-1": no placement (A/B measurements); an integer >= 0 forces that node
     if (e && (!strcmp(e, "off") || !strcmp(e, "-1"))) return -1;
     if (e && isdigit((unsigned char)e[0]) && strcmp(e, "auto")) return atoi(e);
     return gpu_numa_node(device);
 }
-// Pages come from an anonymous mapping of this process bound to the node with mbind() and touched here, then pinned with
-// cudaHostRegister: cudaHostAlloc's pages are allocated inside the driver and were measured to ignore the caller's memory policy
-// (profiles/r2_numa_probe.json: all on node 0 with the GPU on node 1, single-stream H2D 23 instead of 52 GB/s).
+// Measured on the bench hosts (tools/numa_probe.py, profiles/r2h_numa_probe.json): one stream reads such a block at 55 GB/s from
+// either NUMA node, but cudaHostAlloc / torch.pin_memory() buffers -- whose pages the driver allocates, ignoring the caller's
+// memory policy -- at 19-29 GB/s (writes: 55 GB/s both ways).  The placement itself made no difference on these hosts; it is kept
+// because it costs nothing and two-socket hosts with a slower inter-socket link exist.
 static std::mutex g_host_mu;
 static std::map<void*, size_t> g_host_blocks;      // base -> mapped bytes
 int lmpc_host_alloc(int device, size_t bytes, void** out) {
