@@ -422,7 +422,7 @@ int lmpc_device_count(void) {
 
 // ---- pinned host memory for the `_host` entry points ----------------------------------------------------------------------
 // The `_host` entry points move 21.5 MB per configs[1] step over PCIe.  lmpc_host_alloc hands out blocks a single DMA stream
-// reads at link rate: an anonymous mapping in whole 2 MiB units (transparent huge pages), placed on the NUMA node the GPU hangs
+// reads at link rate: an anonymous mapping in whole 2 MiB units, placed on the NUMA node the GPU hangs
 // off (mbind; raw syscalls, libnuma is not in the image), touched, then pinned with cudaHostRegister.
 static int gpu_numa_node(int device) {
     char bus[32] = {0};
@@ -453,7 +453,7 @@ int lmpc_host_alloc(int device, size_t bytes, void** out) {
     if (!out || bytes == 0) return fail(LMPC_E_INVALID, "lmpc_host_alloc: null out or zero size");
     *out = nullptr;
     CK(cudaSetDevice(device));
-    const size_t gran = 2u << 20;                                   // whole 2 MiB units: eligible for transparent huge pages
+    const size_t gran = 2u << 20;                                   // whole 2 MiB units (huge-page sized; no madvise: the hosts measured run THP in madvise mode)
     const size_t len = (bytes + gran - 1) / gran * gran;
     void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED) return fail(LMPC_E_CUDA, "lmpc_host_alloc: mmap failed");
