@@ -453,7 +453,7 @@ int lmpc_host_alloc(int device, size_t bytes, void** out) {
     if (!out || bytes == 0) return fail(LMPC_E_INVALID, "lmpc_host_alloc: null out or zero size");
     *out = nullptr;
     CK(cudaSetDevice(device));
-    const size_t gran = 2u << 20;                                   // whole 2 MiB units (huge-page sized; no madvise: the hosts measured run THP in madvise mode)
+    const size_t gran = 2u << 20;                                   // whole 2 MiB units (huge-page sized; MADV_HUGEPAGE is not requested)
     const size_t len = (bytes + gran - 1) / gran * gran;
     void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED) return fail(LMPC_E_CUDA, "lmpc_host_alloc: mmap failed");
